@@ -1,0 +1,578 @@
+"""
+CPU ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product package
+(`cmblensing.jl_b200/`); only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` leg may import it, and there only as the checker /
+the CPU baseline.
+
+A NumPy/pocketfft restatement of the flat-sky hot path of marius311/CMBLensing.jl
+@ 8e75a7c (v0.10.1).  Every function cites the reference file:line it follows
+(paths relative to /root/reference).  The reference is pure Julia and Julia is not
+installed in this image, so the reference itself cannot be executed here.
+
+PARITY STATUS: **parity unpinned** beyond (a) the known-answer cases the reference's own
+tests hold for this path (test/runtests.jl:252-256,269-273 logdet/tr; 116-131 basis
+round trips; 259-283 logdet/tr vs dense fft) and (b) its property tests (adjoint identity
+:556,:570; finite-difference gradient :559,:573) — the reference ships no golden output
+vectors for LenseFlow / CG, and its FFT lives in un-vendored FFTW.jl 1.7.1 /
+FFTW_jll 3.3.10 / MKL_jll 2023.2 (docs/Manifest.toml).  The DFT definition, normalisation and
+half-plane layout are pinned by those tests; bit patterns are not.
+
+Array layout: Julia `arr[iy, ix, ipol, ibatch]` column-major == NumPy C-order
+`a[ibatch, ipol, ix, iy]` (iy fastest).  Map arrays: (Nb, Npol, Nx, Ny); Fourier arrays:
+(Nb, Npol, Nx, Ny//2+1) complex (the halved dimension is y, `plan_rfft(A,(1,2))`,
+src/util_fft.jl:32-35).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field as _dc_field
+
+import numpy as np
+import scipy.fft as sfft
+
+_WORKERS = int(os.environ.get("CMBL_ORACLE_WORKERS", "1"))
+
+
+def set_workers(n: int):
+    global _WORKERS
+    _WORKERS = max(1, int(n))
+
+
+# ----------------------------------------------------------------------------------------------
+# ProjLambert  (src/proj_lambert.jl:24-75)
+# ----------------------------------------------------------------------------------------------
+class ProjLambert:
+    """ℓ-grids and metadata of a flat-sky Lambert projection, computed in type T exactly in the
+    order of src/proj_lambert.jl:58-71 (Nyquist frequencies carry NEGATIVE ℓ, :63-64)."""
+
+    def __init__(self, Ny: int, Nx: int, theta_pix: float = 1.0, T=np.float64):
+        T = np.dtype(T).type
+        self.Ny, self.Nx, self.theta_pix, self.T = int(Ny), int(Nx), float(theta_pix), T
+        self.cT = np.complex64 if T is np.float32 else np.complex128
+        dx = T(np.deg2rad(self.theta_pix / 60.0))                    # :58
+        self.dx = dx
+        self.dlx = T(2 * np.pi / np.float64(T(Nx) * dx))             # :59  (2π is Float64 in Julia)
+        self.dly = T(2 * np.pi / np.float64(T(Ny) * dx))             # :60
+        self.nyquist = T(2 * np.pi / np.float64(T(2) * dx))          # :61
+        self.omega_pix = T(dx * dx)                                  # :62
+        ky = np.fft.ifftshift(np.arange(-(Ny // 2), (Ny - 1) // 2 + 1))
+        kx = np.fft.ifftshift(np.arange(-(Nx // 2), (Nx - 1) // 2 + 1))
+        self.ly = (ky.astype(T) * self.dly)[: Ny // 2 + 1].astype(T)  # :63  last entry = -(Ny/2)Δℓy
+        self.lx = (kx.astype(T) * self.dlx).astype(T)                 # :64
+        LX, LY = self.lx[:, None], self.ly[None, :]                   # [ix, iy]
+        self.lmag = np.sqrt(LX * LX + LY * LY).astype(T)              # :65
+        phi = np.arctan2(LY + 0 * LX, LX + 0 * LY).astype(T)          # :66 angle(ℓx' + im ℓy)
+        self.sin2phi = np.sin(T(2) * phi).astype(T)                   # :67
+        self.cos2phi = np.cos(T(2) * phi).astype(T)
+        self.lam_rfft = rfft_degeneracy_fac(Ny).astype(T)             # :68
+        if Ny % 2 == 0:                                               # :69-71 (1-based end:-1:Nx÷2+2 ← 2:Nx÷2)
+            self.sin2phi[Nx - 1: Nx // 2: -1, -1] = self.sin2phi[1: Nx // 2, -1]
+
+    @property
+    def map_shape(self):
+        return (self.Nx, self.Ny)
+
+    @property
+    def fourier_shape(self):
+        return (self.Nx, self.Ny // 2 + 1)
+
+
+def rfft_degeneracy_fac(n: int) -> np.ndarray:
+    """src/util_fft.jl:137-143"""
+    if n % 2 == 0:
+        return np.array([1.0] + [2.0] * (n // 2 - 1) + [1.0])
+    return np.array([1.0] + [2.0] * (n // 2))
+
+
+# ----------------------------------------------------------------------------------------------
+# FFT conventions (src/util_fft.jl:26-27,44 ; call sites src/proj_lambert.jl:245-300)
+# ----------------------------------------------------------------------------------------------
+def rfft2(a: np.ndarray) -> np.ndarray:
+    """m_rfft!(dst, arr, (1,2)): unnormalised batched 2-D R2C, halved dim = y (last NumPy axis)."""
+    return sfft.rfftn(a, axes=(-2, -1), workers=_WORKERS)
+
+
+def irfft2(F: np.ndarray, Ny: int) -> np.ndarray:
+    """m_irfft!(dst, arr, (1,2)) = ldiv!(dst, plan, arr): normalised 1/(Ny·Nx); complex IFFT along x
+    then c2r along y, which ignores Im of the ky=0 and ky=Ny/2 rows (FFTW/MKL/cuFFT/pocketfft)."""
+    Nx = F.shape[-2]
+    return sfft.irfftn(F, s=(Nx, Ny), axes=(-2, -1), workers=_WORKERS)
+
+
+# ----------------------------------------------------------------------------------------------
+# Derivative diagonals (src/specialops.jl:144-177 ; src/proj_lambert.jl:146-159)
+# ----------------------------------------------------------------------------------------------
+def grad_diag(proj: ProjLambert, coord: int, prefactor: int = 1) -> np.ndarray:
+    """∇diag(coord, ·, prefactor) materialised on the half-plane: (prefactor·im)·ℓx' or ·ℓy."""
+    if coord == 1:
+        return (prefactor * 1j * proj.lx[:, None]).astype(proj.cT)
+    return (prefactor * 1j * proj.ly[None, :]).astype(proj.cT)
+
+
+def gradhess(proj: ProjLambert, phi_four: np.ndarray):
+    """src/specialops.jl:184-188: g = ∇ⁱ f ; H = [∇₁g₁ ∇₂g₁; ∇₁g₂ ∇₂g₂], all in Fourier basis."""
+    d1, d2 = grad_diag(proj, 1), grad_diag(proj, 2)
+    g = (d1 * phi_four, d2 * phi_four)
+    H = ((d1 * g[0], d2 * g[0]), (d1 * g[1], d2 * g[1]))
+    return g, H
+
+
+# ----------------------------------------------------------------------------------------------
+# Basis rotations (src/proj_lambert.jl:253-271)
+# ----------------------------------------------------------------------------------------------
+def eb_to_qu(proj: ProjLambert, F: np.ndarray, pol0: int = 0) -> np.ndarray:
+    """QUFourier(f::LambertEBFourier) :253-258 on components (pol0, pol0+1)."""
+    out = F.copy()
+    E, B = F[:, pol0], F[:, pol0 + 1]
+    c, s = proj.cos2phi, proj.sin2phi
+    out[:, pol0] = -E * c + B * s
+    out[:, pol0 + 1] = -E * s - B * c
+    return out
+
+
+def qu_to_eb(proj: ProjLambert, F: np.ndarray, pol0: int = 0) -> np.ndarray:
+    """EBFourier(f::LambertQUFourier) :265-271."""
+    out = F.copy()
+    Q, U = F[:, pol0], F[:, pol0 + 1]
+    c, s = proj.cos2phi, proj.sin2phi
+    out[:, pol0] = -Q * c - U * s
+    out[:, pol0 + 1] = Q * s - U * c
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# DiagOp (src/specialops.jl:9-10,18) and nan2zero (src/util.jl:32)
+# ----------------------------------------------------------------------------------------------
+def nan2zero(x: np.ndarray) -> np.ndarray:
+    return np.where(np.isfinite(x), x, np.zeros((), dtype=x.dtype))
+
+
+def pinv_diag(d: np.ndarray) -> np.ndarray:
+    """pinv(D::DiagOp) = Diagonal(pinv.(diag(D))): scalar pinv, 0 → 0."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(d == 0, np.zeros((), dtype=d.dtype), 1 / d)
+    return r.astype(d.dtype)
+
+
+def diag_mul(d: np.ndarray, f: np.ndarray) -> np.ndarray:
+    return d * f
+
+
+def diag_ldiv(d: np.ndarray, f: np.ndarray) -> np.ndarray:
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return nan2zero(f / d).astype(f.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# dot / logdet / tr (src/proj_lambert.jl:318-353)
+# ----------------------------------------------------------------------------------------------
+def dot_map(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """:318-321  per-batch Σ a·b (BatchedReal)."""
+    z = (a * b).astype(np.float64)
+    return z.reshape(z.shape[0], -1).sum(axis=1)
+
+
+def dot_fourier(proj: ProjLambert, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """:322-325  per-batch Σ Re(conj(a)·b)·λ_rfft / (Ny·Nx)."""
+    z = np.real(np.conj(a) * b).astype(np.float64) * proj.lam_rfft.astype(np.float64)
+    return z.reshape(z.shape[0], -1).sum(axis=1) / (proj.Ny * proj.Nx)
+
+
+def logdet_fourier(proj: ProjLambert, d: np.ndarray) -> np.ndarray:
+    """:331-336"""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = nan2zero(np.log(np.abs(d)) * proj.lam_rfft)
+    return np.real(z.reshape(z.shape[0], -1).sum(axis=1))
+
+
+def logdet_map(d: np.ndarray) -> np.ndarray:
+    """:337-342"""
+    n = d.shape[0]
+    flat = d.reshape(n, -1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.log(np.abs(flat)).sum(axis=1) + np.log(np.prod(np.sign(flat), axis=1))
+
+
+def tr_fourier(proj: ProjLambert, d: np.ndarray) -> np.ndarray:
+    """:346-350"""
+    z = d * proj.lam_rfft
+    return np.real(z.reshape(z.shape[0], -1).sum(axis=1))
+
+
+def tr_map(d: np.ndarray) -> np.ndarray:
+    return d.reshape(d.shape[0], -1).sum(axis=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# Cℓ → 2-D (src/numerical_algorithms.jl:148-177, src/cls.jl:9-30, src/proj_lambert.jl:173-175,361-371)
+# ----------------------------------------------------------------------------------------------
+def linear_interp_nan(xdat: np.ndarray, ydat: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """LinearInterpolation(xdat, ydat; extrapolation_bc=NaN)."""
+    x = np.asarray(x, dtype=np.float64)
+    out = np.interp(x, xdat, ydat)
+    out = np.where((x < xdat[0]) | (x > xdat[-1]), np.nan, out)
+    return out
+
+
+def cl_to_2d(proj: ProjLambert, ell: np.ndarray, cl: np.ndarray) -> np.ndarray:
+    """Cℓ_to_2D: T.(nan2zero.(Cℓ(ℓmag)))."""
+    v = linear_interp_nan(np.asarray(ell, dtype=np.float64), np.asarray(cl, dtype=np.float64), proj.lmag)
+    return nan2zero(v).astype(proj.T)
+
+
+def cl_to_cov(proj: ProjLambert, ell, cl, units=None) -> np.ndarray:
+    """Cℓ_to_Cov(:I, ...) : Cℓ_to_2D / units, default units = Ωpix (:361-364)."""
+    units = proj.omega_pix if units is None else proj.T(units)
+    return (cl_to_2d(proj, ell, cl) / units).astype(proj.T)
+
+
+def noise_cls(ell: np.ndarray, muK_arcmin_T: float = 3.0, lknee: float = 100.0, aknee: float = 3.0, pol: bool = False):
+    """noiseCℓs (src/cls.jl:288-299) with beamFWHM=0 (Bℓ≡1): white + 1/f; ×2 for EE/BB."""
+    ell = np.asarray(ell, dtype=np.float64)
+    n1f = 1.0 + (lknee / ell) ** aknee
+    return (2.0 if pol else 1.0) * np.deg2rad(muK_arcmin_T / 60.0) ** 2 * n1f
+
+
+def beam_cls(ell: np.ndarray, fwhm_arcmin: float):
+    """beamCℓs (src/cls.jl:307-309)."""
+    ell = np.asarray(ell, dtype=np.float64)
+    return np.exp(-ell ** 2 * np.deg2rad(fwhm_arcmin / 60.0) ** 2 / (8 * np.log(2)))
+
+
+def lowpass_wl(lmax: int, dl: int = 50):
+    """LowPass(ℓ; Δℓ=50) = BandPassOp(0:ℓ, [ones(ℓ-Δℓ+1); cos_ramp_down(Δℓ)]) (src/specialops.jl:236-241)."""
+    ramp_up = (np.cos(np.linspace(np.pi, 0, dl)) + 1) / 2
+    return np.arange(0, lmax + 1), np.concatenate([np.ones(lmax - dl + 1), 1 - ramp_up])
+
+
+# ----------------------------------------------------------------------------------------------
+# LenseFlow (src/lenseflow.jl, src/flowops.jl, src/field_vectors.jl, src/numerical_algorithms.jl)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class CachedLenseFlow:
+    """CachedLenseFlow (src/lenseflow.jl:33-60): p[τ], M⁻¹[τ] at the 2n+1 times k/(2n)."""
+    proj: ProjLambert
+    nsteps: int
+    p: list = _dc_field(default_factory=list)       # p[k] = (p1, p2) maps, shape (Nbϕ,1,Nx,Ny)
+    Minv: list = _dc_field(default_factory=list)    # Minv[k] = ((m11,m12),(m21,m22))
+    ts: list = _dc_field(default_factory=list)
+
+
+def precompute(proj: ProjLambert, phi, nsteps: int = 7, phi_is_fourier: bool = False) -> CachedLenseFlow:
+    """precompute! (src/lenseflow.jl:131-142); pinv! (src/field_vectors.jl:86-94, note a,c,b,d =
+    H11,H21,H21,H22: the off-diagonal is read twice from [2,1]); p = M⁻¹' ∇ϕ (:46-47)."""
+    T = proj.T
+    phi = np.asarray(phi)
+    if phi.ndim == 2:
+        phi = phi[None, None]
+    F = phi.astype(proj.cT) if phi_is_fourier else rfft2(phi.astype(T))
+    g, H = gradhess(proj, F)
+    g = [irfft2(x, proj.Ny).astype(T) for x in g]
+    H11, H21, H22 = (irfft2(H[0][0], proj.Ny).astype(T), irfft2(H[1][0], proj.Ny).astype(T),
+                     irfft2(H[1][1], proj.Ny).astype(T))
+    L = CachedLenseFlow(proj, nsteps)
+    for k in range(2 * nsteps + 1):
+        t = T(k / (2 * nsteps))
+        a = T(1) + t * H11
+        d = T(1) + t * H22
+        b = c = t * H21
+        det = a * d - b * c
+        idet = pinv_diag(det)
+        m11, m12, m21, m22 = idet * d, -idet * b, -idet * c, idet * a
+        p1 = m11 * g[0] + m21 * g[1]
+        p2 = m12 * g[0] + m22 * g[1]
+        L.ts.append(t)
+        L.p.append((p1.astype(T), p2.astype(T)))
+        L.Minv.append(((m11, m12), (m21, m22)))
+    return L
+
+
+def velocity(L: CachedLenseFlow, k: int, f: np.ndarray) -> np.ndarray:
+    """velocity → v! (src/lenseflow.jl:150-161): state in Map basis."""
+    proj = L.proj
+    p1, p2 = L.p[k]
+    F = rfft2(f)
+    dx = irfft2(grad_diag(proj, 1) * F, proj.Ny)
+    dy = irfft2(grad_diag(proj, 2) * F, proj.Ny)
+    return (p1 * dx + p2 * dy).astype(f.dtype)
+
+
+def velocity_H(L: CachedLenseFlow, k: int, F: np.ndarray) -> np.ndarray:
+    """velocityᴴ → v! (src/lenseflow.jl:163-174): state in Fourier basis."""
+    proj = L.proj
+    p1, p2 = L.p[k]
+    f = irfft2(F, proj.Ny)
+    return (grad_diag(proj, 1) * rfft2(p1 * f) + grad_diag(proj, 2) * rfft2(p2 * f)).astype(F.dtype)
+
+
+def neg_delta_velocity_H(L: CachedLenseFlow, k: int, state, bug_compat: bool = True):
+    """negδvelocityᴴ → v! (src/lenseflow.jl:176-214) on (f Map, δf Fourier, δϕ Fourier).
+    bug_compat=True reproduces the aliased in-place 2×2 product (:198-200 with
+    src/field_vectors.jl:48-49, both operands bound to L.memŁvϕ): m₂ uses the *new* m₁."""
+    proj = L.proj
+    f, df, dphi = state
+    t = L.ts[k]
+    p1, p2 = L.p[k]
+    (m11, m12), (m21, m22) = L.Minv[k]
+    d1, d2 = grad_diag(proj, 1), grad_diag(proj, 2)
+    Ldf = irfft2(df, proj.Ny)
+    ddf_dt = d1 * rfft2(p1 * Ldf) + d2 * rfft2(p2 * Ldf)
+    Ff = rfft2(f)
+    gx, gy = irfft2(d1 * Ff, proj.Ny), irfft2(d2 * Ff, proj.Ny)
+    df_dt = p1 * gx + p2 * gy
+    w1 = (Ldf * gx).sum(axis=1, keepdims=True)          # spin_adjoint(Łδf) * Ł∇f  (src/proj_lambert.jl:423-430)
+    w2 = (Ldf * gy).sum(axis=1, keepdims=True)
+    m1 = m11 * w1 + m12 * w2
+    m2 = (m21 * m1 + m22 * w2) if bug_compat else (m21 * w1 + m22 * w2)
+    ddphi_dt = d1 * rfft2(m1) + d2 * rfft2(m2)
+    nd = (-d1, -d2)                                     # ∇'  = conj → −iℓ
+    for i, mi in enumerate((m1, m2)):
+        for j, pj in enumerate((p1, p2)):
+            ddphi_dt = ddphi_dt + nd[i] * (nd[j] * rfft2(t * pj * mi))
+    return (df_dt.astype(f.dtype), ddf_dt.astype(df.dtype), ddphi_dt.astype(dphi.dtype))
+
+
+def _axpy(y, a, k):
+    if isinstance(y, tuple):
+        return tuple(_axpy(yi, a, ki) for yi, ki in zip(y, k))
+    return (y + y.real.dtype.type(a) * k).astype(y.dtype)
+
+
+def rk4(F, y0, k0: int, k1: int, nsteps: int):
+    """RK4Solver (src/numerical_algorithms.jl:11-24) on the stage grid k=0..2n (t=k/2n):
+    h=(t₁−t₀)/n; stages at k, k±1, k±1, k±2."""
+    sgn = 1 if k1 > k0 else -1
+    h = sgn / nsteps
+    y = y0
+    k = k0
+    for _ in range(nsteps):
+        a = F(k, y)
+        b = F(k + sgn, _axpy(y, h / 2, a))
+        c = F(k + sgn, _axpy(y, h / 2, b))
+        d = F(k + 2 * sgn, _axpy(y, h, c))
+        if isinstance(y, tuple):
+            y = tuple((yi + yi.real.dtype.type(h) * (ai + 2 * (bi + ci) + di) / 6).astype(yi.dtype)
+                      for yi, ai, bi, ci, di in zip(y, a, b, c, d))
+        else:
+            y = (y + y.real.dtype.type(h) * (a + 2 * (b + c) + d) / 6).astype(y.dtype)
+        k += 2 * sgn
+    return y
+
+
+OP_L, OP_LH, OP_LINV, OP_LHINV = 0, 1, 2, 3
+
+
+def lenseflow_apply(L: CachedLenseFlow, op: int, x: np.ndarray) -> np.ndarray:
+    """*, \\ on FlowOp / Adjoint (src/flowops.jl:11-14).  op 0: L*f (Map→Map, t 0→1);
+    1: L'*f (Fourier→Fourier, t 1→0); 2: L\\f (Map, t 1→0); 3: L'\\f (Fourier, t 0→1)."""
+    n = L.nsteps
+    if op == OP_L:
+        return rk4(lambda k, y: velocity(L, k, y), x, 0, 2 * n, n)
+    if op == OP_LH:
+        return rk4(lambda k, y: velocity_H(L, k, y), x, 2 * n, 0, n)
+    if op == OP_LINV:
+        return rk4(lambda k, y: velocity(L, k, y), x, 2 * n, 0, n)
+    if op == OP_LHINV:
+        return rk4(lambda k, y: velocity_H(L, k, y), x, 0, 2 * n, n)
+    raise ValueError(op)
+
+
+def lenseflow_grad(L: CachedLenseFlow, op: int, f_out: np.ndarray, delta_four: np.ndarray, bug_compat=True):
+    """Pullback of L*f (op 0: δ-flow t 1→0 from (L f, Δ, 0)) or L\\f (op 2: t 0→1)
+    (src/flowops.jl:40-68).  Returns (δf Fourier, δϕ Fourier)."""
+    n = L.nsteps
+    nbphi = L.p[0][0].shape[0]
+    dphi0 = np.zeros((nbphi, 1) + L.proj.fourier_shape, dtype=L.proj.cT)
+    k0, k1 = (2 * n, 0) if op == OP_L else (0, 2 * n)
+    _, df, dphi = rk4(lambda k, y: neg_delta_velocity_H(L, k, y, bug_compat), (f_out, delta_four, dphi0), k0, k1, n)
+    return df, dphi
+
+
+# ----------------------------------------------------------------------------------------------
+# DataSet / Wiener filter (src/dataset.jl:37-137, src/maximization.jl:17-42, src/numerical_algorithms.jl:73-134)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class DataSet:
+    """BaseDataSet restricted to what load_sim builds for pol ∈ {I, P} (src/dataset.jl:186-338):
+    Cf, Cn, Cn̂, B, B̂ and the Fourier part of M are diagonals in the harmonic basis of the field
+    (Fourier for I, EBFourier for P; arrays (1|Nb, Npol, Nx, Ny/2+1) real); the pixel part of M is
+    a Map-basis diagonal (QUMap for P).  M = Mfourier * Mpix ; M̂ = Mfourier (:283-296)."""
+    proj: ProjLambert
+    pol: str                      # "I" or "P"
+    Cf: np.ndarray
+    Cn: np.ndarray
+    Cnhat: np.ndarray
+    B: np.ndarray
+    Bhat: np.ndarray
+    Mf: np.ndarray                # Fourier part of M
+    Mpix: np.ndarray | None       # pixel mask (Map basis), or None for I
+    d: np.ndarray | None = None   # data, harmonic basis
+    L: CachedLenseFlow | None = None
+
+    @property
+    def npol(self):
+        return 1 if self.pol == "I" else 2
+
+
+def to_lense_basis(ds_or_pol, proj, F):
+    """Ł(f) for a harmonic-basis field: (EB→QU) then irfft2 (src/generic.jl:88-93)."""
+    pol = ds_or_pol if isinstance(ds_or_pol, str) else ds_or_pol.pol
+    if pol == "P":
+        F = eb_to_qu(proj, F)
+    return irfft2(F, proj.Ny)
+
+
+def to_harmonic_basis(ds_or_pol, proj, f):
+    """EBFourier(f::QUMap) / Fourier(f::Map)."""
+    pol = ds_or_pol if isinstance(ds_or_pol, str) else ds_or_pol.pol
+    F = rfft2(f)
+    if pol == "P":
+        F = qu_to_eb(proj, F)
+    return F
+
+
+def apply_M(ds: DataSet, F):
+    """M*f = Mfourier * (Mpix * f)."""
+    if ds.Mpix is not None:
+        F = to_harmonic_basis(ds, ds.proj, ds.Mpix * to_lense_basis(ds, ds.proj, F))
+    return ds.Mf * F
+
+
+def apply_MH(ds: DataSet, F):
+    """M'*f = Mpix' * (Mfourier' * f); result left in the Map (QUMap) basis when Mpix is present."""
+    F = ds.Mf * F
+    if ds.Mpix is not None:
+        return ds.Mpix * to_lense_basis(ds, ds.proj, F), True
+    return F, False
+
+
+def gradientf_logpdf(ds: DataSet, f_harm: np.ndarray, d: np.ndarray) -> np.ndarray:
+    """gradientf_logpdf(::BaseDataSet) (src/dataset.jl:76-80):
+       Lϕ'*(B'*(M'*(pinv(Cn)*(d − M*(B*(Lϕ*f)))))) − pinv(Cf)*f.
+    Returned in the DerivBasis Fourier representation the reference ends up in
+    (QUFourier for P by basis promotion, src/generic.jl:185-200); we convert back to the harmonic
+    (EB) basis so the caller sees one basis throughout — a unitary change, not a numerical one."""
+    proj = ds.proj
+    ft = lenseflow_apply(ds.L, OP_L, to_lense_basis(ds, proj, f_harm))             # Lϕ*f   (Map)
+    Bf = ds.B * to_harmonic_basis(ds, proj, ft)                                   # B*f̃
+    res = d - apply_M(ds, Bf)
+    x = pinv_diag(ds.Cn) * res
+    x, is_map = apply_MH(ds, x)
+    if is_map:
+        x = to_harmonic_basis(ds, proj, x)
+    x = ds.B * x                                                                  # B' (real diag)
+    xq = eb_to_qu(proj, x) if ds.pol == "P" else x                                # Ð(·) → QUFourier
+    y = lenseflow_apply(ds.L, OP_LH, xq.astype(proj.cT))                          # Lϕ'*  (QU/Fourier)
+    if ds.pol == "P":
+        y = qu_to_eb(proj, y)
+    return (y - pinv_diag(ds.Cf) * f_harm).astype(proj.cT)
+
+
+def hess_preconditioner(ds: DataSet) -> np.ndarray:
+    """Hessian_logpdf_preconditioner(:f) (src/dataset.jl:129-132): pinv(Cf) + B̂'M̂'pinv(Cn̂)M̂B̂."""
+    return (pinv_diag(ds.Cf) + ds.Bhat * ds.Mf * pinv_diag(ds.Cnhat) * ds.Mf * ds.Bhat).astype(ds.proj.T)
+
+
+def conjugate_gradient(Mdiag, A, dot, b, x0, nsteps: int, tol: float):
+    """conjugate_gradient (src/numerical_algorithms.jl:73-134), exact update order; `Mdiag` is the
+    diagonal preconditioner (M \\ r = nan2zero(r ./ diag)); per-batch scalars broadcast over axis 0
+    (BatchedReal, src/batching.jl:9-45).  Returns (bestx, history[(i, res)])."""
+    def bc(s, like):
+        return np.asarray(s, dtype=like.real.dtype).reshape((-1,) + (1,) * (like.ndim - 1))
+    x = x0
+    r = b - A(x)
+    z = diag_ldiv(Mdiag, r)
+    p = z
+    res = dot(r, z)
+    assert not np.any(np.isnan(res))
+    bestres, bestx = res.copy(), x
+    hist = [(1, res.copy())]
+    for i in range(2, nsteps + 1):
+        Ap = A(p)
+        alpha = res / dot(p, Ap)
+        x = (x + bc(alpha, x) * p).astype(x.dtype)
+        r = (r - bc(alpha, r) * Ap).astype(r.dtype)
+        z = diag_ldiv(Mdiag, r)
+        res2 = dot(r, z)
+        p = (z + bc(res2 / res, p) * p).astype(p.dtype)
+        res = res2
+        if np.all(res < bestres):
+            bestres, bestx = res.copy(), x
+        hist.append((i, res.copy()))
+        if np.all(res < tol):
+            break
+    return bestx, hist
+
+
+def argmaxf_logpdf(ds: DataSet, d=None, fstart=None, nsteps: int = 500, tol: float = 1e-1, offset: bool = False):
+    """argmaxf_logpdf (src/maximization.jl:17-42)."""
+    proj = ds.proj
+    d = ds.d if d is None else d
+    zero_f = np.zeros(d.shape, dtype=proj.cT)
+    b = -gradientf_logpdf(ds, zero_f, d)
+    a0 = gradientf_logpdf(ds, zero_f, np.zeros_like(d))
+    if offset:
+        b = b + a0
+    A = lambda f: gradientf_logpdf(ds, f, np.zeros_like(d)) - a0
+    dot = lambda u, v: dot_fourier(proj, u, v)
+    return conjugate_gradient(hess_preconditioner(ds), A, dot, b, zero_f if fstart is None else fstart, nsteps, tol)
+
+
+# ----------------------------------------------------------------------------------------------
+# Synthetic flat-sky inputs (harness; mirrors load_sim defaults, src/dataset.jl:186-338)
+# ----------------------------------------------------------------------------------------------
+def load_fiducial_cls(path=None):
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "fiducial_cls.npz")
+    z = np.load(path)
+    return {k: z[k] for k in z.files}
+
+
+def simulate_diag(proj: ProjLambert, cov_half: np.ndarray, rng, nb=1) -> np.ndarray:
+    """simulate(rng, D::DiagOp) = sqrt(D) * randn (src/specialops.jl:6): white Map noise → Fourier → ×√C."""
+    npol = cov_half.shape[1]
+    w = rng.standard_normal((nb, npol) + proj.map_shape).astype(proj.T)
+    return (np.sqrt(cov_half) * rfft2(w)).astype(proj.cT)
+
+
+def cosine_border_mask(proj: ProjLambert, border_deg: float = 1.0) -> np.ndarray:
+    """Harness-made pixel mask: 1 inside, cosine-apodised to 0 over `border_deg` at each edge."""
+    def prof(n):
+        w = max(2, int(round(border_deg * 60.0 / proj.theta_pix)))
+        w = min(w, n // 4)
+        x = np.ones(n)
+        ramp = 0.5 * (1 - np.cos(np.pi * (np.arange(w) + 0.5) / w))
+        x[:w] = ramp
+        x[-w:] = ramp[::-1]
+        return x
+    return np.outer(prof(proj.Nx), prof(proj.Ny)).astype(proj.T)
+
+
+def make_dataset(Ny, Nx, theta_pix, pol="I", T=np.float64, nb=1, seed=0, nsteps=7, mask=True,
+                 muK_arcmin_T=3.0, lknee=100.0, aknee=3.0, beam_fwhm=0.0, lowpass=3000, cls=None,
+                 mask_border_deg=1.0):
+    """load_sim restricted to pol ∈ {I,P}; returns dict(f, phi, d, ds, proj) with harmonic-basis fields."""
+    cls = cls or load_fiducial_cls()
+    proj = ProjLambert(Ny, Nx, theta_pix, T)
+    ell = cls["ell"].astype(np.float64)
+    rng = np.random.default_rng(seed)
+    keys = ("ut_TT",) if pol == "I" else ("ut_EE", "ut_BB")
+    Cf = np.stack([cl_to_cov(proj, ell, cls[k]) for k in keys])[None]
+    Cphi = cl_to_cov(proj, ell, cls["pp"])[None, None]
+    Cn = np.stack([cl_to_cov(proj, ell, noise_cls(ell, muK_arcmin_T, lknee, aknee, pol=(pol == "P"))) for _ in keys])[None]
+    lb, wl = lowpass_wl(lowpass)
+    Mf = np.stack([cl_to_cov(proj, lb, wl, units=1) for _ in keys])[None]
+    B = np.stack([cl_to_cov(proj, ell, np.sqrt(beam_cls(ell, beam_fwhm)), units=1) for _ in keys])[None]
+    Mpix = None
+    if mask:
+        m = cosine_border_mask(proj, mask_border_deg)
+        Mpix = np.broadcast_to(m, (1, len(keys)) + m.shape).copy()
+    f = simulate_diag(proj, Cf, rng, nb)
+    phi = simulate_diag(proj, Cphi, rng, nb)
+    n = simulate_diag(proj, Cn, rng, nb)
+    L = precompute(proj, phi, nsteps, phi_is_fourier=True)
+    ds = DataSet(proj, pol, Cf, Cn, Cn.copy(), B, B.copy(), Mf, Mpix, None, L)
+    ft = lenseflow_apply(L, OP_L, to_lense_basis(pol, proj, f))
+    d = (apply_M(ds, B * to_harmonic_basis(pol, proj, ft)) + n).astype(proj.cT)
+    ds.d = d
+    return dict(f=f, phi=phi, d=d, ds=ds, proj=proj, Cphi=Cphi)
