@@ -1,0 +1,96 @@
+// extern "C": LenseFlow entry points.
+#include "api_common.cuh"
+#include "flow.cuh"
+
+struct cmbl_flow { std::unique_ptr<cmbl::FlowBase> f; cmbl_plan* plan; };
+
+namespace cmbl {
+template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,
+                                  bool bug_compat, cmblStream_t st);
+}
+
+extern "C" {
+
+int cmbl_lenseflow_create(cmbl_flow** flow, cmbl_plan* plan, int nsteps, int Npol, int Nb_f, int Nb_phi) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(flow && plan && plan->p, "NULL argument");
+    CMBL_REQUIRE(nsteps >= 1 && nsteps <= 64, "nsteps must be in 1..64");
+    CMBL_REQUIRE(Npol >= 1 && Npol <= 3 && Nb_f >= 1, "Npol must be 1..3 and Nb_f >= 1");
+    CMBL_REQUIRE(Nb_phi == 1 || Nb_phi == Nb_f, "Nb_phi must be 1 or Nb_f (batch sizes must broadcast, src/batching.jl)");
+    auto h = std::make_unique<cmbl_flow>();
+    h->plan = plan;
+    CMBL_DISPATCH(plan->p.get(), {
+        auto F = std::make_unique<cmbl::FlowT<T>>();
+        F->plan = &P; F->P = &P; F->nsteps = nsteps; F->Npol = Npol; F->Nb = Nb_f; F->Nbphi = Nb_phi; F->C = Npol * Nb_f;
+        h->f = std::move(F);
+    });
+    *flow = h.release();
+    CMBL_API_END
+}
+
+int cmbl_lenseflow_destroy(cmbl_flow* flow) {
+    CMBL_API_BEGIN
+    delete flow;
+    CMBL_API_END
+}
+
+int cmbl_lenseflow_precompute(cmbl_flow* flow, const void* phi, int phi_basis, int with_minv, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(flow && flow->f && phi, "NULL argument");
+    CMBL_REQUIRE(phi_basis == CMBL_MAP || phi_basis == CMBL_FOURIER, "phi_basis must be Map or Fourier");
+    CMBL_DISPATCH(flow->f->plan, cmbl::flow_precompute<T>(*static_cast<cmbl::FlowT<T>*>(flow->f.get()), phi, phi_basis,
+                                                          with_minv != 0, as_stream(stream)));
+    CMBL_API_END
+}
+
+int cmbl_lenseflow_apply(cmbl_flow* flow, int op, const void* in, void* out, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(flow && flow->f && in && out, "NULL argument");
+    CMBL_DISPATCH(flow->f->plan, cmbl::flow_apply<T>(*static_cast<cmbl::FlowT<T>*>(flow->f.get()), op, in, out, as_stream(stream)));
+    CMBL_API_END
+}
+
+int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(flow && flow->f && in_host && out_host, "NULL argument");
+    CMBL_REQUIRE(op >= 0 && op <= 3, "LenseFlow op must be 0..3");
+    CMBL_DISPATCH(flow->f->plan, {
+        auto& F = *static_cast<cmbl::FlowT<T>*>(flow->f.get());
+        const bool four = (op == CMBL_OP_LH || op == CMBL_OP_LHINV);
+        const size_t bytes = (four ? sizeof(cmbl::C2<T>) * P.four_elems() : sizeof(T) * P.map_elems()) * (size_t)F.C;
+        static thread_local cmbl::DevBuf io;
+        void* d = io.reserve(bytes);
+#ifdef CMBL_EMU
+        memcpy(d, in_host, bytes);
+#else
+        CMBL_CUDA(cudaMemcpyAsync(d, in_host, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+#endif
+        cmbl::flow_apply<T>(F, op, d, d, as_stream(stream));
+        cmbl::dev_download(out_host, d, bytes, as_stream(stream));
+    });
+    CMBL_API_END
+}
+
+int cmbl_lenseflow_grad(cmbl_flow* flow, int op, const void* f_out_map, const void* delta_four, void* dfield_four,
+                        void* dphi_four, int bug_compat, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(flow && flow->f && f_out_map && delta_four && dfield_four && dphi_four, "NULL argument");
+    CMBL_REQUIRE(op == CMBL_OP_L || op == CMBL_OP_LINV, "gradient is defined for op 0 (L*f) and 2 (L\\f)");
+    CMBL_DISPATCH(flow->f->plan, cmbl::flow_grad<T>(*static_cast<cmbl::FlowT<T>*>(flow->f.get()), op, (const T*)f_out_map,
+                  (const cmbl::C2<T>*)delta_four, (cmbl::C2<T>*)dfield_four, (cmbl::C2<T>*)dphi_four, bug_compat != 0, as_stream(stream)));
+    CMBL_API_END
+}
+
+int cmbl_lenseflow_get_p(cmbl_flow* flow, int k, void* out_host) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(flow && flow->f && out_host, "NULL argument");
+    CMBL_DISPATCH(flow->f->plan, {
+        auto& F = *static_cast<cmbl::FlowT<T>*>(flow->f.get());
+        CMBL_REQUIRE(F.have_p, "precompute first");
+        CMBL_REQUIRE(k >= 0 && k <= 2 * F.nsteps, "k out of range");
+        cmbl::dev_download(out_host, F.pk(k), sizeof(T) * F.nmap() * 2 * F.Nbphi, 0);
+    });
+    CMBL_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// extern "C": plan, FFT entry points, error reporting.
+#include "api_common.cuh"
+#include "fft2d.cuh"
+
+namespace cmbl {
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& s) { t_last_error = s; }
+}
+
+extern "C" {
+
+const char* cmbl_last_error(void) { return cmbl::t_last_error.c_str(); }
+
+const char* cmbl_version(void) {
+#ifdef CMBL_EMU
+    return "cmbl_b200 0.1 (host kernel-logic emulator: tests only)";
+#else
+    return "cmbl_b200 0.1 (sm_100a)";
+#endif
+}
+
+long long cmbl_launch_count(void) { return cmbl::g_launch_count; }
+
+int cmbl_plan_create(cmbl_plan** plan, int device, int Ny, int Nx, double theta_pix_arcmin, int dtype) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan != nullptr, "plan out-pointer is NULL");
+    auto h = std::make_unique<cmbl_plan>();
+    h->p = cmbl::make_plan(device, Ny, Nx, theta_pix_arcmin, dtype);
+    *plan = h.release();
+    CMBL_API_END
+}
+
+int cmbl_plan_destroy(cmbl_plan* plan) {
+    CMBL_API_BEGIN
+    delete plan;
+    CMBL_API_END
+}
+
+int cmbl_plan_grids(cmbl_plan* plan, void* lx, void* ly, void* lam, void* s2, void* c2, double* scalars) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan && plan->p, "NULL plan");
+    CMBL_DISPATCH(plan->p.get(), {
+        if (lx) memcpy(lx, P.h_lx.data(), P.h_lx.size() * sizeof(T));
+        if (ly) memcpy(ly, P.h_ly.data(), P.h_ly.size() * sizeof(T));
+        if (lam) memcpy(lam, P.h_lam.data(), P.h_lam.size() * sizeof(T));
+        if (s2) memcpy(s2, P.h_sin2phi.data(), P.h_sin2phi.size() * sizeof(T));
+        if (c2) memcpy(c2, P.h_cos2phi.data(), P.h_cos2phi.size() * sizeof(T));
+        if (scalars) { scalars[0] = P.dx; scalars[1] = P.dlx; scalars[2] = P.dly; scalars[3] = P.omega_pix; scalars[4] = P.nyquist; }
+    });
+    CMBL_API_END
+}
+
+int cmbl_rfft2(cmbl_plan* plan, const void* map, void* four, int C, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan && plan->p, "NULL plan");
+    CMBL_REQUIRE(C >= 0 && (C == 0 || (map && four)), "NULL buffer");
+    CMBL_DISPATCH(plan->p.get(), cmbl::rfft2<T>(P, (const T*)map, (cmbl::C2<T>*)four, C, as_stream(stream)));
+    CMBL_API_END
+}
+
+int cmbl_irfft2(cmbl_plan* plan, const void* four, void* map, int C, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan && plan->p, "NULL plan");
+    CMBL_REQUIRE(C >= 0 && (C == 0 || (map && four)), "NULL buffer");
+    CMBL_DISPATCH(plan->p.get(), cmbl::irfft2<T>(P, (const cmbl::C2<T>*)four, (T*)map, C, as_stream(stream)));
+    CMBL_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Shared infrastructure for the cmbl_b200 kernels.
+//
+// Every kernel in this library is written in "phase style": a body functor whose work is a sequence of
+// block-wide thread loops (CMBL_FOR_THREADS) separated by CMBL_SYNC().  Compiled by nvcc for sm_100a the loop
+// collapses to `tid = threadIdx.x` and the sync to `__syncthreads()`.  Compiled by g++ with -DCMBL_EMU the very
+// same source runs the threads of a block one after another on the host; that build (tests/_emu) exists ONLY so
+// the kernel index arithmetic can be unit-tested on machines without a GPU.  It is not shipped and the product
+// package never loads it.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <stdexcept>
+#include <vector>
+#ifdef CMBL_EMU
+#include <thread>
+#include <atomic>
+#endif
+
+#ifdef CMBL_EMU
+#define HD inline
+#define DEV inline
+typedef void* cmblStream_t;
+#define CMBL_FOR_THREADS(tid, NT) for (int tid = 0; tid < (NT); ++tid)
+#define CMBL_SYNC() ((void)0)
+#define CMBL_LDG(p) ::cmbl::ldg(p)
+#else
+#include <cuda_runtime.h>
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+typedef cudaStream_t cmblStream_t;
+#define CMBL_FOR_THREADS(tid, NT) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
+#define CMBL_SYNC() __syncthreads()
+#define CMBL_LDG(p) ::cmbl::ldg(p)
+#endif
+
+namespace cmbl {
+
+// ---------------------------------------------------------------------------------------------------------------
+// complex pair, aligned so the compiler emits one 64/128-bit access
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct alignas(2 * sizeof(T)) C2 { T x, y; };
+template <class T> HD C2<T> mk(T x, T y) { C2<T> r; r.x = x; r.y = y; return r; }
+template <class T> HD C2<T> operator+(C2<T> a, C2<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <class T> HD C2<T> operator-(C2<T> a, C2<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <class T> HD C2<T> cmul(C2<T> a, C2<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <class T> HD C2<T> cmulc(C2<T> a, C2<T> b) { /* a * conj(b) */ return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+template <class T> HD C2<T> cconj(C2<T> a) { return mk<T>(a.x, -a.y); }
+template <class T> HD C2<T> cscale(C2<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+
+// read-only (non-coherent) global loads
+template <class U> HD U ldg(const U* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+template <> HD C2<float> ldg<C2<float>>(const C2<float>* p) {
+#ifdef __CUDA_ARCH__
+    float2 v = __ldg(reinterpret_cast<const float2*>(p)); return mk<float>(v.x, v.y);
+#else
+    return *p;
+#endif
+}
+template <> HD C2<double> ldg<C2<double>>(const C2<double>* p) {
+#ifdef __CUDA_ARCH__
+    double2 v = __ldg(reinterpret_cast<const double2*>(p)); return mk<double>(v.x, v.y);
+#else
+    return *p;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CMBL_REQUIRE(cond, msg) do { if (!(cond)) throw ::cmbl::Error(std::string(msg) + "  [" #cond "]"); } while (0)
+
+#ifndef CMBL_EMU
+#define CMBL_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) \
+    throw ::cmbl::Error(std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------
+// device memory / copies (host malloc in the emulator build)
+// ---------------------------------------------------------------------------------------------------------------
+inline void* dev_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+#ifdef CMBL_EMU
+    void* p = nullptr; if (posix_memalign(&p, 256, bytes)) throw Error("host alloc failed"); return p;
+#else
+    void* p = nullptr; CMBL_CUDA(cudaMalloc(&p, bytes)); return p;
+#endif
+}
+inline void dev_free(void* p) {
+    if (!p) return;
+#ifdef CMBL_EMU
+    free(p);
+#else
+    cudaFree(p);
+#endif
+}
+inline void dev_upload(void* dst, const void* src, size_t bytes, cmblStream_t st) {
+#ifdef CMBL_EMU
+    (void)st; memcpy(dst, src, bytes);
+#else
+    CMBL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    CMBL_CUDA(cudaStreamSynchronize(st));          // src may be a temporary
+#endif
+}
+inline void dev_download(void* dst, const void* src, size_t bytes, cmblStream_t st) {
+#ifdef CMBL_EMU
+    (void)st; memcpy(dst, src, bytes);
+#else
+    CMBL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    CMBL_CUDA(cudaStreamSynchronize(st));
+#endif
+}
+inline void dev_copy(void* dst, const void* src, size_t bytes, cmblStream_t st) {
+#ifdef CMBL_EMU
+    (void)st; memmove(dst, src, bytes);
+#else
+    CMBL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+#endif
+}
+inline void dev_zero(void* dst, size_t bytes, cmblStream_t st) {
+#ifdef CMBL_EMU
+    (void)st; memset(dst, 0, bytes);
+#else
+    CMBL_CUDA(cudaMemsetAsync(dst, 0, bytes, st));
+#endif
+}
+
+// RAII device buffer that can grow
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { dev_free(p); }
+    void* reserve(size_t bytes) {
+        if (bytes > cap) {
+#ifndef CMBL_EMU
+            if (p) cudaDeviceSynchronize();
+#endif
+            dev_free(p); p = dev_alloc(bytes); cap = bytes;
+        }
+        return p;
+    }
+    template <class U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel launch: Body has `static constexpr int NT` and `void operator()(int blk, unsigned char* smem) const`
+// ---------------------------------------------------------------------------------------------------------------
+extern long long g_launch_count;      // number of kernels of this library launched (bench.py reports it)
+
+#ifndef CMBL_EMU
+template <class Body> __global__ void __launch_bounds__(Body::NT) kern(const Body b) {
+    extern __shared__ __align__(16) unsigned char cmbl_smem[];
+    b((int)blockIdx.x, cmbl_smem);
+}
+#endif
+
+template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStream_t st) {
+    if (grid <= 0) return;
+    ++g_launch_count;
+#ifdef CMBL_EMU
+    (void)st;
+    int nthr = (int)std::thread::hardware_concurrency(); if (nthr < 1) nthr = 1; if (nthr > grid) nthr = grid;
+    if (const char* e = getenv("CMBL_EMU_THREADS")) { nthr = atoi(e); if (nthr < 1) nthr = 1; }
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        std::vector<unsigned char> buf(smem + 64);
+        unsigned char* sm = buf.data(); sm += (64 - ((uintptr_t)sm & 63)) & 63;
+        for (;;) { int blk = next.fetch_add(1); if (blk >= grid) break; b(blk, sm); }
+    };
+    if (nthr == 1) worker();
+    else { std::vector<std::thread> th; for (int i = 0; i < nthr; ++i) th.emplace_back(worker); for (auto& t : th) t.join(); }
+#else
+    static thread_local bool configured = false;              // one attribute call per instantiation per thread
+    CMBL_REQUIRE(smem <= 227 * 1024, "kernel tile exceeds 227 KB of shared memory");
+    if (smem > 48 * 1024 && !configured) {
+        CMBL_CUDA(cudaFuncSetAttribute(kern<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = true;
+    }
+    kern<Body><<<grid, Body::NT, smem, st>>>(b);
+    CMBL_CUDA(cudaGetLastError());
+#endif
+}
+
+HD int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+}  // namespace cmbl

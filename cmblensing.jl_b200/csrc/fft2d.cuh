@@ -1,0 +1,141 @@
+// Batched 2-D real FFT over planes laid out like the reference's arrays: Map (Ny,Nx,C) column-major = [c][x][y],
+// Fourier (Ny/2+1,Nx,C) = [c][x][ky]  (src/proj_cartesian.jl:51-56; transforms src/util_fft.jl:26-27 m_rfft!/m_irfft!).
+//   rfft2 : column pass (two real columns packed as one complex line, R2C along y) then row pass (C2C along x,
+//           in place on the output).  Unnormalised.
+//   irfft2: row pass (inverse C2C along x, into plan scratch so the input is never clobbered, util_fft.jl:44) then
+//           column pass (C2R along y: imaginary parts of the ky=0 and ky=Ny/2 rows are ignored, like FFTW / cuFFT).
+//           Normalised by 1/(Ny·Nx).
+#pragma once
+#include "plan.cuh"
+
+namespace cmbl {
+
+inline int tile_budget_bytes() {
+    static int v = [] { const char* e = getenv("CMBL_TILE_KB"); int kb = e ? atoi(e) : 72; if (kb < 8) kb = 8; if (kb > 200) kb = 200; return kb * 1024; }();
+    return v;
+}
+inline int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+
+// lines per tile for column kernels (line-major tile); `extra` = additional lines the kernel appends
+template <class T> int col_lines(int N, int Nother, int extra = 0) {
+    size_t per = sizeof(C2<T>) * (size_t)Tile<T, false>::pitch_for(N);
+    int L = (int)(tile_budget_bytes() / per) - extra;
+    if (L < 1) L = 1;
+    L = pow2_floor(L);
+    if (L > Nother / 2) L = Nother / 2;
+    if (L > 64) L = 64;
+    return L;
+}
+// lines per tile for row kernels (interleaved tile)
+template <class T> int row_lines(int N, int maxL) {
+    size_t per = sizeof(C2<T>) * (size_t)N;
+    int L = (int)(tile_budget_bytes() / per);
+    if (L < 1) L = 1;
+    L = pow2_floor(L);
+    if (L > maxL) L = pow2_floor(maxL);
+    if (L > 64) L = 64;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// column pass of rfft2
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct R2CColBody {
+    static constexpr int NT = 256;
+    Fft1D<T> fy; int Ny, Nx, Nyh, L, tiles_per_plane;
+    const T* in; C2<T>* out;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
+        Tile<T, false> tv{reinterpret_cast<C2<T>*>(smem), L, Tile<T, false>::pitch_for(Ny)};
+        const T* src = in + ((size_t)c * Nx + x0) * Ny;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Ny; e += NT) {
+                int l = e / Ny, y = e - l * Ny;
+                tv.at(l, y) = mk<T>(src[(size_t)(2 * l) * Ny + y], src[(size_t)(2 * l + 1) * Ny + y]);
+            }
+        }
+        CMBL_SYNC();
+        fft_forward_passes<T, false, NT>(tv, fy, 0, fy.npass);
+        C2<T>* dst = out + ((size_t)c * Nx + x0) * Nyh;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Nyh; e += NT) {
+                int l = e / Nyh, k = e - l * Nyh;
+                C2<T> zk = tv.at(l, CMBL_LDG(&fy.pos[k]));
+                C2<T> zm = tv.at(l, CMBL_LDG(&fy.pos[(Ny - k) & (Ny - 1)]));
+                const T h = (T)0.5;
+                dst[(size_t)(2 * l) * Nyh + k] = mk<T>((zk.x + zm.x) * h, (zk.y - zm.y) * h);
+                dst[(size_t)(2 * l + 1) * Nyh + k] = mk<T>((zk.y + zm.y) * h, (zm.x - zk.x) * h);
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// row pass (C2C along x) on a chunk of L consecutive ky, forward (in place allowed) or inverse (in -> out)
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, bool INV> struct C2CRowBody {
+    static constexpr int NT = 256;
+    Fft1D<T> fx; int Nx, Nyh, L, tiles_per_plane;
+    const C2<T>* in; C2<T>* out;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        const int c = blk / tiles_per_plane, k0 = (blk % tiles_per_plane) * L;
+        Tile<T, true> tv{reinterpret_cast<C2<T>*>(smem), L, 0};
+        const C2<T>* src = in + (size_t)c * Nx * Nyh;
+        C2<T>* dst = out + (size_t)c * Nx * Nyh;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Nx; e += NT) {
+                int x = e / L, l = e - x * L;
+                C2<T> v = (k0 + l < Nyh) ? src[(size_t)x * Nyh + k0 + l] : mk<T>(0, 0);
+                tv.at(l, INV ? CMBL_LDG(&fx.pos[x]) : x) = v;
+            }
+        }
+        CMBL_SYNC();
+        if (INV) fft_inverse_passes<T, true, NT>(tv, fx, 0, fx.npass);
+        else fft_forward_passes<T, true, NT>(tv, fx, 0, fx.npass);
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Nx; e += NT) {
+                int x = e / L, l = e - x * L;
+                if (k0 + l < Nyh) dst[(size_t)x * Nyh + k0 + l] = tv.at(l, INV ? x : CMBL_LDG(&fx.pos[x]));
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// column pass of irfft2 (C2R along y)
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct C2RColBody {
+    static constexpr int NT = 256;
+    Fft1D<T> fy; int Ny, Nx, Nyh, L, tiles_per_plane; T scale;
+    const C2<T>* in; T* out;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
+        Tile<T, false> tv{reinterpret_cast<C2<T>*>(smem), L, Tile<T, false>::pitch_for(Ny)};
+        const C2<T>* src = in + ((size_t)c * Nx + x0) * Nyh;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Nyh; e += NT) {
+                int l = e / Nyh, k = e - l * Nyh;
+                C2<T> a = src[(size_t)(2 * l) * Nyh + k], b = src[(size_t)(2 * l + 1) * Nyh + k];
+                if (k == 0 || 2 * k == Ny) { a.y = 0; b.y = 0; }            // c2r ignores Im of DC / Nyquist rows
+                tv.at(l, CMBL_LDG(&fy.pos[k])) = mk<T>(a.x - b.y, a.y + b.x);
+                if (k != 0 && 2 * k != Ny) tv.at(l, CMBL_LDG(&fy.pos[Ny - k])) = mk<T>(a.x + b.y, b.x - a.y);
+            }
+        }
+        CMBL_SYNC();
+        fft_inverse_passes<T, false, NT>(tv, fy, 0, fy.npass);
+        T* dst = out + ((size_t)c * Nx + x0) * Ny;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Ny; e += NT) {
+                int l = e / Ny, y = e - l * Ny;
+                C2<T> z = tv.at(l, y);
+                dst[(size_t)(2 * l) * Ny + y] = z.x * scale;
+                dst[(size_t)(2 * l + 1) * Ny + y] = z.y * scale;
+            }
+        }
+    }
+};
+
+template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmblStream_t st);
+template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st);
+
+}  // namespace cmbl

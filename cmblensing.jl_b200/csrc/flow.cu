@@ -1,0 +1,135 @@
+#include "flow.cuh"
+#include "../../include/cmbl_b200.h"
+
+namespace cmbl {
+
+template <class T> void flow_precompute(FlowT<T>& F, const void* phi, int phi_basis, bool with_minv, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
+    const size_t nmap = P.map_elems(), nf = P.four_elems();
+    const int nk = 2 * F.nsteps + 1;
+    const C2<T>* phif;
+    if (phi_basis == CMBL_FOURIER) phif = reinterpret_cast<const C2<T>*>(phi);
+    else {
+        C2<T>* s = reinterpret_cast<C2<T>*>(F.spec.reserve(sizeof(C2<T>) * nf * F.Nbphi));
+        rfft2<T>(P, reinterpret_cast<const T*>(phi), s, F.Nbphi, st);
+        phif = s;
+    }
+    // the 5 gradient/Hessian spectra live behind the (optional) ϕ spectrum in the same scratch buffer
+    DevBuf& ghs = F.gh;
+    C2<T>* spec5 = reinterpret_cast<C2<T>*>(ghs.reserve(sizeof(C2<T>) * nf * 5 * F.Nbphi + sizeof(T) * nmap * 5 * F.Nbphi));
+    T* maps5 = reinterpret_cast<T*>(spec5 + nf * 5 * F.Nbphi);
+    {
+        GradHessSpecBody<T> b{P.Nx, P.Nyh, P.lx, P.ly, phif, spec5, nf * (size_t)F.Nbphi};
+        launch(b, (int)((b.total + b.NT - 1) / b.NT), 0, st);
+    }
+    irfft2<T>(P, spec5, maps5, 5 * F.Nbphi, st);
+    T* pc = reinterpret_cast<T*>(F.pcache.reserve(sizeof(T) * nmap * 2 * F.Nbphi * nk));
+    T* mi = with_minv ? reinterpret_cast<T*>(F.minv.reserve(sizeof(T) * nmap * 3 * F.Nbphi * nk)) : nullptr;
+    {
+        PCacheBody<T> b{nk, F.Nbphi, nmap, maps5, pc, mi};
+        launch(b, (int)((nmap * F.Nbphi + b.NT - 1) / b.NT), 0, st);
+    }
+    F.have_p = true; F.have_minv = with_minv;
+}
+
+template <class T, bool ADJ>
+static void flow_stage(FlowT<T>& F, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
+                       T ca, T cb, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
+    T* tmp = reinterpret_cast<T*>(F.tmp.p); T* nline = reinterpret_cast<T*>(F.nline.p);
+    {
+        FlowRowBody<T, ADJ> b;
+        b.fx = P.ax.fft; b.mult = P.ax.mult_deriv;
+        b.Ny = P.Ny; b.Nx = P.Nx; b.L = row_lines<T>(P.Nx, P.Ny / 2); b.tiles_per_plane = P.Ny / (2 * b.L);
+        b.Npol = F.Npol; b.Nbphi = F.Nbphi;
+        b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.nline = nline; b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
+        launch(b, F.C * b.tiles_per_plane, Tile<T, true>::bytes(P.Nx, b.L), st);
+    }
+    {
+        FlowColBody<T, ADJ> b;
+        b.fy = P.ay.fft; b.mult_d = P.ay.mult_deriv; b.mult_s = P.ay.mult_sign;
+        b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.Ny, P.Nx, 1); b.tiles_per_plane = P.Nx / (2 * b.L);
+        b.Npol = F.Npol; b.Nbphi = F.Nbphi;
+        b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.nline = nline; b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
+        b.cN = P.ax.ell_nyq / (T)P.Nx;
+        b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
+        launch(b, F.C * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L + 1), st);
+    }
+}
+
+template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st) {
+    CMBL_REQUIRE(F.have_p, "LenseFlow used before cmbl_lenseflow_precompute");
+    PlanT<T>& P = *F.P;
+    const size_t nmap = P.map_elems();
+    const int n = F.nsteps;
+    T* acc = reinterpret_cast<T*>(F.acc.reserve(sizeof(T) * nmap * F.C));
+    T* ub = reinterpret_cast<T*>(F.ubuf.reserve(sizeof(T) * nmap * F.C));
+    F.tmp.reserve(sizeof(T) * nmap * F.C);
+    F.nline.reserve(sizeof(T) * (size_t)P.Ny * F.C);
+    const int sgn = k1 > k0 ? 1 : -1;
+    const double h = (double)sgn / n;
+    const T h2 = (T)(h / 2), h1 = (T)h, h6 = (T)(h / 6), h3 = (T)(h / 3);
+    int kk = k0;
+    for (int step = 0; step < n; ++step) {
+        for (int s = 0; s < 4; ++s) {
+            const int kq = kk + (s == 0 ? 0 : (s < 3 ? sgn : 2 * sgn));
+            const T* u = (s == 0) ? y : ub;
+            const T* ybase = (s == 3) ? nullptr : y;
+            const T* acc_in = (s == 0) ? nullptr : acc;
+            T* acc_out = (s == 3) ? y : acc;
+            T* u_out = (s == 3) ? nullptr : ub;
+            const T ca = (s < 2) ? h2 : h1, cb = (s == 0 || s == 3) ? h6 : h3;
+            if (adj) flow_stage<T, true>(F, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st);
+            else flow_stage<T, false>(F, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st);
+        }
+        kk += 2 * sgn;
+    }
+}
+
+template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
+    const size_t nmap = P.map_elems(), nf = P.four_elems();
+    const int n = F.nsteps;
+    CMBL_REQUIRE(op >= 0 && op <= 3, "LenseFlow op must be 0..3");
+    if (op == CMBL_OP_L || op == CMBL_OP_LINV) {
+        T* y = reinterpret_cast<T*>(out);
+        if (in != out) dev_copy(y, in, sizeof(T) * nmap * F.C, st);
+        if (op == CMBL_OP_L) flow_integrate<T>(F, false, y, 0, 2 * n, st);
+        else flow_integrate<T>(F, false, y, 2 * n, 0, st);
+        return;
+    }
+    // adjoint flows: Fourier state integrated in map space (see flow.cuh)
+    const C2<T>* Y0 = reinterpret_cast<const C2<T>*>(in);
+    C2<T>* Yout = reinterpret_cast<C2<T>*>(out);
+    T* y = reinterpret_cast<T*>(F.ybuf.reserve(sizeof(T) * nmap * F.C));
+    C2<T>* rows0 = reinterpret_cast<C2<T>*>(F.rows0.reserve(sizeof(C2<T>) * 2 * (size_t)P.Nx * F.C));
+    T* nacc = reinterpret_cast<T*>(F.nacc.reserve(sizeof(T) * (size_t)P.Ny * F.C));
+    T* macc = reinterpret_cast<T*>(F.macc.reserve(sizeof(T) * (size_t)P.Nx * F.C));
+    {
+        AdjRowsSaveBody<T> b{P.Nx, P.Nyh, Y0, rows0};
+        launch(b, F.C, 0, st);
+    }
+    dev_zero(nacc, sizeof(T) * (size_t)P.Ny * F.C, st);
+    dev_zero(macc, sizeof(T) * (size_t)P.Nx * F.C, st);
+    irfft2<T>(P, Y0, y, F.C, st);
+    if (op == CMBL_OP_LH) flow_integrate<T>(F, true, y, 2 * n, 0, st);
+    else flow_integrate<T>(F, true, y, 0, 2 * n, st);
+    rfft2<T>(P, y, Yout, F.C, st);
+    {
+        AdjFixBody<T> b;
+        b.fx = P.ax.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh; b.lxN = P.ax.ell_nyq; b.lyN = P.ay.ell_nyq;
+        b.rows0 = rows0; b.nacc = nacc; b.macc = macc; b.out = Yout;
+        size_t smem = sizeof(C2<T>) * Tile<T, false>::pitch_for(P.Nx) + sizeof(T) * 2 * b.NT;
+        launch(b, F.C, smem, st);
+    }
+    (void)nf;
+}
+
+#define INST(T)                                                                                        \
+    template void flow_precompute<T>(FlowT<T>&, const void*, int, bool, cmblStream_t);                 \
+    template void flow_integrate<T>(FlowT<T>&, bool, T*, int, int, cmblStream_t);                      \
+    template void flow_apply<T>(FlowT<T>&, int, const void*, void*, cmblStream_t);
+INST(float)
+INST(double)
+
+}  // namespace cmbl

@@ -1,0 +1,268 @@
+// LenseFlow on the device (src/lenseflow.jl, src/flowops.jl:11-14, RK4 src/numerical_algorithms.jl:11-24).
+//
+// The reference evaluates the velocity  v = p₁·∂ₓf + p₂·∂ᵧf  with three full 2-D FFTs per RK stage
+// (src/lenseflow.jl:150-161).  ∂ᵧ only involves transforms along y and ∂ₓ only transforms along x, so here a stage is
+// two 1-D spectral-derivative kernels and no 2-D transform at all:
+//     row kernel    (FlowRowBody): tiles of rows, all x      → ∂ₓ (Hermitian part), Nyquist-in-x line N(y)
+//     column kernel (FlowColBody): tiles of columns, all y   → ∂ᵧ, the Nyquist correction, velocity, RK4 update
+// What makes this exact rather than approximate is the reference's treatment of the x-Nyquist mode: ℓ at Nyquist is
+// −(N/2)Δℓ and is not zeroed (src/proj_lambert.jl:63-64), so iℓₓF is non-Hermitian there and the final C2R along y
+// (which drops Im of the ky=0, Ny/2 rows) turns that mode into  (ℓ_N/Nx)(−1)^x · J[N](y),  N(y)=Σₓ(−1)^x f(y,x),
+// J = Hilbert-type multiplier i·sign(ky) with DC/Nyquist removed.  The column kernel adds exactly this rank-one term.
+// The adjoint flow (src/lenseflow.jl:163-174), whose state the reference keeps in Fourier space, is integrated in map
+// space in divergence form; the non-Hermitian spectrum entries the reference accumulates on the ky∈{0,Ny/2} rows are
+// carried as two 1-D accumulators and restored by AdjFixBody after the final rfft2.
+#pragma once
+#include "fft2d.cuh"
+
+namespace cmbl {
+
+// p[k] pointer for plane c:  pcache layout [k][Nbphi][2][Nx][Ny]
+template <class T> HD const T* p_plane(const T* pk, int c, int Npol, int Nbphi, int comp, size_t nmap) {
+    int bphi = (Nbphi == 1) ? 0 : c / Npol;
+    return pk + ((size_t)bphi * 2 + comp) * nmap;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// row kernel: tmp = ∂ₓ_herm(g),  g = u (forward) or p₁·u (adjoint);  nline = N(y) = Σₓ (−1)^x g
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, bool ADJ> struct RowMid {
+    const T* mult; T* nline_c; T* nacc_c; T wgt; int y0;
+    template <int R> HD void run(int l, int i0, C2<T>* v) const {
+        if (i0 == 0) {
+            C2<T> nq = v[R / 2];                                  // Nyquist coefficient sits at tile position R/2
+            nline_c[y0 + 2 * l] = nq.x; nline_c[y0 + 2 * l + 1] = nq.y;
+            if (ADJ) { nacc_c[y0 + 2 * l] += wgt * nq.x; nacc_c[y0 + 2 * l + 1] += wgt * nq.y; }
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) { T m = CMBL_LDG(&mult[i0 + q]); v[q] = mk<T>(-m * v[q].y, m * v[q].x); }
+    }
+};
+
+template <class T, bool ADJ> struct FlowRowBody {
+    static constexpr int NT = 256;
+    Fft1D<T> fx; const T* mult;
+    int Ny, Nx, L, tiles_per_plane, Npol, Nbphi;
+    const T* u; const T* pk; T* tmp; T* nline; T* nacc; T wgt;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        const int c = blk / tiles_per_plane, y0 = (blk % tiles_per_plane) * 2 * L;
+        const size_t nmap = (size_t)Ny * Nx;
+        Tile<T, true> tv{reinterpret_cast<C2<T>*>(smem), L, 0};
+        const T* uc = u + (size_t)c * nmap + y0;
+        const T* p1 = ADJ ? p_plane(pk, c, Npol, Nbphi, 0, nmap) + y0 : nullptr;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Nx; e += NT) {
+                int x = e / L, l = e - x * L;
+                size_t idx = (size_t)x * Ny + 2 * l;
+                C2<T> v = *reinterpret_cast<const C2<T>*>(uc + idx);
+                if (ADJ) { C2<T> pp = *reinterpret_cast<const C2<T>*>(p1 + idx); v.x *= pp.x; v.y *= pp.y; }
+                tv.at(l, x) = v;
+            }
+        }
+        CMBL_SYNC();
+        RowMid<T, ADJ> mid{mult, nline + (size_t)c * Ny, ADJ ? nacc + (size_t)c * Ny : nullptr, wgt, y0};
+        fft_spectral_op<T, true, NT>(tv, fx, mid);
+        T* tc = tmp + (size_t)c * nmap + y0;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Nx; e += NT) {
+                int x = e / L, l = e - x * L;
+                *reinterpret_cast<C2<T>*>(tc + (size_t)x * Ny + 2 * l) = tv.at(l, x);
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// column kernel: ∂ᵧ, Nyquist correction, velocity k, RK4 update
+//   forward: k = p₁·(tmp ± cN·J[N]) + p₂·∂ᵧu          adjoint: k = tmp ± cN·J[N] + ∂ᵧ(p₂·u)
+//   acc_out = (acc_in ? acc_in : ybase) + cb·k ;  u_out = ybase + ca·k  (if u_out)
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, bool ADJ> struct ColMid {
+    const T* mult_d; const T* mult_s; T* macc_c; T wgt; int x0, L;
+    template <int R> HD void run(int l, int i0, C2<T>* v) const {
+        if (ADJ && i0 == 0 && l < L) {
+            C2<T> nq = v[R / 2];
+            macc_c[x0 + 2 * l] += wgt * nq.x; macc_c[x0 + 2 * l + 1] += wgt * nq.y;
+        }
+        const T* mult = (l == L) ? mult_s : mult_d;
+#pragma unroll
+        for (int q = 0; q < R; ++q) { T m = CMBL_LDG(&mult[i0 + q]); v[q] = mk<T>(-m * v[q].y, m * v[q].x); }
+    }
+};
+
+template <class T, bool ADJ> struct FlowColBody {
+    static constexpr int NT = 256;
+    Fft1D<T> fy; const T* mult_d; const T* mult_s;
+    int Ny, Nx, L, tiles_per_plane, Npol, Nbphi;
+    const T* u; const T* pk; const T* tmp; const T* nline; T* macc; T wgt; T cN;
+    const T* ybase; const T* acc_in; T* acc_out; T* u_out; T ca, cb;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
+        const size_t nmap = (size_t)Ny * Nx, off = (size_t)c * nmap + (size_t)x0 * Ny;
+        Tile<T, false> tv{reinterpret_cast<C2<T>*>(smem), L + 1, Tile<T, false>::pitch_for(Ny)};
+        const T* uc = u + off;
+        const T* p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap) + (size_t)x0 * Ny;
+        const T* p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap) + (size_t)x0 * Ny;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Ny; e += NT) {
+                int l = e / Ny, y = e - l * Ny;
+                size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
+                T a = uc[ia], b = uc[ib];
+                if (ADJ) { a *= p2[ia]; b *= p2[ib]; }
+                tv.at(l, y) = mk<T>(a, b);
+            }
+            for (int y = tid; y < Ny; y += NT) tv.at(L, y) = mk<T>(nline[(size_t)c * Ny + y], (T)0);
+        }
+        CMBL_SYNC();
+        ColMid<T, ADJ> mid{mult_d, mult_s, ADJ ? macc + (size_t)c * Nx : nullptr, wgt, x0, L};
+        fft_spectral_op<T, false, NT>(tv, fy, mid);
+        const T* tc = tmp + off;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < L * Ny; e += NT) {
+                int l = e / Ny, y = e - l * Ny;
+                size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
+                C2<T> z = tv.at(l, y);
+                T jn = cN * tv.at(L, y).x;
+                T ka, kb;
+                if (ADJ) { ka = tc[ia] + jn + z.x; kb = tc[ib] - jn + z.y; }
+                else { ka = p1[ia] * (tc[ia] + jn) + p2[ia] * z.x; kb = p1[ib] * (tc[ib] - jn) + p2[ib] * z.y; }
+                T base_a = 0, base_b = 0;
+                if (ybase) { base_a = ybase[off + ia]; base_b = ybase[off + ib]; }
+                T a0 = acc_in ? acc_in[off + ia] : base_a, b0 = acc_in ? acc_in[off + ib] : base_b;
+                acc_out[off + ia] = a0 + cb * ka; acc_out[off + ib] = b0 + cb * kb;
+                if (u_out) { u_out[off + ia] = base_a + ca * ka; u_out[off + ib] = base_b + ca * kb; }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// adjoint flow bookkeeping on the ky ∈ {0, Ny/2} rows of the Fourier state
+// ---------------------------------------------------------------------------------------------------------------
+// rows0[c][r][kx] = Y[c][kx][r ? Ny/2 : 0]
+template <class T> struct AdjRowsSaveBody {
+    static constexpr int NT = 256;
+    int Nx, Nyh; const C2<T>* Y; C2<T>* rows0;
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < 2 * Nx; e += NT) {
+                int r = e / Nx, kx = e - r * Nx;
+                rows0[((size_t)blk * 2 + r) * Nx + kx] = Y[((size_t)blk * Nx + kx) * Nyh + (r ? Nyh - 1 : 0)];
+            }
+        }
+    }
+};
+
+// out = rfft2(y_final) + (I − P)·Y₀ + Nyquist accumulators   (one block per plane; see header comment)
+template <class T> struct AdjFixBody {
+    static constexpr int NT = 256;
+    Fft1D<T> fx; int Ny, Nx, Nyh; T lxN, lyN;
+    const C2<T>* rows0; const T* nacc; const T* macc; C2<T>* out;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        const int c = blk;
+        C2<T>* line = reinterpret_cast<C2<T>*>(smem);
+        T* red = reinterpret_cast<T*>(line + Tile<T, false>::pitch_for(Nx));          // [2][NT]
+        Tile<T, false> tv{line, 1, Tile<T, false>::pitch_for(Nx)};
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int x = tid; x < Nx; x += NT) tv.at(0, x) = mk<T>(macc[(size_t)c * Nx + x], (T)0);
+            T s0 = 0, s1 = 0;
+            for (int y = tid; y < Ny; y += NT) { T v = nacc[(size_t)c * Ny + y]; s0 += v; s1 += (y & 1) ? -v : v; }
+            red[tid] = s0; red[NT + tid] = s1;
+        }
+        CMBL_SYNC();
+        fft_forward_passes<T, false, NT>(tv, fx, 0, fx.npass);
+        C2<T>* oc = out + (size_t)c * Nx * Nyh;
+        const C2<T>* r0 = rows0 + (size_t)c * 2 * Nx;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < 2 * Nx; e += NT) {
+                int r = e / Nx, kx = e - r * Nx;
+                C2<T> X = r0[(size_t)r * Nx + kx], Xm = r0[(size_t)r * Nx + ((Nx - kx) & (Nx - 1))];
+                C2<T> add = mk<T>((X.x - Xm.x) * (T)0.5, (X.y + Xm.y) * (T)0.5);     // (X − conj X₋ₖ)/2
+                if (r == 1) {                                                          // + iℓyN · FFTx(Macc)
+                    C2<T> m = tv.at(0, CMBL_LDG(&fx.pos[kx]));
+                    add.x += -lyN * m.y; add.y += lyN * m.x;
+                }
+                if (kx == Nx / 2) {                                                    // + iℓxN · Σ(±)Nacc
+                    T s = 0;
+                    for (int i = 0; i < NT; ++i) s += red[r * NT + i];
+                    add.y += lxN * s;
+                }
+                C2<T>& o = oc[(size_t)kx * Nyh + (r ? Nyh - 1 : 0)];
+                o = o + add;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// precompute! (src/lenseflow.jl:131-142; gradhess src/specialops.jl:184-188; pinv! src/field_vectors.jl:86-94)
+// ---------------------------------------------------------------------------------------------------------------
+// Φ[bphi] -> 5 spectra [bphi][5]: g1=iℓxΦ, g2=iℓyΦ, H11=iℓx g1, H21=iℓx g2, H22=iℓy g2
+template <class T> struct GradHessSpecBody {
+    static constexpr int NT = 256;
+    int Nx, Nyh; const T* lx; const T* ly; const C2<T>* phi; C2<T>* out; size_t total;   // total = Nbphi*Nx*Nyh
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < total) {
+                size_t nf = (size_t)Nx * Nyh;
+                size_t b = e / nf, r = e - b * nf;
+                int kx = (int)(r / Nyh), ky = (int)(r - (size_t)kx * Nyh);
+                C2<T> d1 = mk<T>((T)0, lx[kx]), d2 = mk<T>((T)0, ly[ky]);
+                C2<T> F = phi[e];
+                C2<T> g1 = cmul(d1, F), g2 = cmul(d2, F);
+                C2<T>* o = out + b * 5 * nf + r;
+                o[0] = g1; o[nf] = g2; o[2 * nf] = cmul(d1, g1); o[3 * nf] = cmul(d1, g2); o[4 * nf] = cmul(d2, g2);
+            }
+        }
+    }
+};
+
+// maps gh[bphi][5] -> pcache[k][bphi][2], minv[k][bphi][3] (m11, m21, m22) for k = 0..2n
+template <class T> struct PCacheBody {
+    static constexpr int NT = 256;
+    int nk, Nbphi; size_t nmap; const T* gh; T* pcache; T* minv;
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < nmap * Nbphi) {
+                size_t b = e / nmap, r = e - b * nmap;
+                const T* g = gh + b * 5 * nmap + r;
+                T g1 = g[0], g2 = g[nmap], H11 = g[2 * nmap], H21 = g[3 * nmap], H22 = g[4 * nmap];
+                for (int k = 0; k < nk; ++k) {
+                    T t = (T)((double)k / (double)(nk - 1));
+                    T a = (T)1 + t * H11, d = (T)1 + t * H22, bb = t * H21;
+                    T det = a * d - bb * bb;
+                    T idet = (det == (T)0) ? (T)0 : (T)1 / det;              // scalar pinv: 0 -> 0
+                    T m11 = idet * d, m21 = -idet * bb, m22 = idet * a;      // m12 == m21 (field_vectors.jl:87 reads [2,1] twice)
+                    size_t o = ((size_t)k * Nbphi + b) * 2 * nmap + r;
+                    pcache[o] = m11 * g1 + m21 * g2;
+                    pcache[o + nmap] = m21 * g1 + m22 * g2;
+                    if (minv) {
+                        size_t om = ((size_t)k * Nbphi + b) * 3 * nmap + r;
+                        minv[om] = m11; minv[om + nmap] = m21; minv[om + 2 * nmap] = m22;
+                    }
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+struct FlowBase { PlanBase* plan = nullptr; virtual ~FlowBase() {} };
+
+template <class T> struct FlowT : FlowBase {
+    PlanT<T>* P = nullptr;
+    int nsteps = 7, Npol = 1, Nb = 1, Nbphi = 1, C = 1;
+    bool have_p = false, have_minv = false;
+    DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, nacc, macc, rows0, spec, gh;
+    size_t nmap() const { return P->map_elems(); }
+    const T* pk(int k) const { return reinterpret_cast<T*>(pcache.p) + (size_t)k * Nbphi * 2 * nmap(); }
+};
+
+template <class T> void flow_precompute(FlowT<T>& F, const void* phi, int phi_basis, bool with_minv, cmblStream_t st);
+// integrate the map-space flow in place on y from stage index k0 to k1 (0 or 2n)
+template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st);
+template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st);
+
+}  // namespace cmbl
