@@ -1,0 +1,447 @@
+"""cmblensing.jl_b200 — host-side mirror of CMBLensing.jl's flat-sky operator API over libcmbl_b200.so.
+
+The reference's host language is Julia, which is not available in this image, so this thin Python layer stands where
+`CMBLensingB200Ext.jl` would: same names, argument meaning and error behaviour as the reference for the
+hot path — `ProjLambert`, `FlatMap/FlatFourier/FlatQUMap/...`, basis conversions `Map(f)`, `Fourier(f)`, `QUFourier(f)`,
+`EBFourier(f)`, `LenseFlow(ϕ) * f`, `L.H * f`, `L.ldiv(f)` (Julia `L \\ f`), `DiagOp`, `dot`, `BaseDataSet`,
+`gradientf_logpdf`, `argmaxf_logpdf`, `conjugate_gradient`.  All arithmetic runs in the CUDA library (sm_100a); torch
+is used only to own device memory and streams.  There is no CPU fallback.
+
+Array layout: Julia's column-major (Ny, Nx, Npol, Nb) is the C-order tensor [Nb, Npol, Nx, Ny] (Ny fastest); Fourier
+arrays are [Nb, Npol, Nx, Ny//2+1] complex (src/proj_cartesian.jl:51-56).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CmblError, DatasetDesc, FOURIER, MAP, OP_L, OP_LH, OP_LHINV, OP_LINV, load
+
+__all__ = [
+    "ProjLambert", "Field", "FlatMap", "FlatFourier", "FlatQUMap", "FlatQUFourier", "FlatEBMap", "FlatEBFourier",
+    "Map", "Fourier", "QUMap", "QUFourier", "EBMap", "EBFourier", "LenseBasis", "DerivBasis", "HarmonicBasis",
+    "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "dot", "BaseDataSet", "gradientf_logpdf",
+    "Hessian_logpdf_preconditioner", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
+    "CmblError", "load",
+]
+
+_TORCH_REAL = {0: torch.float32, 1: torch.float64}
+_TORCH_CPLX = {0: torch.complex64, 1: torch.complex128}
+_NP_REAL = {0: np.float32, 1: np.float64}
+
+
+def _ptr(t: torch.Tensor) -> c_void_p:
+    return c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor) -> c_void_p:
+    if t.is_cuda:
+        return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return c_void_p(0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ProjLambert (src/proj_lambert.jl:24-75) + FFT plan (src/util_fft.jl:32-39)
+# ------------------------------------------------------------------------------------------------------------------
+class ProjLambert:
+    _memo: dict = {}
+
+    def __new__(cls, Ny, Nx=None, θpix=1.0, T=torch.float32, device="cuda:0", lib=None):
+        Nx = Ny if Nx is None else Nx
+        lib = lib or load()
+        key = (int(Ny), int(Nx), float(θpix), T, str(device), lib.path)
+        if key in cls._memo:                                      # @memoize, src/proj_lambert.jl:47
+            return cls._memo[key]
+        self = super().__new__(cls)
+        self._init(int(Ny), int(Nx), float(θpix), T, torch.device(device), lib)
+        cls._memo[key] = self
+        return self
+
+    def _init(self, Ny, Nx, θpix, T, device, lib):
+        if T not in (torch.float32, torch.float64):
+            raise CmblError("T must be torch.float32 or torch.float64")
+        if device.type == "cuda" and lib.is_emulator:
+            raise CmblError("the host emulator build cannot drive CUDA tensors")
+        if device.type != "cuda" and not lib.is_emulator:
+            raise CmblError("cmblensing.jl_b200 needs a CUDA device (no CPU fallback)")
+        self.lib, self.Ny, self.Nx, self.θpix, self.T, self.device = lib, Ny, Nx, θpix, T, device
+        self.dtype_code = 0 if T == torch.float32 else 1
+        self.cT = _TORCH_CPLX[self.dtype_code]
+        self.handle = c_void_p()
+        dev_index = device.index or 0
+        lib.call("cmbl_plan_create", byref(self.handle), dev_index, Ny, Nx, c_double(θpix), self.dtype_code)
+        npT = _NP_REAL[self.dtype_code]
+        Nyh = Ny // 2 + 1
+        self.ℓx, self.ℓy, self.λ_rfft = np.zeros(Nx, npT), np.zeros(Nyh, npT), np.zeros(Nyh, npT)
+        self.sin2ϕ, self.cos2ϕ = np.zeros((Nx, Nyh), npT), np.zeros((Nx, Nyh), npT)
+        sc = (c_double * 5)()
+        P = lambda a: a.ctypes.data_as(c_void_p)
+        lib.call("cmbl_plan_grids", self.handle, P(self.ℓx), P(self.ℓy), P(self.λ_rfft), P(self.sin2ϕ), P(self.cos2ϕ), sc)
+        self.Δx, self.Δℓx, self.Δℓy, self.Ωpix, self.nyquist = (float(v) for v in sc)
+        self.ℓmag = np.sqrt(self.ℓx[:, None] ** 2 + self.ℓy[None, :] ** 2).astype(npT)     # :65
+
+    @property
+    def Nyh(self):
+        return self.Ny // 2 + 1
+
+    def map_shape(self, Npol, Nb):
+        return (Nb, Npol, self.Nx, self.Ny)
+
+    def fourier_shape(self, Npol, Nb):
+        return (Nb, Npol, self.Nx, self.Nyh)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fields (src/base_fields.jl:14-21; bases src/generic.jl:9-16)
+# ------------------------------------------------------------------------------------------------------------------
+_BASES = {"Map": (1, False, None), "Fourier": (1, True, None), "QUMap": (2, False, "QU"), "QUFourier": (2, True, "QU"),
+          "EBMap": (2, False, "EB"), "EBFourier": (2, True, "EB")}
+
+
+class Field:
+    """BaseField{B,M,T,A}: an array plus ProjLambert metadata, tagged with its basis."""
+
+    def __init__(self, basis: str, arr: torch.Tensor, proj: ProjLambert):
+        if basis not in _BASES:
+            raise CmblError(f"unknown basis {basis}")
+        npol, four, _ = _BASES[basis]
+        if arr.dim() == 2:
+            arr = arr[None, None]
+        elif arr.dim() == 3:
+            arr = arr[None]
+        want = proj.fourier_shape(npol, arr.shape[0]) if four else proj.map_shape(npol, arr.shape[0])
+        if tuple(arr.shape) != tuple(want):
+            raise CmblError(f"Size-mismatched array {tuple(arr.shape)} and metadata {want} in Field constructor.")   # base_fields.jl:19
+        want_dt = proj.cT if four else proj.T
+        self.basis, self.proj = basis, proj
+        self.arr = arr.to(device=proj.device, dtype=want_dt).contiguous()
+
+    # -- metadata -------------------------------------------------------------------------------------------
+    @property
+    def Npol(self): return _BASES[self.basis][0]
+    @property
+    def is_fourier(self): return _BASES[self.basis][1]
+    @property
+    def Nbatch(self): return self.arr.shape[0]
+    @property
+    def C(self): return self.arr.shape[0] * self.arr.shape[1]
+
+    def _like(self, arr, basis=None):
+        return Field(basis or self.basis, arr, self.proj)
+
+    def _check(self, o):
+        if o.proj is not self.proj:
+            raise CmblError("Can't broadcast fields with mismatched metadata (src/proj_lambert.jl:111-114)")
+
+    # -- broadcast-style arithmetic (generic, not the hot path) ------------------------------------------------
+    def _bin(self, o, fn):
+        if isinstance(o, Field):
+            self._check(o)
+            o = convert(o, self.basis).arr
+        elif isinstance(o, (list, tuple, np.ndarray, torch.Tensor)):                 # BatchedReal (src/batching.jl:9-45)
+            o = torch.as_tensor(o, device=self.arr.device, dtype=self.proj.T).reshape(-1, 1, 1, 1)
+        return self._like(fn(self.arr, o))
+
+    def __add__(self, o): return self._bin(o, torch.add)
+    def __sub__(self, o): return self._bin(o, torch.sub)
+    def __mul__(self, o): return self._bin(o, torch.mul)
+    def __truediv__(self, o): return self._bin(o, torch.div)
+    __radd__ = __add__
+    __rmul__ = __mul__
+    def __neg__(self): return self._like(-self.arr)
+    def __rsub__(self, o): return (-self) + o
+    def zero(self): return self._like(torch.zeros_like(self.arr))
+    def copy(self): return self._like(self.arr.clone())
+    def cpu_numpy(self): return self.arr.detach().cpu().numpy()
+    def batch_index(self, i): return self._like(self.arr[i:i + 1].clone())                  # src/proj_lambert.jl:456-459
+    def __repr__(self): return f"Flat{self.basis}(Ny={self.proj.Ny}, Nx={self.proj.Nx}, Nbatch={self.Nbatch}, T={self.proj.T})"
+
+
+def _mk(basis):
+    def ctor(arr, proj=None, θpix=1.0, device="cuda:0", lib=None):
+        if isinstance(arr, np.ndarray):
+            arr = torch.from_numpy(np.ascontiguousarray(arr))
+        if proj is None:
+            Nx, Ny = arr.shape[-2], arr.shape[-1]
+            if _BASES[basis][1]:
+                raise CmblError("pass proj= when constructing a Fourier-basis field (Ny is ambiguous)")
+            T = torch.float64 if arr.dtype in (torch.float64, torch.complex128) else torch.float32
+            proj = ProjLambert(Ny, Nx, θpix, T, device, lib)
+        return Field(basis, arr, proj)
+    ctor.__name__ = "Flat" + basis
+    return ctor
+
+
+FlatMap, FlatFourier, FlatQUMap, FlatQUFourier, FlatEBMap, FlatEBFourier = (
+    _mk(b) for b in ("Map", "Fourier", "QUMap", "QUFourier", "EBMap", "EBFourier"))
+
+
+def batch(fields):
+    """batch(fs...) — concatenate along the batch dimension (src/proj_lambert.jl:446-449)."""
+    f0 = fields[0]
+    return f0._like(torch.cat([f.arr for f in fields], dim=0))
+
+
+def unbatch(f):
+    return [f.batch_index(i) for i in range(f.Nbatch)]
+
+
+# -- basis conversion: the FFT call sites (src/proj_lambert.jl:245-300) -------------------------------------------------
+def _fft(f: Field, inverse: bool) -> torch.Tensor:
+    p = f.proj
+    if inverse:
+        out = torch.empty(p.map_shape(f.Npol, f.Nbatch), dtype=p.T, device=p.device)
+        p.lib.call("cmbl_irfft2", p.handle, _ptr(f.arr), _ptr(out), f.C, _stream(out))
+    else:
+        out = torch.empty(p.fourier_shape(f.Npol, f.Nbatch), dtype=p.cT, device=p.device)
+        p.lib.call("cmbl_rfft2", p.handle, _ptr(f.arr), _ptr(out), f.C, _stream(out))
+    return out
+
+
+def _rot(f: Field, to_eb: bool) -> torch.Tensor:
+    p = f.proj
+    out = torch.empty_like(f.arr)
+    p.lib.call("cmbl_qu_eb", p.handle, 1 if to_eb else 0, _ptr(f.arr), _ptr(out), f.Nbatch, 2, 0, _stream(out))
+    return out
+
+
+def convert(f: Field, basis: str) -> Field:
+    if f.basis == basis:
+        return f
+    npol, four, pb = _BASES[basis]
+    if npol != f.Npol:
+        raise CmblError(f"cannot convert {f.basis} to {basis}")
+    cur = f
+    cur_pb = _BASES[cur.basis][2]
+    if pb != cur_pb:                                  # the rotation lives in Fourier space
+        if not cur.is_fourier:
+            cur = cur._like(_fft(cur, False), cur_pb + "Fourier")
+        cur = cur._like(_rot(cur, to_eb=(pb == "EB")), pb + "Fourier")
+    if cur.is_fourier != four:
+        name = (pb or "") + ("Fourier" if four else "Map")
+        cur = cur._like(_fft(cur, inverse=not four), name)
+    return cur
+
+
+def Map(f): return convert(f, "Map")
+def Fourier(f): return convert(f, "Fourier" if f.Npol == 1 else f.basis.replace("Map", "Fourier"))
+def QUMap(f): return convert(f, "QUMap")
+def QUFourier(f): return convert(f, "QUFourier")
+def EBMap(f): return convert(f, "EBMap")
+def EBFourier(f): return convert(f, "EBFourier")
+def LenseBasis(f): return convert(f, "Map" if f.Npol == 1 else "QUMap")                      # Ł, src/generic.jl:88-93
+def DerivBasis(f): return convert(f, "Fourier" if f.Npol == 1 else "QUFourier")               # Ð
+def HarmonicBasis(f): return convert(f, "Fourier" if f.Npol == 1 else "EBFourier")
+
+
+def dot(a: Field, b: Field) -> np.ndarray:
+    """dot(a,b) (src/proj_lambert.jl:318-328): per-batch values (BatchedReal) as a float64 array."""
+    a._check(b)
+    if a.basis != b.basis:                                          # mixed bases → both to the Ð basis (:328)
+        a, b = DerivBasis(a), DerivBasis(b)
+    p = a.proj
+    nb = max(a.Nbatch, b.Nbatch)
+    if a.Nbatch != b.Nbatch:
+        a = a._like(a.arr.expand(nb, -1, -1, -1).contiguous()); b = b._like(b.arr.expand(nb, -1, -1, -1).contiguous())
+    out = (c_double * nb)()
+    p.lib.call("cmbl_dot", p.handle, FOURIER if a.is_fourier else MAP, _ptr(a.arr), _ptr(b.arr), a.Npol, nb, out, _stream(a.arr))
+    return np.array(out[:], dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# DiagOp (src/specialops.jl:9-22)
+# ------------------------------------------------------------------------------------------------------------------
+class DiagOp:
+    """Diagonal(f): `D * f` converts f to D's basis and multiplies; `D.ldiv(f)` is Julia's `D \\ f` with nan2zero."""
+
+    def __init__(self, diag: Field):
+        d = diag
+        if d.is_fourier and d.arr.is_complex():
+            if float(d.arr.imag.abs().max()) != 0.0:
+                raise CmblError("DiagOp on this path needs a real diagonal (Cf, Cn, B, masks)")
+            self._real = d.arr.real.contiguous()
+        else:
+            self._real = d.arr.contiguous()
+        self.diag = d
+
+    def _apply(self, f: Field, ldiv: bool) -> Field:
+        f = convert(f, self.diag.basis)
+        p = f.proj
+        out = torch.empty_like(f.arr)
+        Cd = self._real.shape[0] * self._real.shape[1]
+        if self._real.shape[0] not in (1, f.Nbatch):
+            raise CmblError("batch sizes must be equal or 1 (src/batching.jl)")
+        p.lib.call("cmbl_diag_mul", p.handle, FOURIER if f.is_fourier else MAP, _ptr(self._real), Cd, _ptr(f.arr), _ptr(out),
+                   f.C, 1 if ldiv else 0, _stream(out))
+        return f._like(out)
+
+    def __mul__(self, f): return self._apply(f, False)
+    def ldiv(self, f): return self._apply(f, True)
+
+    def pinv(self):
+        r = torch.where(self._real == 0, torch.zeros_like(self._real), 1 / self._real)
+        return DiagOp(Field(self.diag.basis, r.to(self.diag.arr.dtype), self.diag.proj))
+
+
+Diagonal = DiagOp
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LenseFlow (src/lenseflow.jl:19-60, src/flowops.jl:11-14)
+# ------------------------------------------------------------------------------------------------------------------
+class CachedLenseFlow:
+    def __init__(self, ϕ: Field, n: int, Npol: int, Nb_f: int, with_minv=False):
+        if ϕ.Npol != 1:
+            raise CmblError("ϕ must be a spin-0 field")
+        p = ϕ.proj
+        self.proj, self.n, self.Npol, self.Nb_f, self.Nb_ϕ, self.ϕ = p, n, Npol, Nb_f, ϕ.Nbatch, ϕ
+        self.handle = c_void_p()
+        p.lib.call("cmbl_lenseflow_create", byref(self.handle), p.handle, n, Npol, Nb_f, ϕ.Nbatch)
+        p.lib.call("cmbl_lenseflow_precompute", self.handle, _ptr(ϕ.arr), FOURIER if ϕ.is_fourier else MAP,
+                   1 if with_minv else 0, _stream(ϕ.arr))
+        self.with_minv = with_minv
+
+    def __del__(self):
+        try:
+            self.proj.lib.call("cmbl_lenseflow_destroy", self.handle)
+        except Exception:
+            pass
+
+    def apply(self, op: int, f: Field) -> Field:
+        p = self.proj
+        if op in (OP_L, OP_LINV):
+            f = LenseBasis(f)
+        else:
+            f = DerivBasis(f)
+        out = torch.empty_like(f.arr)
+        p.lib.call("cmbl_lenseflow_apply", self.handle, op, _ptr(f.arr), _ptr(out), _stream(out))
+        return f._like(out)
+
+
+class LenseFlow:
+    """LenseFlow(ϕ, n=7): lazy wrapper; the cache is (re)built when first applied to a field of a new shape
+    (precompute!!, src/lenseflow.jl:80-129)."""
+
+    def __init__(self, ϕ: Field, n: int = 7):
+        self.ϕ, self.n, self._cache = ϕ, n, {}
+
+    def cache(self, f: Field, with_minv=False) -> CachedLenseFlow:
+        key = (f.Npol, f.Nbatch, with_minv)
+        if key not in self._cache:
+            if self.ϕ.Nbatch not in (1, f.Nbatch):
+                raise CmblError("batch sizes must be equal or 1")
+            self._cache[key] = CachedLenseFlow(self.ϕ, self.n, f.Npol, f.Nbatch, with_minv)
+        return self._cache[key]
+
+    def __mul__(self, f): return self.cache(f).apply(OP_L, f)                    # Lϕ * f
+    def ldiv(self, f): return self.cache(f).apply(OP_LINV, f)                    # Lϕ \ f
+    @property
+    def H(self): return _AdjointFlow(self)                                       # Lϕ'
+    adjoint = H
+
+
+class _AdjointFlow:
+    def __init__(self, L): self.L = L
+    def __mul__(self, f): return self.L.cache(f).apply(OP_LH, f)                 # Lϕ' * f
+    def ldiv(self, f): return self.L.cache(f).apply(OP_LHINV, f)                 # Lϕ' \ f
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# DataSet + CG Wiener filter (src/dataset.jl:37-137, src/maximization.jl:17-42, src/numerical_algorithms.jl:73-134)
+# ------------------------------------------------------------------------------------------------------------------
+class BaseDataSet:
+    """The fields of BaseDataSet used by argmaxf_logpdf: d, Cf, Cn, Cn̂, B, B̂, M = Mf∘Mpix, M̂ = Mf, L (src/dataset.jl:37-57).
+    Diagonals are DiagOps over real harmonic-basis fields with batch 1; `Mpix` is a Map-basis DiagOp or None."""
+
+    def __init__(self, d: Field, Cf: DiagOp, Cn: DiagOp, B: DiagOp, Mf: DiagOp, Mpix: DiagOp | None = None,
+                 Cnhat: DiagOp | None = None, Bhat: DiagOp | None = None, L=LenseFlow, nsteps: int = 7):
+        self.d, self.Cf, self.Cn, self.B, self.Mf, self.Mpix = HarmonicBasis(d), Cf, Cn, B, Mf, Mpix
+        self.Cnhat, self.Bhat, self.L, self.nsteps = Cnhat or Cn, Bhat or B, L, nsteps
+        self._cg = {}
+
+    def _solver(self, ϕ: Field):
+        key = id(ϕ)
+        if key in self._cg:
+            return self._cg[key]
+        d = self.d
+        p = d.proj
+        L = self.L(ϕ, self.nsteps) if isinstance(self.L, type) else self.L
+        cache = L.cache(d)                                                    # keyed on (Npol, Nbatch)
+        desc = DatasetDesc(d.Npol, d.Nbatch, *(c_void_p(D._real.data_ptr()) for D in (self.Cf, self.Cn, self.Cnhat, self.B, self.Bhat, self.Mf)),
+                           c_void_p(self.Mpix._real.data_ptr()) if self.Mpix is not None else c_void_p(0), _ptr(d.arr))
+        h = c_void_p()
+        p.lib.call("cmbl_cg_create", byref(h), cache.handle, byref(desc), _stream(d.arr))
+        self._cg.clear()
+        self._cg[key] = (h, cache, L, ϕ)
+        return self._cg[key]
+
+
+def gradientf_logpdf(ds: BaseDataSet, f: Field, ϕ: Field, d: Field | None = None, d_zero=False) -> Field:
+    """gradientf_logpdf(ds; f, ϕ, d) (src/dataset.jl:76-80), returned in the harmonic basis."""
+    h, *_ = ds._solver(ϕ)
+    f = HarmonicBasis(f)
+    out = torch.empty_like(f.arr)
+    p = f.proj
+    dptr = _ptr(HarmonicBasis(d).arr) if d is not None else c_void_p(0)
+    p.lib.call("cmbl_gradientf_logpdf", h, _ptr(f.arr), dptr, 1 if d_zero else 0, _ptr(out), _stream(out))
+    return f._like(out)
+
+
+def Hessian_logpdf_preconditioner(ds: BaseDataSet) -> DiagOp:
+    """pinv(Cf) + B̂'M̂'pinv(Cn̂)M̂B̂ (src/dataset.jl:129-132)."""
+    pinv = lambda t: torch.where(t == 0, torch.zeros_like(t), 1 / t)
+    r = pinv(ds.Cf._real) + ds.Bhat._real * ds.Mf._real * pinv(ds.Cnhat._real) * ds.Mf._real * ds.Bhat._real
+    return DiagOp(Field(ds.Cf.diag.basis, r.to(ds.Cf.diag.arr.dtype), ds.Cf.diag.proj))
+
+
+def conjugate_gradient_wiener(ds: BaseDataSet, ϕ: Field, fstart: Field | None = None, nsteps=500, tol=1e-1, offset=False,
+                              group=None):
+    """conjugate_gradient (src/numerical_algorithms.jl:73-134) specialised to the Wiener-filter Hessian.  Returns
+    (bestx, history) with history = [(i, res[Nb]), ...].  With a torch.distributed `group` the batch is sharded over ranks and
+    the lock-step rules `all(res<bestres)` / `all(res<tol)` are taken across ranks (one tiny all-reduce per iteration)."""
+    h, cache, L, _ = ds._solver(ϕ)
+    p = ds.d.proj
+    nb = ds.d.Nbatch
+    st = _stream(ds.d.arr)
+    res = (c_double * nb)()
+    fs = _ptr(HarmonicBasis(fstart).arr) if fstart is not None else c_void_p(0)
+    out = torch.empty_like(ds.d.arr)
+    if group is None:
+        hist = (c_double * (nsteps * nb))()
+        iters = c_int(0)
+        p.lib.call("cmbl_wiener_cg", h, fs, _ptr(out), nsteps, c_double(tol), 1 if offset else 0, byref(iters), hist, st)
+        H = np.array(hist[: iters.value * nb]).reshape(iters.value, nb)
+        return ds.d._like(out), [(i + 1, H[i]) for i in range(iters.value)]
+    import torch.distributed as dist
+
+    def all_true(flag: bool) -> bool:
+        t = torch.tensor([0 if flag else 1], dtype=torch.int32, device=ds.d.arr.device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return int(t.item()) == 0
+
+    p.lib.call("cmbl_cg_begin", h, fs, 1 if offset else 0, res, st)
+    r = np.array(res[:]); best = r.copy(); hist = [(1, r.copy())]
+    for i in range(2, nsteps + 1):
+        p.lib.call("cmbl_cg_step", h, res, st)
+        r = np.array(res[:])
+        if all_true(bool(np.all(r < best))):
+            best = r.copy()
+            p.lib.call("cmbl_cg_mark_best", h, st)
+        hist.append((i, r.copy()))
+        if all_true(bool(np.all(r < tol))):
+            break
+    p.lib.call("cmbl_cg_result", h, 0, _ptr(out), st)
+    return ds.d._like(out), hist
+
+
+def argmaxf_logpdf(ds: BaseDataSet, ϕ: Field, fstart: Field | None = None, offset=False,
+                   conjgrad_kwargs=dict(tol=1e-1, nsteps=500), group=None):
+    """argmaxf_logpdf(ds, (;ϕ)) (src/maximization.jl:17-42): the Wiener filter of ds.d at fixed ϕ; returns (f, history)."""
+    return conjugate_gradient_wiener(ds, ϕ, fstart=fstart, offset=offset, group=group, **conjgrad_kwargs)
+
+
+argmaxf_lnP = argmaxf_logpdf          # the name BASELINE.json uses (pre-0.10 spelling)

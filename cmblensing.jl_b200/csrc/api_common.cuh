@@ -10,6 +10,7 @@ struct CgBase;     // cg.cuh
 }
 
 struct cmbl_plan { std::unique_ptr<cmbl::PlanBase> p; };
+#define CMBL_FLOW_STRUCT struct cmbl_flow { std::unique_ptr<cmbl::FlowBase> f; cmbl_plan* plan; }
 
 #define CMBL_API_BEGIN try {
 #define CMBL_API_END                                                                          \

@@ -2,7 +2,7 @@
 #include "api_common.cuh"
 #include "flow.cuh"
 
-struct cmbl_flow { std::unique_ptr<cmbl::FlowBase> f; cmbl_plan* plan; };
+CMBL_FLOW_STRUCT;
 
 namespace cmbl {
 template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,

@@ -1,0 +1,245 @@
+// Elementwise / reduction kernels: DiagOp products (src/specialops.jl:9-10), QU<->EB rotation
+// (src/proj_lambert.jl:253-271), dot (src/proj_lambert.jl:318-328) and the fused vector updates of
+// conjugate_gradient (src/numerical_algorithms.jl:99-108).
+#pragma once
+#include "plan.cuh"
+
+namespace cmbl {
+
+constexpr int RED_BLOCKS = 64;      // partial sums per batch item (fixed → deterministic reductions)
+
+template <class T> HD T nan2zero(T v) { return (v - v == (T)0) ? v : (T)0; }          // isfinite(v) ? v : 0
+template <class T> HD C2<T> nan2zero(C2<T> v) {                                       // complex: both parts finite
+    bool fin = (v.x - v.x == (T)0) && (v.y - v.y == (T)0);
+    return fin ? v : mk<T>((T)0, (T)0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DiagOp * f , DiagOp \ f
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, bool CPLX> struct DiagMulBody {
+    static constexpr int NT = 256;
+    size_t plane, total; int Cd; bool ldiv;
+    const T* diag; const void* in; void* out;
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < total) {
+                size_t c = e / plane, r = e - c * plane;
+                T dg = diag[(c % Cd) * plane + r];
+                if (CPLX) {
+                    C2<T> v = reinterpret_cast<const C2<T>*>(in)[e];
+                    v = ldiv ? nan2zero(mk<T>(v.x / dg, v.y / dg)) : mk<T>(dg * v.x, dg * v.y);
+                    reinterpret_cast<C2<T>*>(out)[e] = v;
+                } else {
+                    T v = reinterpret_cast<const T*>(in)[e];
+                    reinterpret_cast<T*>(out)[e] = ldiv ? nan2zero(v / dg) : dg * v;
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused Fourier-space chain on harmonic-basis fields (Npol = 1: no rotation; Npol = 2: planes (E,B) / (Q,U)):
+//   v = in;  v *= din;  v = d − v (or −v when neg);  v *= pre;  v = Rot(v);  v *= post;  v −= sdiag·sub;  out = v
+// every diagonal is REAL with Npol planes shared across the batch (NULL = skip).
+// rot: 0 none, 1 EB→QU, 2 QU→EB  (src/proj_lambert.jl:253-271)
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct FourierChainBody {
+    static constexpr int NT = 256;
+    int Npol, Nb; size_t nf; int rot; bool neg;
+    const T *sin2phi, *cos2phi;
+    const C2<T>* in; const T* din; const C2<T>* d; const T* pre; const T* post; const T* sdiag; const C2<T>* sub; C2<T>* out;
+    HD C2<T> head(C2<T> v, size_t r, int pol, size_t e) const {
+        if (din) v = cscale(v, din[pol * nf + r]);
+        if (d) v = d[e] - v; else if (neg) v = mk<T>(-v.x, -v.y);
+        if (pre) v = cscale(v, pre[pol * nf + r]);
+        return v;
+    }
+    HD C2<T> tail(C2<T> v, size_t r, int pol, size_t e) const {
+        if (post) v = cscale(v, post[pol * nf + r]);
+        if (sub) v = v - cscale(sub[e], sdiag[pol * nf + r]);
+        return v;
+    }
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t t = (size_t)blk * NT + tid;
+            if (Npol == 2) {
+                if (t < nf * Nb) {
+                    size_t b = t / nf, r = t - b * nf;
+                    size_t e0 = (b * 2) * nf + r, e1 = e0 + nf;
+                    C2<T> a = head(in[e0], r, 0, e0), c = head(in[e1], r, 1, e1);
+                    if (rot) {
+                        T s = sin2phi[r], co = cos2phi[r];
+                        C2<T> na, nc;
+                        if (rot == 1) {      // Q = −E c + B s ; U = −E s − B c
+                            na = mk<T>(-a.x * co + c.x * s, -a.y * co + c.y * s);
+                            nc = mk<T>(-a.x * s - c.x * co, -a.y * s - c.y * co);
+                        } else {             // E = −Q c − U s ; B = Q s − U c
+                            na = mk<T>(-a.x * co - c.x * s, -a.y * co - c.y * s);
+                            nc = mk<T>(a.x * s - c.x * co, a.y * s - c.y * co);
+                        }
+                        a = na; c = nc;
+                    }
+                    out[e0] = tail(a, r, 0, e0); out[e1] = tail(c, r, 1, e1);
+                }
+            } else {
+                if (t < nf * Nb * Npol) {
+                    size_t cpl = t / nf, r = t - cpl * nf;
+                    int pol = (int)(cpl % Npol);
+                    out[t] = tail(head(in[t], r, pol, t), r, pol, t);
+                }
+            }
+        }
+    }
+};
+
+// standalone rotation with arbitrary plane stride (cmbl_qu_eb)
+template <class T> struct QuEbBody {
+    static constexpr int NT = 256;
+    int Nb, stride_planes, first_plane, dir; size_t nf;
+    const T *sin2phi, *cos2phi; const C2<T>* in; C2<T>* out;
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t t = (size_t)blk * NT + tid;
+            if (t < nf * Nb) {
+                size_t b = t / nf, r = t - b * nf;
+                size_t e0 = (b * stride_planes + first_plane) * nf + r, e1 = e0 + nf;
+                C2<T> a = in[e0], c = in[e1];
+                T s = sin2phi[r], co = cos2phi[r];
+                if (dir == 0) { out[e0] = mk<T>(-a.x * co + c.x * s, -a.y * co + c.y * s); out[e1] = mk<T>(-a.x * s - c.x * co, -a.y * s - c.y * co); }
+                else { out[e0] = mk<T>(-a.x * co - c.x * s, -a.y * co - c.y * s); out[e1] = mk<T>(a.x * s - c.x * co, a.y * s - c.y * co); }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// dot: partial[b][j] (double), j < RED_BLOCKS.   Fourier: Σ Re(conj(a) b) λ[ky] / (Ny Nx);  Map: Σ a b
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, bool CPLX> struct DotBody {
+    static constexpr int NT = 256;
+    size_t per_batch; int Nyh; const T* lam; double scale;
+    const void* a; const void* b; double* partial;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        double* sm = reinterpret_cast<double*>(smem);
+        const int bi = blk / RED_BLOCKS, j = blk % RED_BLOCKS;
+        const size_t base = (size_t)bi * per_batch;
+        CMBL_FOR_THREADS(tid, NT) {
+            double s = 0;
+            for (size_t e = (size_t)j * NT + tid; e < per_batch; e += (size_t)RED_BLOCKS * NT) {
+                if (CPLX) {
+                    C2<T> x = reinterpret_cast<const C2<T>*>(a)[base + e], y = reinterpret_cast<const C2<T>*>(b)[base + e];
+                    s += ((double)x.x * (double)y.x + (double)x.y * (double)y.y) * (double)lam[e % Nyh];
+                } else {
+                    s += (double)reinterpret_cast<const T*>(a)[base + e] * (double)reinterpret_cast<const T*>(b)[base + e];
+                }
+            }
+            sm[tid] = s;
+        }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) {
+            if (tid == 0) { double s = 0; for (int i = 0; i < NT; ++i) s += sm[i]; partial[blk] = s * scale; }
+        }
+    }
+};
+
+HD double sum_partials(const double* p) { double s = 0; for (int i = 0; i < RED_BLOCKS; ++i) s += p[i]; return s; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// CG update 1 (numerical_algorithms.jl:101-105):  α = res/Σ pAp;  x += α p;  r −= α Ap;  z = M \ r;  partial(res′ = r·z)
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct CgUpdate1Body {
+    static constexpr int NT = 256;
+    size_t per_batch, nf; int Npol, Nyh; const T* lam; double scale;
+    const double* res; const double* pAp_part; const T* Mdiag;
+    const C2<T>* p; const C2<T>* Ap; C2<T>* x; C2<T>* r; C2<T>* z; double* res_part;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        double* sm = reinterpret_cast<double*>(smem);
+        const int bi = blk / RED_BLOCKS, j = blk % RED_BLOCKS;
+        const size_t base = (size_t)bi * per_batch;
+        CMBL_FOR_THREADS(tid, NT) {
+            const T alpha = (T)(res[bi] / sum_partials(pAp_part + (size_t)bi * RED_BLOCKS));
+            double s = 0;
+            for (size_t e = (size_t)j * NT + tid; e < per_batch; e += (size_t)RED_BLOCKS * NT) {
+                C2<T> pv = p[base + e], av = Ap[base + e], xv = x[base + e], rv = r[base + e];
+                xv = mk<T>(xv.x + alpha * pv.x, xv.y + alpha * pv.y);
+                rv = mk<T>(rv.x - alpha * av.x, rv.y - alpha * av.y);
+                T m = Mdiag[e];                                   // Npol planes, shared across the batch
+                C2<T> zv = nan2zero(mk<T>(rv.x / m, rv.y / m));
+                x[base + e] = xv; r[base + e] = rv; z[base + e] = zv;
+                s += ((double)rv.x * (double)zv.x + (double)rv.y * (double)zv.y) * (double)lam[e % Nyh];
+            }
+            sm[tid] = s;
+        }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) {
+            if (tid == 0) { double s = 0; for (int i = 0; i < NT; ++i) s += sm[i]; res_part[blk] = s * scale; }
+        }
+    }
+};
+
+// CG update 2 (:106-107):  res′ = Σ partial;  p = z + (res′/res) p;  res_out[b] = res′
+template <class T> struct CgUpdate2Body {
+    static constexpr int NT = 256;
+    size_t per_batch; const double* res; const double* res_part; double* res_out;
+    const C2<T>* z; C2<T>* p;
+    DEV void operator()(int blk, unsigned char*) const {
+        const int bi = blk / RED_BLOCKS, j = blk % RED_BLOCKS;
+        const size_t base = (size_t)bi * per_batch;
+        CMBL_FOR_THREADS(tid, NT) {
+            const double rn = sum_partials(res_part + (size_t)bi * RED_BLOCKS);
+            const T beta = (T)(rn / res[bi]);
+            for (size_t e = (size_t)j * NT + tid; e < per_batch; e += (size_t)RED_BLOCKS * NT) {
+                C2<T> zv = z[base + e], pv = p[base + e];
+                p[base + e] = mk<T>(zv.x + beta * pv.x, zv.y + beta * pv.y);
+            }
+            if (j == 0 && tid == 0) res_out[bi] = rn;
+        }
+    }
+};
+
+// r = b − Ax ; z = M \ r ; p = z ; partial(res = r·z)   (numerical_algorithms.jl:89-92)
+template <class T> struct CgInitBody {
+    static constexpr int NT = 256;
+    size_t per_batch; int Nyh; const T* lam; double scale; const T* Mdiag;
+    const C2<T>* b; const C2<T>* Ax; C2<T>* r; C2<T>* z; C2<T>* p; double* res_part;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        double* sm = reinterpret_cast<double*>(smem);
+        const int bi = blk / RED_BLOCKS, j = blk % RED_BLOCKS;
+        const size_t base = (size_t)bi * per_batch;
+        CMBL_FOR_THREADS(tid, NT) {
+            double s = 0;
+            for (size_t e = (size_t)j * NT + tid; e < per_batch; e += (size_t)RED_BLOCKS * NT) {
+                C2<T> rv = b[base + e];
+                if (Ax) rv = rv - Ax[base + e];
+                T m = Mdiag[e];
+                C2<T> zv = nan2zero(mk<T>(rv.x / m, rv.y / m));
+                r[base + e] = rv; z[base + e] = zv; p[base + e] = zv;
+                s += ((double)rv.x * (double)zv.x + (double)rv.y * (double)zv.y) * (double)lam[e % Nyh];
+            }
+            sm[tid] = s;
+        }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) {
+            if (tid == 0) { double s = 0; for (int i = 0; i < NT; ++i) s += sm[i]; res_part[blk] = s * scale; }
+        }
+    }
+};
+
+// res_out[b] = Σ partial[b][:]
+struct SumPartialsBody {
+    static constexpr int NT = 32;
+    int Nb; const double* part; double* out;
+    DEV void operator()(int, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) { for (int b = tid; b < Nb; b += NT) out[b] = sum_partials(part + (size_t)b * RED_BLOCKS); }
+    }
+};
+
+template <class T> void diag_mul(PlanT<T>& P, int basis, const T* diag, int Cd, const void* in, void* out, int C, bool ldiv, cmblStream_t st);
+template <class T> void qu_eb(PlanT<T>& P, int dir, const C2<T>* in, C2<T>* out, int Nb, int stride_planes, int first_plane, cmblStream_t st);
+// per-batch dot into device partial sums; returns pointer to partial[Nb][RED_BLOCKS] (plan scratch)
+template <class T> void dot_partials(PlanT<T>& P, int basis, const void* a, const void* b, int Npol, int Nb, double* partial, cmblStream_t st);
+
+}  // namespace cmbl

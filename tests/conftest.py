@@ -1,4 +1,7 @@
-import os, sys
+import os
+import subprocess
+import sys
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -6,6 +9,32 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
+EMU_PATH = os.path.join(ROOT, "tests", "_emu", "libcmbl_emu.so")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    import __graft_entry__ as g
+    return g.load_package()
+
+
+@pytest.fixture(scope="session")
+def emu(pkg):
+    """Host emulator build of the CUDA kernel sources (g++ -DCMBL_EMU): lets the CPU suite check kernel index logic
+    against the oracle.  Test infrastructure only — the package never loads it by itself."""
+    csrc = os.path.join(ROOT, "cmblensing.jl_b200", "csrc")
+    subprocess.run(["make", "-C", csrc, "-j", str(os.cpu_count() or 2), "emu"], check=True, stdout=subprocess.DEVNULL)
+    return pkg._lib.Library(EMU_PATH)
+
+
+@pytest.fixture(scope="session")
+def cuda_pkg(pkg):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    pkg.load()          # raises loudly if libcmbl_b200.so is missing: there is no fallback
+    return pkg

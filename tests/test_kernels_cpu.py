@@ -1,0 +1,175 @@
+"""CPU unit tests of the CUDA kernel sources through the host emulator build (same .cu files, g++ -DCMBL_EMU), checked
+against the oracle.  These validate index arithmetic / algorithm structure without a GPU; the `-m gpu` tests repeat the
+comparisons on the real sm_100a library."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import cmbl_oracle as O
+from common import make_problem, relerr, T_of
+
+SIZES = [(8, 8), (4, 8), (8, 4), (32, 16), (64, 128), (128, 64)]        # runtests.jl:52-53 incl. non-square, tiny
+TOL = {"f64": 1e-12, "f32": 2e-5}
+
+
+def test_abi_exports_every_symbol(pkg):
+    """The C-ABI header and the loader agree; the built libraries export every declared symbol."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "cmbl_b200.h")).read()
+    declared = set(re.findall(r"\b(cmbl_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(pkg._lib.SIGNATURES), declared ^ set(pkg._lib.SIGNATURES)
+    so = os.path.join(root, "cmblensing.jl_b200", "libcmbl_b200.so")
+    if os.path.exists(so):                      # loads without a GPU; no compute calls
+        lib = ctypes.CDLL(so)
+        for name in declared:
+            assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(pkg.CmblError):
+        pkg.ProjLambert(16, 16, 1.0, torch.float64, "cpu", pkg._lib.Library(pkg._lib.DEFAULT_PATH)) if __import__("os").path.exists(pkg._lib.DEFAULT_PATH) \
+            else pkg._lib.Library(pkg._lib.DEFAULT_PATH)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("Ny,Nx", SIZES + [(256, 256), (512, 8), (8, 2048)])
+def test_rfft2_irfft2(pkg, emu, Ny, Nx, dtype):
+    npT, tT = T_of(dtype)
+    rng = np.random.default_rng(0)
+    proj = pkg.ProjLambert(Ny, Nx, 2.0, tT, "cpu", emu)
+    a = rng.standard_normal((3, 1, Nx, Ny)).astype(npT)
+    f = pkg.batch([pkg.FlatMap(a[i], proj) for i in range(3)])
+    F = pkg.Fourier(f)
+    ref = O.rfft2(a.astype(np.float64))
+    assert relerr(F.cpu_numpy(), ref) < TOL[dtype]
+    # inverse of a NON-Hermitian spectrum: c2r must ignore Im of the ky = 0, Ny/2 rows like FFTW/cuFFT
+    G = (ref + rng.standard_normal(ref.shape) + 1j * rng.standard_normal(ref.shape))
+    g = pkg.Field("Fourier", torch.from_numpy(G), proj)
+    keep = g.arr.clone()
+    back = pkg.Map(g)
+    assert torch.equal(keep, g.arr)                                   # input untouched (util_fft.jl:44)
+    assert relerr(back.cpu_numpy(), O.irfft2(G, Ny)) < TOL[dtype]
+    assert relerr(pkg.Map(pkg.Fourier(f)).cpu_numpy(), a) < TOL[dtype]   # Bin(Bout(Bin(f))) ≈ f, runtests.jl:116-131
+
+
+@pytest.mark.parametrize("Ny,Nx", [(8, 8), (64, 32)])
+def test_grids_match_oracle(pkg, emu, Ny, Nx):
+    for dtype in ("f64", "f32"):
+        npT, tT = T_of(dtype)
+        p = pkg.ProjLambert(Ny, Nx, 3.0, tT, "cpu", emu)
+        o = O.ProjLambert(Ny, Nx, 3.0, npT)
+        assert np.array_equal(p.ℓx, o.lx) and np.array_equal(p.ℓy, o.ly) and np.array_equal(p.λ_rfft, o.lam_rfft.astype(npT))
+        assert p.ℓy[-1] < 0                                           # Nyquist carries negative ℓ (proj_lambert.jl:63)
+        assert np.allclose(p.sin2ϕ, o.sin2phi, atol=4 * np.finfo(npT).eps) and np.allclose(p.cos2ϕ, o.cos2phi, atol=4 * np.finfo(npT).eps)
+        assert np.isclose(p.Ωpix, float(o.omega_pix), rtol=1e-7)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_qu_eb_diag_dot(pkg, emu, dtype):
+    pr = make_problem(pkg, 32, 16, "P", dtype, nb=2, lib=emu)
+    f, oproj = pr["f"], pr["oproj"]
+    fo = pr["sim"]["f"]
+    qu = pkg.QUFourier(f)
+    assert relerr(qu.cpu_numpy(), O.eb_to_qu(oproj, fo)) < TOL[dtype]
+    assert relerr(pkg.EBFourier(qu).cpu_numpy(), fo) < 10 * TOL[dtype]
+    assert relerr(pkg.QUMap(f).cpu_numpy(), O.to_lense_basis("P", oproj, fo)) < TOL[dtype]
+    Cf = pr["ds"].Cf
+    assert relerr((Cf * f).cpu_numpy(), pr["dso"].Cf * fo) < TOL[dtype]
+    assert relerr(Cf.ldiv(f).cpu_numpy(), O.diag_ldiv(pr["dso"].Cf, fo)) < TOL[dtype]      # nan2zero at the ℓ=0 mode
+    assert np.all(np.isfinite(Cf.ldiv(f).cpu_numpy()))
+    assert np.allclose(pkg.dot(f, f), O.dot_fourier(oproj, fo, fo), rtol=1e-12 if dtype == "f64" else 1e-5)
+    m = pkg.QUMap(f)
+    assert np.allclose(pkg.dot(m, m), O.dot_map(m.cpu_numpy(), m.cpu_numpy()), rtol=1e-12 if dtype == "f64" else 1e-5)
+    # dot is basis independent (Parseval with λ_rfft), runtests.jl:183-184
+    assert np.allclose(pkg.dot(m, m), pkg.dot(qu, qu), rtol=1e-10 if dtype == "f64" else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(8, 8, "I", 1, 1), (4, 8, "I", 2, 2), (8, 4, "P", 1, 1), (32, 16, "I", 1, 1),
+                                                 (16, 64, "P", 2, 2), (64, 64, "P", 3, 1), (128, 64, "I", 2, 1)])
+def test_lenseflow_all_ops(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
+    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=4, mask=False, seed=3, lib=emu)
+    L = pkg.LenseFlow(pr["phi"], 4)
+    Lo, oproj = pr["Lo"], pr["oproj"]
+    rng = np.random.default_rng(1)
+    fm = O.to_lense_basis(pol, oproj, pr["sim"]["f"])
+    F0 = O.rfft2(fm)
+    Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
+    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, "Fourier" if pol == "I" else "QUFourier")
+    tol = 1e-11 if dtype == "f64" else 2e-5                 # SURVEY §8c tolerances
+    assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
+    assert relerr(L.ldiv(fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LINV, fm)) < tol
+    assert relerr((L.H * ffour).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LH, Fn)) < tol
+    assert relerr(L.H.ldiv(ffour).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LHINV, Fn)) < tol
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("pol", ["I", "P"])
+def test_lenseflow_adjoint_identity(pkg, emu, pol, dtype):
+    """f'(Lϕ g) ≈ (f'Lϕ) g  (runtests.jl:556,570)."""
+    pr = make_problem(pkg, 64, 32, pol, dtype, nb=1, nsteps=7, mask=False, seed=5, lib=emu)
+    L = pkg.LenseFlow(pr["phi"], 7)
+    g = pkg.LenseBasis(pr["f"])
+    rng = np.random.default_rng(2)
+    f = pr["F"](rng.standard_normal(g.arr.shape), pr["lense"])
+    lhs = pkg.dot(f, L * g)
+    rhs = pkg.dot(L.H * pkg.DerivBasis(f), pkg.DerivBasis(g))
+    assert np.allclose(lhs, rhs, rtol=1e-11 if dtype == "f64" else 5e-4)
+
+
+@pytest.mark.parametrize("dtype,pol,mask", [("f64", "I", False), ("f64", "P", True), ("f64", "I", True), ("f32", "P", True)])
+def test_gradientf_and_cg(pkg, emu, dtype, pol, mask):
+    pr = make_problem(pkg, 32, 32, pol, dtype, nb=2, nsteps=3, mask=mask, seed=7, theta=3.0, lib=emu)
+    ds, dso, f = pr["ds"], pr["dso"], pr["f"]
+    g = pkg.gradientf_logpdf(ds, f, pr["phi"])
+    go = O.gradientf_logpdf(dso, pr["sim"]["f"], dso.d)
+    tol = 1e-10 if dtype == "f64" else 1e-4
+    assert relerr(g.cpu_numpy(), go) < tol
+    pre = pkg.Hessian_logpdf_preconditioner(ds)
+    assert relerr(pre._real.numpy(), O.hess_preconditioner(dso)) < (1e-13 if dtype == "f64" else 1e-6)
+    n_it = 6
+    x, hist = pkg.argmaxf_logpdf(ds, pr["phi"], conjgrad_kwargs=dict(tol=0.0, nsteps=n_it))
+    xo, histo = O.argmaxf_logpdf(dso, nsteps=n_it, tol=0.0)
+    assert len(hist) == len(histo) == n_it
+    for (i, r), (io, ro) in zip(hist, histo):
+        assert i == io and np.allclose(r, ro, rtol=1e-9 if dtype == "f64" else 2e-3)
+    assert relerr(x.cpu_numpy(), xo) < (1e-9 if dtype == "f64" else 2e-3)
+
+
+def test_cg_stops_on_tol_like_reference(pkg, emu):
+    pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=emu)
+    _, h0 = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=0.0)
+    tol = float(np.max(h0[12][1])) * 1.0001              # reached (for all batch items) around iteration 13
+    x, hist = pkg.argmaxf_logpdf(pr["ds"], pr["phi"], conjgrad_kwargs=dict(tol=tol, nsteps=30))
+    xo, histo = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=tol)
+    assert len(hist) == len(histo) < 30
+    assert relerr(x.cpu_numpy(), xo) < 1e-9
+
+
+def test_error_behaviour(pkg, emu):
+    proj = pkg.ProjLambert(8, 8, 1.0, torch.float64, "cpu", emu)
+    with pytest.raises(pkg.CmblError):                                    # size mismatch, runtests.jl:113 / base_fields.jl:19
+        pkg.Field("Map", torch.zeros(1, 1, 8, 4, dtype=torch.float64), proj)
+    with pytest.raises(pkg.CmblError):
+        pkg.ProjLambert(12, 8, 1.0, torch.float64, "cpu", emu)            # non power of two
+    p2 = pkg.ProjLambert(8, 8, 2.0, torch.float64, "cpu", emu)
+    a = pkg.FlatMap(np.zeros((8, 8)), proj); b = pkg.FlatMap(np.zeros((8, 8)), p2)
+    with pytest.raises(pkg.CmblError):                                    # mismatched metadata, proj_lambert.jl:111-114
+        a + b
+    phi = pkg.batch([a, a, a]); f = pkg.batch([a, a])
+    with pytest.raises(pkg.CmblError):                                    # batch 3 vs 2 cannot broadcast
+        pkg.LenseFlow(phi) * f
+
+
+def test_golden_fixture_emulator(pkg, emu):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lenseflow_golden.npz"))
+    proj = pkg.ProjLambert(int(z["Ny"]), int(z["Nx"]), float(z["theta"]), torch.float64, "cpu", emu)
+    L = pkg.LenseFlow(pkg.Field("Fourier", torch.from_numpy(z["phi"]), proj), int(z["nsteps"]))
+    f = pkg.Field("QUMap", torch.from_numpy(z["f_qumap"]), proj)
+    assert relerr((L * f).cpu_numpy(), z["L_f"]) < 1e-12
+    assert relerr((L.H * pkg.QUFourier(f)).cpu_numpy(), z["LH_f"]) < 1e-12
+    assert relerr(L.ldiv(f).cpu_numpy(), z["Linv_f"]) < 1e-12
