@@ -31,6 +31,8 @@ SIGNATURES = {
     "cmbl_last_error": (c_char_p, []),
     "cmbl_version": (c_char_p, []),
     "cmbl_launch_count": (c_longlong, []),
+    "cmbl_profile_begin": (c_int, []),
+    "cmbl_profile_end": (c_char_p, []),
     "cmbl_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_double, c_int]),
     "cmbl_plan_destroy": (c_int, [c_void_p]),
     "cmbl_plan_grids": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double)]),

@@ -3,7 +3,9 @@
 #include "fft2d.cuh"
 
 namespace cmbl {
+std::string prof_report();
 static thread_local std::string t_last_error;
+static std::string g_prof_text;
 void set_last_error(const std::string& s) { t_last_error = s; }
 }
 
@@ -20,6 +22,14 @@ const char* cmbl_version(void) {
 }
 
 long long cmbl_launch_count(void) { return cmbl::g_launch_count; }
+
+int cmbl_profile_begin(void) { cmbl::g_profiling = true; return CMBL_OK; }
+
+const char* cmbl_profile_end(void) {
+    cmbl::g_profiling = false;
+    cmbl::g_prof_text = cmbl::prof_report();
+    return cmbl::g_prof_text.c_str();
+}
 
 int cmbl_plan_create(cmbl_plan** plan, int device, int Ny, int Nx, double theta_pix_arcmin, int dtype) {
     CMBL_API_BEGIN

@@ -5,6 +5,7 @@ namespace cmbl {
 // elementwise helpers for the derived diagonals --------------------------------------------------------------
 template <class T> struct DerivedDiagBody {
     static constexpr int NT = 256;
+    static const char* name() { return "derived_diag"; }
     size_t n; const T *Cf, *Cn, *Cnhat, *B, *Bhat, *Mf;
     T *inv_Cf, *inv_Cn, *inv_Cn_Mf, *precond;
     HD static T pinv(T v) { return v == (T)0 ? (T)0 : (T)1 / v; }

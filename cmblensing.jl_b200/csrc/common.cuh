@@ -159,6 +159,12 @@ struct DevBuf {
 // ---------------------------------------------------------------------------------------------------------------
 extern long long g_launch_count;      // number of kernels of this library launched (bench.py reports it)
 
+// optional per-kernel timing with CUDA events on the launching stream (cmbl_profile_begin / cmbl_profile_end)
+extern bool g_profiling;
+void prof_before(const char* name, cmblStream_t st);
+void prof_after(cmblStream_t st);
+template <class Body> struct KernelName { static const char* get() { return Body::name(); } };
+
 #ifndef CMBL_EMU
 template <class Body> __global__ void __launch_bounds__(Body::NT) kern(const Body b) {
     extern __shared__ __align__(16) unsigned char cmbl_smem[];
@@ -188,7 +194,9 @@ template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStre
         CMBL_CUDA(cudaFuncSetAttribute(kern<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         configured = true;
     }
+    if (g_profiling) prof_before(Body::name(), st);
     kern<Body><<<grid, Body::NT, smem, st>>>(b);
+    if (g_profiling) prof_after(st);
     CMBL_CUDA(cudaGetLastError());
 #endif
 }

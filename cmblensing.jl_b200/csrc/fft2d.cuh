@@ -42,6 +42,7 @@ template <class T> int row_lines(int N, int maxL) {
 // ---------------------------------------------------------------------------------------------------------------
 template <class T> struct R2CColBody {
     static constexpr int NT = 256;
+    static const char* name() { return "rfft2_cols"; }
     Fft1D<T> fy; int Ny, Nx, Nyh, L, tiles_per_plane;
     const T* in; C2<T>* out;
     DEV void operator()(int blk, unsigned char* smem) const {
@@ -75,6 +76,7 @@ template <class T> struct R2CColBody {
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool INV> struct C2CRowBody {
     static constexpr int NT = 256;
+    static const char* name() { return "fft2_rows"; }
     Fft1D<T> fx; int Nx, Nyh, L, tiles_per_plane;
     const C2<T>* in; C2<T>* out;
     DEV void operator()(int blk, unsigned char* smem) const {
@@ -106,6 +108,7 @@ template <class T, bool INV> struct C2CRowBody {
 // ---------------------------------------------------------------------------------------------------------------
 template <class T> struct C2RColBody {
     static constexpr int NT = 256;
+    static const char* name() { return "irfft2_cols"; }
     Fft1D<T> fy; int Ny, Nx, Nyh, L, tiles_per_plane; T scale;
     const C2<T>* in; T* out;
     DEV void operator()(int blk, unsigned char* smem) const {

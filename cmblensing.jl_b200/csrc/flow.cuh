@@ -41,6 +41,7 @@ template <class T, bool ADJ> struct RowMid {
 
 template <class T, bool ADJ> struct FlowRowBody {
     static constexpr int NT = 256;
+    static const char* name() { return "flow_rows"; }
     Fft1D<T> fx; const T* mult;
     int Ny, Nx, L, tiles_per_plane, Npol, Nbphi;
     const T* u; const T* pk; T* tmp; T* nline; T* nacc; T wgt;
@@ -92,6 +93,7 @@ template <class T, bool ADJ> struct ColMid {
 
 template <class T, bool ADJ> struct FlowColBody {
     static constexpr int NT = 256;
+    static const char* name() { return "flow_cols"; }
     Fft1D<T> fy; const T* mult_d; const T* mult_s;
     int Ny, Nx, L, tiles_per_plane, Npol, Nbphi;
     const T* u; const T* pk; const T* tmp; const T* nline; T* macc; T wgt; T cN;
@@ -142,6 +144,7 @@ template <class T, bool ADJ> struct FlowColBody {
 // rows0[c][r][kx] = Y[c][kx][r ? Ny/2 : 0]
 template <class T> struct AdjRowsSaveBody {
     static constexpr int NT = 256;
+    static const char* name() { return "adj_rows_save"; }
     int Nx, Nyh; const C2<T>* Y; C2<T>* rows0;
     DEV void operator()(int blk, unsigned char*) const {
         CMBL_FOR_THREADS(tid, NT) {
@@ -156,6 +159,7 @@ template <class T> struct AdjRowsSaveBody {
 // out = rfft2(y_final) + (I − P)·Y₀ + Nyquist accumulators   (one block per plane; see header comment)
 template <class T> struct AdjFixBody {
     static constexpr int NT = 256;
+    static const char* name() { return "adj_fix"; }
     Fft1D<T> fx; int Ny, Nx, Nyh; T lxN, lyN;
     const C2<T>* rows0; const T* nacc; const T* macc; C2<T>* out;
     DEV void operator()(int blk, unsigned char* smem) const {
@@ -200,6 +204,7 @@ template <class T> struct AdjFixBody {
 // Φ[bphi] -> 5 spectra [bphi][5]: g1=iℓxΦ, g2=iℓyΦ, H11=iℓx g1, H21=iℓx g2, H22=iℓy g2
 template <class T> struct GradHessSpecBody {
     static constexpr int NT = 256;
+    static const char* name() { return "gradhess_spec"; }
     int Nx, Nyh; const T* lx; const T* ly; const C2<T>* phi; C2<T>* out; size_t total;   // total = Nbphi*Nx*Nyh
     DEV void operator()(int blk, unsigned char*) const {
         CMBL_FOR_THREADS(tid, NT) {
@@ -221,6 +226,7 @@ template <class T> struct GradHessSpecBody {
 // maps gh[bphi][5] -> pcache[k][bphi][2], minv[k][bphi][3] (m11, m21, m22) for k = 0..2n
 template <class T> struct PCacheBody {
     static constexpr int NT = 256;
+    static const char* name() { return "pcache"; }
     int nk, Nbphi; size_t nmap; const T* gh; T* pcache; T* minv;
     DEV void operator()(int blk, unsigned char*) const {
         CMBL_FOR_THREADS(tid, NT) {

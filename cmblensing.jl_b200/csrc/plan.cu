@@ -5,6 +5,41 @@
 namespace cmbl {
 
 long long g_launch_count = 0;
+bool g_profiling = false;
+
+#ifndef CMBL_EMU
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof;
+}
+void prof_before(const char* name, cmblStream_t st) {
+    ProfRec r; r.name = name;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+}
+void prof_after(cmblStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
+// returns "name count total_ms\n" lines
+std::string prof_report() {
+    cudaDeviceSynchronize();
+    std::vector<std::string> names; std::vector<double> tot; std::vector<long long> cnt;
+    for (auto& r : g_prof) {
+        float ms = 0; cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+        size_t i = 0; for (; i < names.size(); ++i) if (names[i] == r.name) break;
+        if (i == names.size()) { names.push_back(r.name); tot.push_back(0); cnt.push_back(0); }
+        tot[i] += ms; cnt[i] += 1;
+    }
+    g_prof.clear();
+    std::string out;
+    for (size_t i = 0; i < names.size(); ++i) out += names[i] + " " + std::to_string(cnt[i]) + " " + std::to_string(tot[i]) + "\n";
+    return out;
+}
+#else
+void prof_before(const char*, cmblStream_t) {}
+void prof_after(cmblStream_t) {}
+std::string prof_report() { return ""; }
+#endif
 
 void fft_schedule(int N, int& npass, int* radix) {
     CMBL_REQUIRE(N >= 4 && (N & (N - 1)) == 0, "FFT length must be a power of two >= 4");

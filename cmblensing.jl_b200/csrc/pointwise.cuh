@@ -19,6 +19,7 @@ template <class T> HD C2<T> nan2zero(C2<T> v) {                                 
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool CPLX> struct DiagMulBody {
     static constexpr int NT = 256;
+    static const char* name() { return "diag_mul"; }
     size_t plane, total; int Cd; bool ldiv;
     const T* diag; const void* in; void* out;
     DEV void operator()(int blk, unsigned char*) const {
@@ -48,6 +49,7 @@ template <class T, bool CPLX> struct DiagMulBody {
 // ---------------------------------------------------------------------------------------------------------------
 template <class T> struct FourierChainBody {
     static constexpr int NT = 256;
+    static const char* name() { return "fourier_chain"; }
     int Npol, Nb; size_t nf; int rot; bool neg;
     const T *sin2phi, *cos2phi;
     const C2<T>* in; const T* din; const C2<T>* d; const T* pre; const T* post; const T* sdiag; const C2<T>* sub; C2<T>* out;
@@ -98,6 +100,7 @@ template <class T> struct FourierChainBody {
 // standalone rotation with arbitrary plane stride (cmbl_qu_eb)
 template <class T> struct QuEbBody {
     static constexpr int NT = 256;
+    static const char* name() { return "qu_eb"; }
     int Nb, stride_planes, first_plane, dir; size_t nf;
     const T *sin2phi, *cos2phi; const C2<T>* in; C2<T>* out;
     DEV void operator()(int blk, unsigned char*) const {
@@ -120,6 +123,7 @@ template <class T> struct QuEbBody {
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool CPLX> struct DotBody {
     static constexpr int NT = 256;
+    static const char* name() { return "dot"; }
     size_t per_batch; int Nyh; const T* lam; double scale;
     const void* a; const void* b; double* partial;
     DEV void operator()(int blk, unsigned char* smem) const {
@@ -152,6 +156,7 @@ HD double sum_partials(const double* p) { double s = 0; for (int i = 0; i < RED_
 // ---------------------------------------------------------------------------------------------------------------
 template <class T> struct CgUpdate1Body {
     static constexpr int NT = 256;
+    static const char* name() { return "cg_update1"; }
     size_t per_batch, nf; int Npol, Nyh; const T* lam; double scale;
     const double* res; const double* pAp_part; const T* Mdiag;
     const C2<T>* p; const C2<T>* Ap; C2<T>* x; C2<T>* r; C2<T>* z; double* res_part;
@@ -183,6 +188,7 @@ template <class T> struct CgUpdate1Body {
 // CG update 2 (:106-107):  res′ = Σ partial;  p = z + (res′/res) p;  res_out[b] = res′
 template <class T> struct CgUpdate2Body {
     static constexpr int NT = 256;
+    static const char* name() { return "cg_update2"; }
     size_t per_batch; const double* res; const double* res_part; double* res_out;
     const C2<T>* z; C2<T>* p;
     DEV void operator()(int blk, unsigned char*) const {
@@ -203,6 +209,7 @@ template <class T> struct CgUpdate2Body {
 // r = b − Ax ; z = M \ r ; p = z ; partial(res = r·z)   (numerical_algorithms.jl:89-92)
 template <class T> struct CgInitBody {
     static constexpr int NT = 256;
+    static const char* name() { return "cg_init"; }
     size_t per_batch; int Nyh; const T* lam; double scale; const T* Mdiag;
     const C2<T>* b; const C2<T>* Ax; C2<T>* r; C2<T>* z; C2<T>* p; double* res_part;
     DEV void operator()(int blk, unsigned char* smem) const {
@@ -231,6 +238,7 @@ template <class T> struct CgInitBody {
 // res_out[b] = Σ partial[b][:]
 struct SumPartialsBody {
     static constexpr int NT = 32;
+    static const char* name() { return "sum_partials"; }
     int Nb; const double* part; double* out;
     DEV void operator()(int, unsigned char*) const {
         CMBL_FOR_THREADS(tid, NT) { for (int b = tid; b < Nb; b += NT) out[b] = sum_partials(part + (size_t)b * RED_BLOCKS); }

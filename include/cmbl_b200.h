@@ -46,6 +46,11 @@ const char* cmbl_last_error(void);
 const char* cmbl_version(void);
 /* number of kernels this library has launched in this process so far (bench.py reports the per-step delta) */
 long long cmbl_launch_count(void);
+/* per-kernel device timing (CUDA events around every launch of this library, on the launching stream) between
+ * cmbl_profile_begin() and cmbl_profile_end(); the latter synchronises and returns lines "kernel count total_ms\n".
+ * Diagnostic only (bench.py's roofline line): event pairs add launch gaps, so never enable it inside a timed region. */
+int cmbl_profile_begin(void);
+const char* cmbl_profile_end(void);
 
 /* ---- plan: ProjLambert metadata + FFT plan (src/proj_lambert.jl:24-75, src/util_fft.jl:32-39) ------------------- */
 int cmbl_plan_create(cmbl_plan** plan, int device, int Ny, int Nx, double theta_pix_arcmin, int dtype);
