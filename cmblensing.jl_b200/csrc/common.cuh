@@ -166,7 +166,9 @@ void prof_after(cmblStream_t st);
 template <class Body> struct KernelName { static const char* get() { return Body::name(); } };
 
 #ifndef CMBL_EMU
-template <class Body> __global__ void __launch_bounds__(Body::NT) kern(const Body b) {
+template <class Body, class = void> struct MinBlocks { static constexpr int value = 1; };
+template <class Body> struct MinBlocks<Body, decltype((void)Body::MINB)> { static constexpr int value = Body::MINB; };
+template <class Body> __global__ void __launch_bounds__(Body::NT, MinBlocks<Body>::value) kern(const Body b) {
     extern __shared__ __align__(16) unsigned char cmbl_smem[];
     b((int)blockIdx.x, cmbl_smem);
 }
@@ -202,5 +204,33 @@ template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStre
 }
 
 HD int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+// inter-block signalling (device atomics; GCC builtins in the emulator, whose blocks run on several host threads)
+DEV int atomic_inc_int(int* p) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, 1);
+#else
+    return __atomic_fetch_add(p, 1, __ATOMIC_ACQ_REL);
+#endif
+}
+DEV void mem_fence() {
+#ifdef __CUDA_ARCH__
+    __threadfence();
+#else
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#endif
+}
+template <class U> DEV U ld_cg(const U* p) {          // read data another block wrote during this launch: bypass L1
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *reinterpret_cast<const volatile U*>(p);
+#endif
+}
+
+// 128-bit vector of T for coalesced global access
+template <class T> struct alignas(16) Vec { static constexpr int N = 16 / sizeof(T); T v[16 / sizeof(T)]; };
+template <class T> HD Vec<T> vload(const T* p) { return *reinterpret_cast<const Vec<T>*>(p); }
+template <class T> HD void vstore(T* p, const Vec<T>& x) { *reinterpret_cast<Vec<T>*>(p) = x; }
 
 }  // namespace cmbl

@@ -11,14 +11,14 @@
 namespace cmbl {
 
 inline int tile_budget_bytes() {
-    static int v = [] { const char* e = getenv("CMBL_TILE_KB"); int kb = e ? atoi(e) : 72; if (kb < 8) kb = 8; if (kb > 200) kb = 200; return kb * 1024; }();
+    static int v = [] { const char* e = getenv("CMBL_TILE_KB"); int kb = e ? atoi(e) : 70; if (kb < 8) kb = 8; if (kb > 200) kb = 200; return kb * 1024; }();
     return v;
 }
 inline int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
-// lines per tile for column kernels (line-major tile); `extra` = additional lines the kernel appends
-template <class T> int col_lines(int N, int Nother, int extra = 0) {
-    size_t per = sizeof(C2<T>) * (size_t)Tile<T, false>::pitch_for(N);
+// lines per line-major tile of transforms of length N (other dimension Nother: 2 real lines per complex line)
+template <class T> int col_lines(const Fft1D<T>& f, int Nother, int extra = 0) {
+    size_t per = sizeof(C2<T>) * (size_t)Tile<T, false>::pitch_for(f.N, f.sk);
     int L = (int)(tile_budget_bytes() / per) - extra;
     if (L < 1) L = 1;
     L = pow2_floor(L);
@@ -47,7 +47,7 @@ template <class T> struct R2CColBody {
     const T* in; C2<T>* out;
     DEV void operator()(int blk, unsigned char* smem) const {
         const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
-        Tile<T, false> tv{reinterpret_cast<C2<T>*>(smem), L, Tile<T, false>::pitch_for(Ny)};
+        Tile<T, false> tv = line_tile<T>(smem, L, fy);
         const T* src = in + ((size_t)c * Nx + x0) * Ny;
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < L * Ny; e += NT) {
@@ -81,7 +81,7 @@ template <class T, bool INV> struct C2CRowBody {
     const C2<T>* in; C2<T>* out;
     DEV void operator()(int blk, unsigned char* smem) const {
         const int c = blk / tiles_per_plane, k0 = (blk % tiles_per_plane) * L;
-        Tile<T, true> tv{reinterpret_cast<C2<T>*>(smem), L, 0};
+        Tile<T, true> tv{reinterpret_cast<C2<T>*>(smem), L, 0, 0};
         const C2<T>* src = in + (size_t)c * Nx * Nyh;
         C2<T>* dst = out + (size_t)c * Nx * Nyh;
         CMBL_FOR_THREADS(tid, NT) {
@@ -113,7 +113,7 @@ template <class T> struct C2RColBody {
     const C2<T>* in; T* out;
     DEV void operator()(int blk, unsigned char* smem) const {
         const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
-        Tile<T, false> tv{reinterpret_cast<C2<T>*>(smem), L, Tile<T, false>::pitch_for(Ny)};
+        Tile<T, false> tv = line_tile<T>(smem, L, fy);
         const C2<T>* src = in + ((size_t)c * Nx + x0) * Nyh;
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < L * Nyh; e += NT) {

@@ -15,7 +15,7 @@ constexpr int MAX_PASSES = 6;
 // One 1-D transform length. `W[t] = exp(-2πi t/N)`; `pos[k]` = tile position that holds frequency k after the
 // forward passes. Device pointers (host pointers in the emulator build).
 template <class T> struct Fft1D {
-    int N = 0, logN = 0, npass = 0;
+    int N = 0, logN = 0, npass = 0, sk = 3;      // sk = log2(last radix): skew shift of line-major tiles
     int radix[MAX_PASSES] = {0, 0, 0, 0, 0, 0};
     const C2<T>* W = nullptr;
     const int* pos = nullptr;
@@ -23,14 +23,19 @@ template <class T> struct Fft1D {
 
 // Shared-memory tile of L complex lines of length N.
 //   LFAST = true : element (l, i) at i*L + l   (lines interleaved; used when lines are strided in global memory)
-//   LFAST = false: element (l, i) at l*pitch + i + (i >> 3)   (line-major with a 1-in-8 skew so that the
-//                  stride-8 accesses of the last radix-8 pass are bank-conflict free)
+//   LFAST = false: element (l, i) at l*pitch + i + (i >> sk)   (line-major; sk = log2 of the LAST radix of the schedule,
+//                  so that the stride-R accesses of the fused middle pass are bank-conflict free)
 template <class T, bool LFAST> struct Tile {
-    C2<T>* s; int L; int pitch;
-    HD C2<T>& at(int l, int i) const { return LFAST ? s[i * L + l] : s[l * pitch + i + (i >> 3)]; }
-    static HD int pitch_for(int N) { return N + (N >> 3) + 1; }
-    static HD size_t bytes(int N, int L) { return sizeof(C2<T>) * (size_t)(LFAST ? N * L : pitch_for(N) * L); }
+    C2<T>* s; int L; int pitch; int sk;
+    HD int phys(int i) const { return i + (i >> sk); }
+    HD C2<T>& at(int l, int i) const { return LFAST ? s[i * L + l] : s[l * pitch + i + (i >> sk)]; }
+    // pitch ≡ 2 (mod 16) elements: transposing tile loads (lines fastest across threads) stay conflict free
+    static HD int pitch_for(int N, int sk) { int p = N + (N >> sk); return p + ((18 - (p & 15)) & 15); }
+    static HD size_t bytes(int N, int L, int sk) { return sizeof(C2<T>) * (size_t)(LFAST ? N * L : pitch_for(N, sk) * L); }
 };
+template <class T> HD Tile<T, false> line_tile(unsigned char* smem, int L, const Fft1D<T>& f) {
+    Tile<T, false> t; t.s = reinterpret_cast<C2<T>*>(smem); t.L = L; t.pitch = Tile<T, false>::pitch_for(f.N, f.sk); t.sk = f.sk; return t;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // register butterflies: v[q] <- sum_m v[m] * exp(∓2πi m q / R)   (INV: + sign, unnormalised)
@@ -135,6 +140,63 @@ HD void fft_pass_thread(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int logn, i
     }
 }
 
+// Line-major tiles: every thread owns a fixed butterfly index j for the whole pass, keeps its R-1 twiddles and R tile
+// offsets in registers and sweeps the lines of the tile with them.
+template <class T, int R, bool INV, int NT>
+HD void fft_pass_lines_thread(const Tile<T, false>& tv, const Fft1D<T>& f, int logn, int tid) {
+    constexpr int logR = (R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4);
+    constexpr bool CACHE_TW = (R <= 8);
+    const int logs = logn - logR, s = 1 << logs;
+    const int lognb = f.logN - logR, nb = 1 << lognb;
+    const int tws = f.logN - logn;
+    int jstep, l0, lstep;
+    if (nb >= NT) { jstep = NT; l0 = 0; lstep = 1; } else { jstep = nb; l0 = tid >> lognb; lstep = NT >> lognb; }
+    for (int j = (nb >= NT) ? tid : (tid & (nb - 1)); j < nb; j += jstep) {
+        const int jj = j & (s - 1);
+        const int i0 = ((j >> logs) << logn) + jj;
+        int off[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) off[m] = tv.phys(i0 + (m << logs));
+        C2<T> w[R];
+        if (CACHE_TW && logs > 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) w[q] = CMBL_LDG(&f.W[(jj * q) << tws]);
+        }
+        for (int l = l0; l < tv.L; l += lstep) {
+            C2<T>* line = tv.s + l * tv.pitch;
+            C2<T> v[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) v[m] = line[off[m]];
+            if (!INV) {
+                dftR<T, R, false>(v);
+                if (logs > 0) {
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[q] = cmul(v[q], CACHE_TW ? w[q] : CMBL_LDG(&f.W[(jj * q) << tws]));
+                }
+            } else {
+                if (logs > 0) {
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], CACHE_TW ? w[q] : CMBL_LDG(&f.W[(jj * q) << tws]));
+                }
+                dftR<T, R, true>(v);
+            }
+#pragma unroll
+            for (int m = 0; m < R; ++m) line[off[m]] = v[m];
+        }
+        if (nb < NT) break;
+    }
+}
+
+template <class T, bool INV, int NT>
+HD void fft_pass_lines_dispatch(const Tile<T, false>& tv, const Fft1D<T>& f, int R, int logn, int tid) {
+    switch (R) {
+        case 2: fft_pass_lines_thread<T, 2, INV, NT>(tv, f, logn, tid); break;
+        case 4: fft_pass_lines_thread<T, 4, INV, NT>(tv, f, logn, tid); break;
+        case 8: fft_pass_lines_thread<T, 8, INV, NT>(tv, f, logn, tid); break;
+        default: fft_pass_lines_thread<T, 16, INV, NT>(tv, f, logn, tid); break;
+    }
+}
+
 template <class T, bool LFAST, bool INV>
 HD void fft_pass_dispatch(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int R, int logn, int tid, int NT) {
     switch (R) {
@@ -145,13 +207,19 @@ HD void fft_pass_dispatch(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int R, in
     }
 }
 
+template <class T, bool LFAST, bool INV, int NT>
+HD void fft_pass_any(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int R, int logn, int tid) {
+    if constexpr (LFAST) fft_pass_dispatch<T, true, INV>(tv, f, R, logn, tid, NT);
+    else fft_pass_lines_dispatch<T, INV, NT>(tv, f, R, logn, tid);
+}
+
 // Forward passes [p0, p1) of the plan (block-wide; includes the trailing sync of each pass).
 template <class T, bool LFAST, int NT>
 DEV void fft_forward_passes(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int p0, int p1) {
     int logn = f.logN;
     for (int p = 0; p < p1; ++p) {
         if (p >= p0) {
-            CMBL_FOR_THREADS(tid, NT) fft_pass_dispatch<T, LFAST, false>(tv, f, f.radix[p], logn, tid, NT);
+            CMBL_FOR_THREADS(tid, NT) fft_pass_any<T, LFAST, false, NT>(tv, f, f.radix[p], logn, tid);
             CMBL_SYNC();
         }
         logn -= ilog2(f.radix[p]);
@@ -165,30 +233,50 @@ DEV void fft_inverse_passes(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int p0,
     lognp[0] = f.logN;
     for (int p = 0; p < f.npass; ++p) lognp[p + 1] = lognp[p] - ilog2(f.radix[p]);
     for (int p = p1 - 1; p >= p0; --p) {
-        CMBL_FOR_THREADS(tid, NT) fft_pass_dispatch<T, LFAST, true>(tv, f, f.radix[p], lognp[p], tid, NT);
+        CMBL_FOR_THREADS(tid, NT) fft_pass_any<T, LFAST, true, NT>(tv, f, f.radix[p], lognp[p], tid);
         CMBL_SYNC();
     }
 }
 
-// Fused middle of a spectral operator: last forward pass (sub-length R, no twiddles) → mid(l, i0, v) on the R
+// Fused middle of a spectral operator: last forward pass (sub-length R, no twiddles) → mid.run<R>(l, i0, v) on the R
 // spectrum values at tile positions i0..i0+R-1 → first inverse pass.  One thread's share.
-template <class T, bool LFAST, int R, class Mid>
-HD void fft_middle_thread(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int tid, int NT, const Mid& mid) {
-    const int logR = (R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4);
-    const int nb = f.N >> logR;
-    const int ntask = nb * tv.L;
-    for (int task = tid; task < ntask; task += NT) {
-        int l, j;
-        if (LFAST) { l = task % tv.L; j = task / tv.L; } else { j = task % nb; l = task / nb; }
-        const int i0 = j << logR;
-        C2<T> v[R];
+template <class T, bool LFAST, int R, int NT, class Mid>
+HD void fft_middle_thread(const Tile<T, LFAST>& tv, const Fft1D<T>& f, int tid, const Mid& mid) {
+    constexpr int logR = (R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4);
+    const int lognb = f.logN - logR, nb = 1 << lognb;
+    if constexpr (LFAST) {
+        const int ntask = nb * tv.L;
+        for (int task = tid; task < ntask; task += NT) {
+            const int l = task % tv.L, j = task / tv.L;
+            const int i0 = j << logR;
+            C2<T> v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = tv.at(l, i0 + m);
-        dftR<T, R, false>(v);
-        mid.template run<R>(l, i0, v);
-        dftR<T, R, true>(v);
+            for (int m = 0; m < R; ++m) v[m] = tv.at(l, i0 + m);
+            dftR<T, R, false>(v);
+            mid.template run<R>(l, i0, v);
+            dftR<T, R, true>(v);
 #pragma unroll
-        for (int m = 0; m < R; ++m) tv.at(l, i0 + m) = v[m];
+            for (int m = 0; m < R; ++m) tv.at(l, i0 + m) = v[m];
+        }
+    } else {
+        int jstep, l0, lstep;
+        if (nb >= NT) { jstep = NT; l0 = 0; lstep = 1; } else { jstep = nb; l0 = tid >> lognb; lstep = NT >> lognb; }
+        for (int j = (nb >= NT) ? tid : (tid & (nb - 1)); j < nb; j += jstep) {
+            const int i0 = j << logR;
+            const int o0 = tv.phys(i0);                       // the R positions of one block are contiguous
+            for (int l = l0; l < tv.L; l += lstep) {
+                C2<T>* line = tv.s + l * tv.pitch + o0;
+                C2<T> v[R];
+#pragma unroll
+                for (int m = 0; m < R; ++m) v[m] = line[m];
+                dftR<T, R, false>(v);
+                mid.template run<R>(l, i0, v);
+                dftR<T, R, true>(v);
+#pragma unroll
+                for (int m = 0; m < R; ++m) line[m] = v[m];
+            }
+            if (nb < NT) break;
+        }
     }
 }
 
@@ -199,10 +287,10 @@ DEV void fft_spectral_op(const Tile<T, LFAST>& tv, const Fft1D<T>& f, const Mid&
     const int R = f.radix[f.npass - 1];
     CMBL_FOR_THREADS(tid, NT) {
         switch (R) {
-            case 2: fft_middle_thread<T, LFAST, 2>(tv, f, tid, NT, mid); break;
-            case 4: fft_middle_thread<T, LFAST, 4>(tv, f, tid, NT, mid); break;
-            case 8: fft_middle_thread<T, LFAST, 8>(tv, f, tid, NT, mid); break;
-            default: fft_middle_thread<T, LFAST, 16>(tv, f, tid, NT, mid); break;
+            case 2: fft_middle_thread<T, LFAST, 2, NT>(tv, f, tid, mid); break;
+            case 4: fft_middle_thread<T, LFAST, 4, NT>(tv, f, tid, mid); break;
+            case 8: fft_middle_thread<T, LFAST, 8, NT>(tv, f, tid, mid); break;
+            default: fft_middle_thread<T, LFAST, 16, NT>(tv, f, tid, mid); break;
         }
     }
     CMBL_SYNC();

@@ -36,24 +36,24 @@ template <class T, bool ADJ>
 static void flow_stage(FlowT<T>& F, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
                        T ca, T cb, cmblStream_t st) {
     PlanT<T>& P = *F.P;
-    T* tmp = reinterpret_cast<T*>(F.tmp.p); T* nline = reinterpret_cast<T*>(F.nline.p);
+    T* tmp = reinterpret_cast<T*>(F.tmp.p); T* nline = reinterpret_cast<T*>(F.nline.p); T* jn = reinterpret_cast<T*>(F.jn.p);
     {
         FlowRowBody<T, ADJ> b;
-        b.fx = P.ax.fft; b.mult = P.ax.mult_deriv;
-        b.Ny = P.Ny; b.Nx = P.Nx; b.L = row_lines<T>(P.Nx, P.Ny / 2); b.tiles_per_plane = P.Ny / (2 * b.L);
+        b.fx = P.ax.fft; b.fy = P.ay.fft; b.mult = P.ax.mult_deriv; b.mult_sign_y = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
+        b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.ax.fft, P.Ny); b.logL = ilog2(b.L); b.tiles_per_plane = P.Ny / (2 * b.L);
         b.Npol = F.Npol; b.Nbphi = F.Nbphi;
-        b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.nline = nline; b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
-        launch(b, F.C * b.tiles_per_plane, Tile<T, true>::bytes(P.Nx, b.L), st);
+        b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.nline = nline; b.jn = jn; b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
+        b.counter = reinterpret_cast<int*>(F.counter.p);
+        launch(b, F.C * b.tiles_per_plane, FlowRowBody<T, ADJ>::smem_bytes(b.fx, b.fy, b.L), st);
     }
     {
         FlowColBody<T, ADJ> b;
-        b.fy = P.ay.fft; b.mult_d = P.ay.mult_deriv; b.mult_s = P.ay.mult_sign;
-        b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.Ny, P.Nx, 1); b.tiles_per_plane = P.Nx / (2 * b.L);
+        b.fy = P.ay.fft; b.mult_d = P.ay.mult_deriv;
+        b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.ay.fft, P.Nx); b.logNyv = ilog2(P.Ny / Vec<T>::N); b.tiles_per_plane = P.Nx / (2 * b.L);
         b.Npol = F.Npol; b.Nbphi = F.Nbphi;
-        b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.nline = nline; b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
-        b.cN = P.ax.ell_nyq / (T)P.Nx;
+        b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.jn = jn; b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
         b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
-        launch(b, F.C * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L + 1), st);
+        launch(b, F.C * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
     }
 }
 
@@ -66,6 +66,8 @@ template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int 
     T* ub = reinterpret_cast<T*>(F.ubuf.reserve(sizeof(T) * nmap * F.C));
     F.tmp.reserve(sizeof(T) * nmap * F.C);
     F.nline.reserve(sizeof(T) * (size_t)P.Ny * F.C);
+    F.jn.reserve(sizeof(T) * (size_t)P.Ny * F.C);
+    if (F.counter.cap < sizeof(int) * (size_t)F.C) { F.counter.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.counter.p, sizeof(int) * (size_t)F.C, st); }
     const int sgn = k1 > k0 ? 1 : -1;
     const double h = (double)sgn / n;
     const T h2 = (T)(h / 2), h1 = (T)h, h6 = (T)(h / 6), h3 = (T)(h / 3);
@@ -119,7 +121,7 @@ template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* ou
         AdjFixBody<T> b;
         b.fx = P.ax.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh; b.lxN = P.ax.ell_nyq; b.lyN = P.ay.ell_nyq;
         b.rows0 = rows0; b.nacc = nacc; b.macc = macc; b.out = Yout;
-        size_t smem = sizeof(C2<T>) * Tile<T, false>::pitch_for(P.Nx) + sizeof(T) * 2 * b.NT;
+        size_t smem = sizeof(C2<T>) * Tile<T, false>::pitch_for(P.Nx, P.ax.fft.sk) + sizeof(T) * 2 * b.NT;
         launch(b, F.C, smem, st);
     }
     (void)nf;

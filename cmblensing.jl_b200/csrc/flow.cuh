@@ -24,7 +24,8 @@ template <class T> HD const T* p_plane(const T* pk, int c, int Npol, int Nbphi, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// row kernel: tmp = ∂ₓ_herm(g),  g = u (forward) or p₁·u (adjoint);  nline = N(y) = Σₓ (−1)^x g
+// row kernel: tmp = ∂ₓ_herm(g),  g = u (forward) or p₁·u (adjoint);  nline = N(y) = Σₓ (−1)^x g.
+// The block that finishes a plane last (ticket counter) also turns that plane's N(y) into jn(y) = cN·J[N](y).
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool ADJ> struct RowMid {
     const T* mult; T* nline_c; T* nacc_c; T wgt; int y0;
@@ -39,22 +40,35 @@ template <class T, bool ADJ> struct RowMid {
     }
 };
 
+template <class T> struct SignMid {                                // J: multiplier i·sign(k)/N (0 at DC / Nyquist)
+    const T* mult;
+    template <int R> HD void run(int, int i0, C2<T>* v) const {
+#pragma unroll
+        for (int q = 0; q < R; ++q) { T m = CMBL_LDG(&mult[i0 + q]); v[q] = mk<T>(-m * v[q].y, m * v[q].x); }
+    }
+};
+
 template <class T, bool ADJ> struct FlowRowBody {
-    static constexpr int NT = 256;
+    static constexpr int NT = 128, MINB = 3;
     static const char* name() { return "flow_rows"; }
-    Fft1D<T> fx; const T* mult;
-    int Ny, Nx, L, tiles_per_plane, Npol, Nbphi;
-    const T* u; const T* pk; T* tmp; T* nline; T* nacc; T wgt;
+    Fft1D<T> fx, fy; const T* mult; const T* mult_sign_y; T cN;
+    int Ny, Nx, L, logL, tiles_per_plane, Npol, Nbphi;
+    const T* u; const T* pk; T* tmp; T* nline; T* jn; T* nacc; T wgt; int* counter;
+    static HD size_t smem_bytes(const Fft1D<T>& fx, const Fft1D<T>& fy, int L) {
+        size_t a = Tile<T, false>::bytes(fx.N, L, fx.sk), b = Tile<T, false>::bytes(fy.N, 1, fy.sk);
+        return (a > b ? a : b) + 16;
+    }
     DEV void operator()(int blk, unsigned char* smem) const {
         const int c = blk / tiles_per_plane, y0 = (blk % tiles_per_plane) * 2 * L;
         const size_t nmap = (size_t)Ny * Nx;
-        Tile<T, true> tv{reinterpret_cast<C2<T>*>(smem), L, 0};
+        Tile<T, false> tv = line_tile<T>(smem, L, fx);
+        int* flag = reinterpret_cast<int*>(smem + smem_bytes(fx, fy, L) - 16);
         const T* uc = u + (size_t)c * nmap + y0;
         const T* p1 = ADJ ? p_plane(pk, c, Npol, Nbphi, 0, nmap) + y0 : nullptr;
         CMBL_FOR_THREADS(tid, NT) {
-            for (int e = tid; e < L * Nx; e += NT) {
-                int x = e / L, l = e - x * L;
-                size_t idx = (size_t)x * Ny + 2 * l;
+            for (int e = tid; e < (Nx << logL); e += NT) {
+                const int x = e >> logL, l = e & (L - 1);
+                const size_t idx = (size_t)x * Ny + 2 * l;
                 C2<T> v = *reinterpret_cast<const C2<T>*>(uc + idx);
                 if (ADJ) { C2<T> pp = *reinterpret_cast<const C2<T>*>(p1 + idx); v.x *= pp.x; v.y *= pp.y; }
                 tv.at(l, x) = v;
@@ -62,77 +76,126 @@ template <class T, bool ADJ> struct FlowRowBody {
         }
         CMBL_SYNC();
         RowMid<T, ADJ> mid{mult, nline + (size_t)c * Ny, ADJ ? nacc + (size_t)c * Ny : nullptr, wgt, y0};
-        fft_spectral_op<T, true, NT>(tv, fx, mid);
+        fft_spectral_op<T, false, NT>(tv, fx, mid);
         T* tc = tmp + (size_t)c * nmap + y0;
         CMBL_FOR_THREADS(tid, NT) {
-            for (int e = tid; e < L * Nx; e += NT) {
-                int x = e / L, l = e - x * L;
+            for (int e = tid; e < (Nx << logL); e += NT) {
+                const int x = e >> logL, l = e & (L - 1);
                 *reinterpret_cast<C2<T>*>(tc + (size_t)x * Ny + 2 * l) = tv.at(l, x);
+            }
+        }
+        // ---- last block of this plane: jn = cN · J[N] ------------------------------------------------------------
+        CMBL_FOR_THREADS(tid, NT) { mem_fence(); }                  // publish this block's nline entries device-wide
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) {
+            if (tid == 0) {
+                mem_fence();
+                *flag = (atomic_inc_int(counter + c) == tiles_per_plane - 1) ? 1 : 0;
+            }
+        }
+        CMBL_SYNC();
+        if (*flag) {
+            Tile<T, false> t1 = line_tile<T>(smem, 1, fy);
+            CMBL_FOR_THREADS(tid, NT) {
+                if (tid == 0) mem_fence();
+                for (int y = tid; y < Ny; y += NT) t1.at(0, y) = mk<T>(ld_cg(nline + (size_t)c * Ny + y), (T)0);
+            }
+            CMBL_SYNC();
+            SignMid<T> smid{mult_sign_y};
+            fft_spectral_op<T, false, NT>(t1, fy, smid);
+            CMBL_FOR_THREADS(tid, NT) {
+                for (int y = tid; y < Ny; y += NT) jn[(size_t)c * Ny + y] = cN * t1.at(0, y).x;
+                if (tid == 0) counter[c] = 0;
             }
         }
     }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// column kernel: ∂ᵧ, Nyquist correction, velocity k, RK4 update
-//   forward: k = p₁·(tmp ± cN·J[N]) + p₂·∂ᵧu          adjoint: k = tmp ± cN·J[N] + ∂ᵧ(p₂·u)
+// column kernel: ∂ᵧ, Nyquist correction, velocity k, RK4 update (128-bit global accesses)
+//   forward: k = p₁·(tmp ± jn) + p₂·∂ᵧu          adjoint: k = tmp ± jn + ∂ᵧ(p₂·u)         (+ for even x, − for odd x)
 //   acc_out = (acc_in ? acc_in : ybase) + cb·k ;  u_out = ybase + ca·k  (if u_out)
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool ADJ> struct ColMid {
-    const T* mult_d; const T* mult_s; T* macc_c; T wgt; int x0, L;
+    const T* mult_d; T* macc_c; T wgt; int x0;
     template <int R> HD void run(int l, int i0, C2<T>* v) const {
-        if (ADJ && i0 == 0 && l < L) {
+        if (ADJ && i0 == 0) {
             C2<T> nq = v[R / 2];
             macc_c[x0 + 2 * l] += wgt * nq.x; macc_c[x0 + 2 * l + 1] += wgt * nq.y;
         }
-        const T* mult = (l == L) ? mult_s : mult_d;
 #pragma unroll
-        for (int q = 0; q < R; ++q) { T m = CMBL_LDG(&mult[i0 + q]); v[q] = mk<T>(-m * v[q].y, m * v[q].x); }
+        for (int q = 0; q < R; ++q) { T m = CMBL_LDG(&mult_d[i0 + q]); v[q] = mk<T>(-m * v[q].y, m * v[q].x); }
     }
 };
 
 template <class T, bool ADJ> struct FlowColBody {
-    static constexpr int NT = 256;
+    static constexpr int NT = 128, MINB = 3;
     static const char* name() { return "flow_cols"; }
-    Fft1D<T> fy; const T* mult_d; const T* mult_s;
-    int Ny, Nx, L, tiles_per_plane, Npol, Nbphi;
-    const T* u; const T* pk; const T* tmp; const T* nline; T* macc; T wgt; T cN;
+    Fft1D<T> fy; const T* mult_d;
+    int Ny, Nx, L, logNyv, tiles_per_plane, Npol, Nbphi;
+    const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
     const T* ybase; const T* acc_in; T* acc_out; T* u_out; T ca, cb;
     DEV void operator()(int blk, unsigned char* smem) const {
+        constexpr int V = Vec<T>::N;
         const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
         const size_t nmap = (size_t)Ny * Nx, off = (size_t)c * nmap + (size_t)x0 * Ny;
-        Tile<T, false> tv{reinterpret_cast<C2<T>*>(smem), L + 1, Tile<T, false>::pitch_for(Ny)};
+        Tile<T, false> tv = line_tile<T>(smem, L, fy);
         const T* uc = u + off;
         const T* p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap) + (size_t)x0 * Ny;
         const T* p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap) + (size_t)x0 * Ny;
+        const int nvec = L << logNyv;                                   // vectors per tile column-set
         CMBL_FOR_THREADS(tid, NT) {
-            for (int e = tid; e < L * Ny; e += NT) {
-                int l = e / Ny, y = e - l * Ny;
-                size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
-                T a = uc[ia], b = uc[ib];
-                if (ADJ) { a *= p2[ia]; b *= p2[ib]; }
-                tv.at(l, y) = mk<T>(a, b);
+            for (int e = tid; e < nvec; e += NT) {
+                const int l = e >> logNyv, y = (e & ((1 << logNyv) - 1)) * V;
+                const size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
+                Vec<T> a = vload(uc + ia), b = vload(uc + ib);
+                if (ADJ) {
+                    Vec<T> pa = vload(p2 + ia), pb = vload(p2 + ib);
+#pragma unroll
+                    for (int k = 0; k < V; ++k) { a.v[k] *= pa.v[k]; b.v[k] *= pb.v[k]; }
+                }
+                C2<T>* dst = &tv.at(l, y);                               // V consecutive tile positions (V | 16)
+#pragma unroll
+                for (int k = 0; k < V; ++k) dst[k] = mk<T>(a.v[k], b.v[k]);
             }
-            for (int y = tid; y < Ny; y += NT) tv.at(L, y) = mk<T>(nline[(size_t)c * Ny + y], (T)0);
         }
         CMBL_SYNC();
-        ColMid<T, ADJ> mid{mult_d, mult_s, ADJ ? macc + (size_t)c * Nx : nullptr, wgt, x0, L};
+        ColMid<T, ADJ> mid{mult_d, ADJ ? macc + (size_t)c * Nx : nullptr, wgt, x0};
         fft_spectral_op<T, false, NT>(tv, fy, mid);
         const T* tc = tmp + off;
+        const T* jc = jn + (size_t)c * Ny;
         CMBL_FOR_THREADS(tid, NT) {
-            for (int e = tid; e < L * Ny; e += NT) {
-                int l = e / Ny, y = e - l * Ny;
-                size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
-                C2<T> z = tv.at(l, y);
-                T jn = cN * tv.at(L, y).x;
-                T ka, kb;
-                if (ADJ) { ka = tc[ia] + jn + z.x; kb = tc[ib] - jn + z.y; }
-                else { ka = p1[ia] * (tc[ia] + jn) + p2[ia] * z.x; kb = p1[ib] * (tc[ib] - jn) + p2[ib] * z.y; }
-                T base_a = 0, base_b = 0;
-                if (ybase) { base_a = ybase[off + ia]; base_b = ybase[off + ib]; }
-                T a0 = acc_in ? acc_in[off + ia] : base_a, b0 = acc_in ? acc_in[off + ib] : base_b;
-                acc_out[off + ia] = a0 + cb * ka; acc_out[off + ib] = b0 + cb * kb;
-                if (u_out) { u_out[off + ia] = base_a + ca * ka; u_out[off + ib] = base_b + ca * kb; }
+            for (int e = tid; e < nvec; e += NT) {
+                const int l = e >> logNyv, y = (e & ((1 << logNyv) - 1)) * V;
+                const size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
+                const C2<T>* src = &tv.at(l, y);
+                Vec<T> j = vload(jc + y), ta = vload(tc + ia), tb = vload(tc + ib), ka, kb;
+                if (ADJ) {
+#pragma unroll
+                    for (int k = 0; k < V; ++k) { C2<T> z = src[k]; ka.v[k] = ta.v[k] + j.v[k] + z.x; kb.v[k] = tb.v[k] - j.v[k] + z.y; }
+                } else {
+                    Vec<T> p1a = vload(p1 + ia), p1b = vload(p1 + ib), p2a = vload(p2 + ia), p2b = vload(p2 + ib);
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        C2<T> z = src[k];
+                        ka.v[k] = p1a.v[k] * (ta.v[k] + j.v[k]) + p2a.v[k] * z.x;
+                        kb.v[k] = p1b.v[k] * (tb.v[k] - j.v[k]) + p2b.v[k] * z.y;
+                    }
+                }
+                Vec<T> ba, bb;
+#pragma unroll
+                for (int k = 0; k < V; ++k) { ba.v[k] = 0; bb.v[k] = 0; }
+                if (ybase) { ba = vload(ybase + off + ia); bb = vload(ybase + off + ib); }
+                Vec<T> a0 = ba, b0 = bb;
+                if (acc_in) { a0 = vload(acc_in + off + ia); b0 = vload(acc_in + off + ib); }
+#pragma unroll
+                for (int k = 0; k < V; ++k) { a0.v[k] += cb * ka.v[k]; b0.v[k] += cb * kb.v[k]; }
+                vstore(acc_out + off + ia, a0); vstore(acc_out + off + ib, b0);
+                if (u_out) {
+#pragma unroll
+                    for (int k = 0; k < V; ++k) { ba.v[k] += ca * ka.v[k]; bb.v[k] += ca * kb.v[k]; }
+                    vstore(u_out + off + ia, ba); vstore(u_out + off + ib, bb);
+                }
             }
         }
     }
@@ -165,8 +228,8 @@ template <class T> struct AdjFixBody {
     DEV void operator()(int blk, unsigned char* smem) const {
         const int c = blk;
         C2<T>* line = reinterpret_cast<C2<T>*>(smem);
-        T* red = reinterpret_cast<T*>(line + Tile<T, false>::pitch_for(Nx));          // [2][NT]
-        Tile<T, false> tv{line, 1, Tile<T, false>::pitch_for(Nx)};
+        T* red = reinterpret_cast<T*>(line + Tile<T, false>::pitch_for(Nx, fx.sk));   // [2][NT]
+        Tile<T, false> tv = line_tile<T>(smem, 1, fx);
         CMBL_FOR_THREADS(tid, NT) {
             for (int x = tid; x < Nx; x += NT) tv.at(0, x) = mk<T>(macc[(size_t)c * Nx + x], (T)0);
             T s0 = 0, s1 = 0;
@@ -261,7 +324,7 @@ template <class T> struct FlowT : FlowBase {
     PlanT<T>* P = nullptr;
     int nsteps = 7, Npol = 1, Nb = 1, Nbphi = 1, C = 1;
     bool have_p = false, have_minv = false;
-    DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, nacc, macc, rows0, spec, gh;
+    DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, jn, counter, nacc, macc, rows0, spec, gh;
     size_t nmap() const { return P->map_elems(); }
     const T* pk(int k) const { return reinterpret_cast<T*>(pcache.p) + (size_t)k * Nbphi * 2 * nmap(); }
 };

@@ -44,18 +44,18 @@ std::string prof_report() { return ""; }
 void fft_schedule(int N, int& npass, int* radix) {
     CMBL_REQUIRE(N >= 4 && (N & (N - 1)) == 0, "FFT length must be a power of two >= 4");
     for (int i = 0; i < MAX_PASSES; ++i) radix[i] = 0;
-    if (N == 4) { npass = 1; radix[0] = 4; return; }
-    int m = ilog2(N) - 3;                       // bits left after the final radix-8 pass
-    int nfirst = (m + 3) / 4;                   // passes of radix <= 16
-    CMBL_REQUIRE(nfirst + 1 <= MAX_PASSES, "FFT length too large");
+    if (N <= 16) { npass = 1; radix[0] = N; return; }
+    // The LAST pass is twiddle-free and fuses with the first inverse pass in registers, so it gets the largest radix (16);
+    // the leading passes carry twiddles (kept in registers for radix <= 8).
+    int m = ilog2(N) - 4;
     npass = 0;
-    for (int i = 0; i < nfirst; ++i) {          // spread the bits as evenly as possible, larger radices first
-        int left = nfirst - i;
-        int bits = (m + left - 1) / left;
+    while (m > 0) {
+        int bits = (m >= 3 && m != 4) ? 3 : (m == 4 ? 2 : m);      // 8s, finishing with 4·4 / 4 / 2
         radix[npass++] = 1 << bits;
         m -= bits;
+        CMBL_REQUIRE(npass < MAX_PASSES, "FFT length too large");
     }
-    radix[npass++] = 8;
+    radix[npass++] = 16;
 }
 
 std::vector<int> fft_positions(int N, int npass, const int* radix) {
@@ -84,6 +84,7 @@ static void build_axis(std::vector<void*>& owned, AxisTables<T>& a, int N, T dl)
     Fft1D<T>& f = a.fft;
     f.N = N; f.logN = ilog2(N);
     fft_schedule(N, f.npass, f.radix);
+    f.sk = ilog2(f.radix[f.npass - 1]);
     std::vector<int> pos = fft_positions(N, f.npass, f.radix);
     std::vector<C2<T>> W(N);
     const long double tau = 6.283185307179586476925286766559005768L;
