@@ -81,6 +81,13 @@ int cmbl_lenseflow_grad(cmbl_flow* flow, int op, const void* f_out_map, const vo
     CMBL_API_END
 }
 
+int cmbl_lenseflow_kernel_path(cmbl_flow* flow) {
+    if (!flow || !flow->f) return 0;
+    int r = 0;
+    try { CMBL_DISPATCH(flow->f->plan, r = cmbl::flow_kernel_path<T>(*static_cast<cmbl::FlowT<T>*>(flow->f.get()))); } catch (...) { r = 0; }
+    return r;
+}
+
 int cmbl_lenseflow_get_p(cmbl_flow* flow, int k, void* out_host) {
     CMBL_API_BEGIN
     CMBL_REQUIRE(flow && flow->f && out_host, "NULL argument");
@@ -88,7 +95,18 @@ int cmbl_lenseflow_get_p(cmbl_flow* flow, int k, void* out_host) {
         auto& F = *static_cast<cmbl::FlowT<T>*>(flow->f.get());
         CMBL_REQUIRE(F.have_p, "precompute first");
         CMBL_REQUIRE(k >= 0 && k <= 2 * F.nsteps, "k out of range");
-        cmbl::dev_download(out_host, F.pk(k), sizeof(T) * F.nmap() * 2 * F.Nbphi, 0);
+        const size_t n = F.nmap() * 2 * F.Nbphi;
+        if (F.pcache_G == 0) cmbl::dev_download(out_host, F.pk(k), sizeof(T) * n, 0);
+        else {                                           // undo the row-grouped layout of the fast path
+            std::vector<T> h(n);
+            cmbl::dev_download(h.data(), F.pk(k), sizeof(T) * n, 0);
+            T* o = reinterpret_cast<T*>(out_host);
+            const int G = F.pcache_G, Nx = P.Nx, Ny = P.Ny;
+            for (size_t pl = 0; pl < (size_t)2 * F.Nbphi; ++pl)
+                for (int x = 0; x < Nx; ++x)
+                    for (int y = 0; y < Ny; ++y)
+                        o[pl * F.nmap() + (size_t)x * Ny + y] = h[pl * F.nmap() + ((size_t)(y / G) * Nx + x) * G + (y % G)];
+        }
     });
     CMBL_API_END
 }

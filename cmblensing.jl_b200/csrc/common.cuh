@@ -203,6 +203,27 @@ template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStre
 #endif
 }
 
+// grid of a persistent kernel: every block that can be resident on the device at once (cached per instantiation)
+template <class Body> int persistent_blocks(size_t smem) {
+#ifdef CMBL_EMU
+    (void)smem;
+    static int v = [] { const char* e = getenv("CMBL_EMU_PERSISTENT"); int n = e ? atoi(e) : 6; return n < 1 ? 1 : n; }();
+    return v;
+#else
+    static thread_local int cached = 0;
+    if (!cached) {
+        CMBL_CUDA(cudaFuncSetAttribute(kern<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        int per_sm = 0, dev = 0, sms = 0;
+        CMBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern<Body>, Body::NT, smem));
+        CMBL_CUDA(cudaGetDevice(&dev));
+        CMBL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CMBL_REQUIRE(per_sm >= 1, "persistent kernel does not fit on an SM");
+        cached = per_sm * sms;
+    }
+    return cached;
+#endif
+}
+
 HD int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 
 // inter-block signalling (device atomics; GCC builtins in the emulator, whose blocks run on several host threads)

@@ -1,5 +1,6 @@
-#include "flow.cuh"
+#include "flow_fast.cuh"
 #include "../../include/cmbl_b200.h"
+#include <algorithm>
 
 namespace cmbl {
 
@@ -26,34 +27,99 @@ template <class T> void flow_precompute(FlowT<T>& F, const void* phi, int phi_ba
     T* pc = reinterpret_cast<T*>(F.pcache.reserve(sizeof(T) * nmap * 2 * F.Nbphi * nk));
     T* mi = with_minv ? reinterpret_cast<T*>(F.minv.reserve(sizeof(T) * nmap * 3 * F.Nbphi * nk)) : nullptr;
     {
-        PCacheBody<T> b{nk, F.Nbphi, nmap, maps5, pc, mi};
+        F.pcache_G = flow_rg_rows(P);
+        PCacheBody<T> b{nk, F.Nbphi, nmap, maps5, pc, mi, F.pcache_G, P.Nx, P.Ny};
         launch(b, (int)((nmap * F.Nbphi + b.NT - 1) / b.NT), 0, st);
     }
     F.have_p = true; F.have_minv = with_minv;
 }
 
+static bool fast_enabled() { static const bool v = [] { const char* e = getenv("CMBL_FLOW_FAST"); return !e || atoi(e) != 0; }(); return v; }
+static int fast_pf() { static const int v = [] { const char* e = getenv("CMBL_FLOW_PF"); return e ? atoi(e) : 3; }(); return v; }
+
+template <class T, int LOGN, bool ADJ>
+static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
+    typedef FastRowBody<T, LOGN, ADJ> B;
+    B b;
+    b.fx = P.ax.fft; b.fy = P.ay.fft; b.mult = P.ax.mult_deriv; b.mult_sign_y = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
+    b.Ny = P.Ny; b.tiles_per_plane = P.Ny / B::ROWS; b.ntiles = nC * b.tiles_per_plane;
+    b.nblocks = std::min(b.ntiles, persistent_blocks<B>(B::SMEM));
+    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
+    b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = reinterpret_cast<T*>(F.jn.p);
+    b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt; b.counter = reinterpret_cast<int*>(F.counter.p);
+    launch(b, b.nblocks, B::SMEM, st);
+}
+template <class T, int LOGN, bool ADJ>
+static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
+    typedef FastColBody<T, LOGN, ADJ> B;
+    B b;
+    b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv;
+    b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / (2 * B::L); b.ntiles = nC * b.tiles_per_plane;
+    b.nblocks = std::min(b.ntiles, persistent_blocks<B>(B::SMEM));
+    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf();
+    b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.jn = reinterpret_cast<T*>(F.jn.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
+    b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
+    launch(b, b.nblocks, B::SMEM, st);
+}
+template <class T> static bool fast_rows_ok(const PlanT<T>& P) {
+    if (!fast_enabled() || !fast_len_ok(P.Nx) || !P.ax.ftw1) return false;
+    const int rows = (FAST_TILE_BYTES / (P.Nx * 16)) * (16 / (int)sizeof(T));
+    return P.Ny % rows == 0 && Tile<T, false>::bytes(P.Ny, 1, P.ay.fft.sk) <= (size_t)FAST_TILE_BYTES;
+}
+template <class T> static bool fast_cols_ok(const PlanT<T>& P) {
+    if (!fast_enabled() || !fast_len_ok(P.Ny) || !P.ay.ftw1) return false;
+    const int cols = FAST_TILE_BYTES / (int)sizeof(T) / P.Ny;
+    return P.Nx % cols == 0;
+}
+
+// rows per group of the row-grouped internal layout (flow_fast.cuh), 0 = the generic kernels on the reference layout
+template <class T> int flow_rg_rows(const PlanT<T>& P) {
+    if (!fast_rows_ok(P) || !fast_cols_ok(P) || P.Ny % 64 != 0 || P.Nx % 32 != 0) return 0;
+    return (FAST_TILE_BYTES / (P.Nx * 16)) * (16 / (int)sizeof(T));
+}
+template <class T, bool TO_RG> static void convert_layout(PlanT<T>& P, int G, const T* in, T* out, int C, cmblStream_t st) {
+    typedef LayoutBody<T, TO_RG> B;
+    B b{P.Ny, P.Nx, G, in, out};
+    launch(b, C * (P.Nx / B::TX) * (P.Ny / B::TY), B::SMEM, st);
+}
+
 template <class T, bool ADJ>
-static void flow_stage(FlowT<T>& F, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
+static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
                        T ca, T cb, cmblStream_t st) {
     PlanT<T>& P = *F.P;
     T* tmp = reinterpret_cast<T*>(F.tmp.p); T* nline = reinterpret_cast<T*>(F.nline.p); T* jn = reinterpret_cast<T*>(F.jn.p);
-    {
+    const bool fast = flow_rg_rows(P) > 0;
+    if (fast) {
+        switch (P.Nx) {
+            case 256: fast_rows<T, 8, ADJ>(F, c0, nC, u, kq, wgt, st); break;
+            case 512: fast_rows<T, 9, ADJ>(F, c0, nC, u, kq, wgt, st); break;
+            default: fast_rows<T, 10, ADJ>(F, c0, nC, u, kq, wgt, st); break;
+        }
+    } else {
         FlowRowBody<T, ADJ> b;
         b.fx = P.ax.fft; b.fy = P.ay.fft; b.mult = P.ax.mult_deriv; b.mult_sign_y = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
         b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.ax.fft, P.Ny); b.logL = ilog2(b.L); b.tiles_per_plane = P.Ny / (2 * b.L);
-        b.Npol = F.Npol; b.Nbphi = F.Nbphi;
+        b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
         b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.nline = nline; b.jn = jn; b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
         b.counter = reinterpret_cast<int*>(F.counter.p);
-        launch(b, F.C * b.tiles_per_plane, FlowRowBody<T, ADJ>::smem_bytes(b.fx, b.fy, b.L), st);
+        launch(b, nC * b.tiles_per_plane, FlowRowBody<T, ADJ>::smem_bytes(b.fx, b.fy, b.L), st);
     }
-    {
+    if (fast) {
+        switch (P.Ny) {
+            case 256: fast_cols<T, 8, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st); break;
+            case 512: fast_cols<T, 9, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st); break;
+            default: fast_cols<T, 10, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st); break;
+        }
+    } else {
         FlowColBody<T, ADJ> b;
         b.fy = P.ay.fft; b.mult_d = P.ay.mult_deriv;
         b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.ay.fft, P.Nx); b.logNyv = ilog2(P.Ny / Vec<T>::N); b.tiles_per_plane = P.Nx / (2 * b.L);
-        b.Npol = F.Npol; b.Nbphi = F.Nbphi;
+        b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
         b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.jn = jn; b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
         b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
-        launch(b, F.C * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
+        launch(b, nC * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
     }
 }
 
@@ -62,6 +128,13 @@ template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int 
     PlanT<T>& P = *F.P;
     const size_t nmap = P.map_elems();
     const int n = F.nsteps;
+    const int G = flow_rg_rows(P);
+    CMBL_REQUIRE(G == F.pcache_G, "p-cache layout does not match the kernel path");
+    T* ycaller = y;
+    if (G) {                                        // integrate on a row-grouped copy of the state (flow_fast.cuh)
+        y = reinterpret_cast<T*>(F.yrg.reserve(sizeof(T) * nmap * F.C));
+        convert_layout<T, true>(P, G, ycaller, y, F.C, st);
+    }
     T* acc = reinterpret_cast<T*>(F.acc.reserve(sizeof(T) * nmap * F.C));
     T* ub = reinterpret_cast<T*>(F.ubuf.reserve(sizeof(T) * nmap * F.C));
     F.tmp.reserve(sizeof(T) * nmap * F.C);
@@ -71,6 +144,10 @@ template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int 
     const int sgn = k1 > k0 ? 1 : -1;
     const double h = (double)sgn / n;
     const T h2 = (T)(h / 2), h1 = (T)h, h6 = (T)(h / 6), h3 = (T)(h / 3);
+    static const int chunk_env = [] { const char* e = getenv("CMBL_FLOW_CHUNK"); return e ? atoi(e) : 0; }();
+    const int chunk = (chunk_env > 0 && chunk_env < F.C) ? chunk_env : F.C;       // planes integrated together (L2 residency)
+    for (int c0 = 0; c0 < F.C; c0 += chunk) {
+    const int nC = (F.C - c0 < chunk) ? F.C - c0 : chunk;
     int kk = k0;
     for (int step = 0; step < n; ++step) {
         for (int s = 0; s < 4; ++s) {
@@ -81,11 +158,13 @@ template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int 
             T* acc_out = (s == 3) ? y : acc;
             T* u_out = (s == 3) ? nullptr : ub;
             const T ca = (s < 2) ? h2 : h1, cb = (s == 0 || s == 3) ? h6 : h3;
-            if (adj) flow_stage<T, true>(F, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st);
-            else flow_stage<T, false>(F, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st);
+            if (adj) flow_stage<T, true>(F, c0, nC, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st);
+            else flow_stage<T, false>(F, c0, nC, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st);
         }
         kk += 2 * sgn;
     }
+    }
+    if (G) convert_layout<T, false>(P, G, y, ycaller, F.C, st);
 }
 
 template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st) {
@@ -127,10 +206,13 @@ template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* ou
     (void)nf;
 }
 
+template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_rg_rows(*F.P) > 0 ? 3 : 0; }
+
 #define INST(T)                                                                                        \
     template void flow_precompute<T>(FlowT<T>&, const void*, int, bool, cmblStream_t);                 \
     template void flow_integrate<T>(FlowT<T>&, bool, T*, int, int, cmblStream_t);                      \
-    template void flow_apply<T>(FlowT<T>&, int, const void*, void*, cmblStream_t);
+    template void flow_apply<T>(FlowT<T>&, int, const void*, void*, cmblStream_t);                     \
+    template int flow_kernel_path<T>(FlowT<T>&);
 INST(float)
 INST(double)
 

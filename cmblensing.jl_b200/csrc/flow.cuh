@@ -52,14 +52,14 @@ template <class T, bool ADJ> struct FlowRowBody {
     static constexpr int NT = 128, MINB = 3;
     static const char* name() { return "flow_rows"; }
     Fft1D<T> fx, fy; const T* mult; const T* mult_sign_y; T cN;
-    int Ny, Nx, L, logL, tiles_per_plane, Npol, Nbphi;
+    int Ny, Nx, L, logL, tiles_per_plane, Npol, Nbphi, cbase;
     const T* u; const T* pk; T* tmp; T* nline; T* jn; T* nacc; T wgt; int* counter;
     static HD size_t smem_bytes(const Fft1D<T>& fx, const Fft1D<T>& fy, int L) {
         size_t a = Tile<T, false>::bytes(fx.N, L, fx.sk), b = Tile<T, false>::bytes(fy.N, 1, fy.sk);
         return (a > b ? a : b) + 16;
     }
     DEV void operator()(int blk, unsigned char* smem) const {
-        const int c = blk / tiles_per_plane, y0 = (blk % tiles_per_plane) * 2 * L;
+        const int c = cbase + blk / tiles_per_plane, y0 = (blk % tiles_per_plane) * 2 * L;
         const size_t nmap = (size_t)Ny * Nx;
         Tile<T, false> tv = line_tile<T>(smem, L, fx);
         int* flag = reinterpret_cast<int*>(smem + smem_bytes(fx, fy, L) - 16);
@@ -132,12 +132,12 @@ template <class T, bool ADJ> struct FlowColBody {
     static constexpr int NT = 128, MINB = 3;
     static const char* name() { return "flow_cols"; }
     Fft1D<T> fy; const T* mult_d;
-    int Ny, Nx, L, logNyv, tiles_per_plane, Npol, Nbphi;
+    int Ny, Nx, L, logNyv, tiles_per_plane, Npol, Nbphi, cbase;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
     const T* ybase; const T* acc_in; T* acc_out; T* u_out; T ca, cb;
     DEV void operator()(int blk, unsigned char* smem) const {
         constexpr int V = Vec<T>::N;
-        const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
+        const int c = cbase + blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
         const size_t nmap = (size_t)Ny * Nx, off = (size_t)c * nmap + (size_t)x0 * Ny;
         Tile<T, false> tv = line_tile<T>(smem, L, fy);
         const T* uc = u + off;
@@ -291,12 +291,15 @@ template <class T> struct PCacheBody {
     static constexpr int NT = 256;
     static const char* name() { return "pcache"; }
     int nk, Nbphi; size_t nmap; const T* gh; T* pcache; T* minv;
+    int G, Nx, Ny;                       // G > 0: write the caches in the row-grouped layout of flow_fast.cuh
     DEV void operator()(int blk, unsigned char*) const {
         CMBL_FOR_THREADS(tid, NT) {
             size_t e = (size_t)blk * NT + tid;
             if (e < nmap * Nbphi) {
                 size_t b = e / nmap, r = e - b * nmap;
-                const T* g = gh + b * 5 * nmap + r;
+                const size_t rin = r;
+                if (G > 0) { const int x = (int)(r / Ny), y = (int)(r - (size_t)x * Ny); r = ((size_t)(y / G) * Nx + x) * G + (y % G); }
+                const T* g = gh + b * 5 * nmap + rin;
                 T g1 = g[0], g2 = g[nmap], H11 = g[2 * nmap], H21 = g[3 * nmap], H22 = g[4 * nmap];
                 for (int k = 0; k < nk; ++k) {
                     T t = (T)((double)k / (double)(nk - 1));
@@ -324,6 +327,8 @@ template <class T> struct FlowT : FlowBase {
     PlanT<T>* P = nullptr;
     int nsteps = 7, Npol = 1, Nb = 1, Nbphi = 1, C = 1;
     bool have_p = false, have_minv = false;
+    int pcache_G = 0;                    // layout of pcache / minv: 0 = reference layout, else rows per row group
+    DevBuf yrg;                          // row-grouped copy of the ODE state
     DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, jn, counter, nacc, macc, rows0, spec, gh;
     size_t nmap() const { return P->map_elems(); }
     const T* pk(int k) const { return reinterpret_cast<T*>(pcache.p) + (size_t)k * Nbphi * 2 * nmap(); }
@@ -333,5 +338,6 @@ template <class T> void flow_precompute(FlowT<T>& F, const void* phi, int phi_ba
 // integrate the map-space flow in place on y from stage index k0 to k1 (0 or 2n)
 template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st);
 template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st);
+template <class T> int flow_kernel_path(FlowT<T>& F);
 
 }  // namespace cmbl

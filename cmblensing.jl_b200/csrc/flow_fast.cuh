@@ -1,0 +1,621 @@
+// Fast path of the two LenseFlow stage kernels (flow.cuh) for transform lengths 256 / 512 / 1024, written for B200:
+//
+//   * persistent blocks (grid = resident blocks of the whole GPU) that walk over tiles blk, blk+G, blk+2G, ...
+//   * every global→shared transfer is asynchronous (cp.async, 16 B per request) into a double-buffered tile, so the
+//     next tile is in flight during all five FFT sweeps of the current one; operands that are only consumed by the
+//     column kernel's RK epilogue are pulled into L2 a few µs ahead with bulk L2 prefetches
+//   * shared-memory layouts are built from the 16-byte chunk the copy engine delivers and XOR-swizzled at chunk
+//     granularity so that all five sweeps (strides N/R1, 16, 1) are bank-conflict free with 128-bit accesses:
+//       column kernel: planar tile, plane p = column x0+p, chunk = V consecutive y;  a thread owns V adjacent butterflies
+//       row kernel   : tile [cl][x], chunk = V consecutive rows at one x (= V/2 complex lines); a thread owns one
+//                      butterfly index and keeps its twiddles in registers for the whole launch
+//   * schedule [R1, R2, 16] (same as plan.cu, so the tile-order multiplier tables are shared): forward R1, forward R2,
+//     fused register-resident middle (forward 16 · multiplier · inverse 16), inverse R2, inverse R1.
+//   * the state of the ODE (y, u, tmp, acc) and the p-cache live in a library-internal ROW-GROUPED layout while the fast
+//     kernels run:  element (x, y) of a plane at  ((y / G)·Nx + x)·G + y % G,  G = rows of one row-kernel tile
+//     (G·sizeof(T) = 32 B at Nx = 1024).  A row tile (all x, G rows) is then ONE contiguous 32 KB run and a column tile
+//     (M columns, all y) is Ny/G runs of M·G·sizeof(T) bytes (128 B fp64 / 256 B fp32) — in the reference's column-major
+//     layout a row tile is 1024 pieces of 32 B at an 8 KB stride, which DRAM serves at < 20 % of its bandwidth
+//     (measured: 1.2 TB/s).  LayoutBody converts caller buffers on entry / exit of flow_integrate.
+// The arithmetic is the generic kernels' (same butterflies, twiddles and order of operations per element).
+#pragma once
+#include "flow.cuh"
+
+namespace cmbl {
+
+// ---------------------------------------------------------------------------------------------------------------
+// asynchronous copy / cache-hint helpers (plain copies in the host emulator)
+// ---------------------------------------------------------------------------------------------------------------
+DEV void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef __CUDA_ARCH__
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+    memcpy(smem_dst, gsrc, 16);
+#endif
+}
+DEV void cp_async_commit() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+DEV void cp_async_wait_all() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// pull [p, p+bytes) into L2 (bytes multiple of 16)
+DEV void l2_prefetch(const void* p, unsigned bytes) {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+    (void)p; (void)bytes;
+#endif
+}
+// streaming 128-bit global load that does not allocate in L1 (L1 is kept for the twiddle / multiplier tables)
+template <class T> DEV Vec<T> vload_stream(const T* p);
+template <> DEV Vec<float> vload_stream<float>(const float* p) {
+    Vec<float> r;
+#ifdef __CUDA_ARCH__
+    asm("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+#else
+    r = vload(p);
+#endif
+    return r;
+}
+template <> DEV Vec<double> vload_stream<double>(const double* p) {
+    Vec<double> r;
+#ifdef __CUDA_ARCH__
+    asm("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
+#else
+    r = vload(p);
+#endif
+    return r;
+}
+// two adjacent 16-byte chunks as one 256-bit store (sm_100: st.global.v8.f32 / v4.f64); p must be 32-byte aligned
+template <class T> DEV void vstore2(T* p, const Vec<T>& a, const Vec<T>& b);
+template <> DEV void vstore2<float>(float* p, const Vec<float>& a, const Vec<float>& b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]), "f"(a.v[3]),
+                 "f"(b.v[0]), "f"(b.v[1]), "f"(b.v[2]), "f"(b.v[3]) : "memory");
+#else
+    vstore(p, a); vstore(p + 4, b);
+#endif
+}
+template <> DEV void vstore2<double>(double* p, const Vec<double>& a, const Vec<double>& b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.v[0]), "d"(a.v[1]), "d"(b.v[0]), "d"(b.v[1]) : "memory");
+#else
+    vstore(p, a); vstore(p + 2, b);
+#endif
+}
+// ticket with release semantics only (MEMBAR.ALL.GPU + ATOMG): unlike __threadfence() it does not invalidate L1
+DEV int ticket_release(int* p) {
+#ifdef __CUDA_ARCH__
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+    return (int)old;
+#else
+    return __atomic_fetch_add(p, 1, __ATOMIC_ACQ_REL);
+#endif
+}
+template <class T> DEV Vec<T> vload_ldg(const T* p) {        // cached read-only 128-bit load (tables)
+#ifdef __CUDA_ARCH__
+    Vec<T> r; const float4 q = __ldg(reinterpret_cast<const float4*>(p)); memcpy(&r, &q, 16); return r;
+#else
+    return vload(p);
+#endif
+}
+
+template <int LOGN> struct FastSched {
+    static constexpr int LOGR1 = (LOGN == 8) ? 2 : 3, LOGR2 = LOGN - 4 - LOGR1;
+    static constexpr int R1 = 1 << LOGR1, R2 = 1 << LOGR2;
+    static_assert(LOGN >= 8 && LOGN <= 10, "fast path covers N = 256, 512, 1024");
+};
+inline bool fast_len_ok(int N) { return N == 256 || N == 512 || N == 1024; }
+constexpr int FAST_TILE_BYTES = 32768;
+
+HD int swz8(int ch) { return ch ^ ((ch >> 3) & 7); }        // column kernel: chunk index within a plane
+HD int swzx(int x) { return x ^ ((x >> 4) & 7); }           // row kernel: x index within a chunk-row
+
+HD size_t rg_index(int x, int y, int Nx, int G) { return ((size_t)(y / G) * Nx + x) * G + (y % G); }
+
+// standard (Ny,Nx) column-major plane  <->  row-grouped plane, staged through shared memory so that both sides move
+// >= 512-byte runs.  One block = TX columns × TY rows of one plane.
+template <class T, bool TO_RG> struct LayoutBody {
+    static constexpr int NT = 256, TX = 32, TY = 64, V = 16 / (int)sizeof(T), PITCH = TY + V;
+    static constexpr size_t SMEM = sizeof(T) * TX * PITCH;
+    static const char* name() { return TO_RG ? "layout_to_rg" : "layout_from_rg"; }
+    int Ny, Nx, G; const T* in; T* out;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        T* t = reinterpret_cast<T*>(smem);
+        const int txn = Nx / TX, tyn = Ny / TY;
+        const int c = blk / (txn * tyn), r = blk % (txn * tyn), x0 = (r / tyn) * TX, y0 = (r % tyn) * TY;
+        const size_t plane = (size_t)c * Ny * Nx;
+        const int GV = G / V;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < TX * TY / V; e += NT) {
+                if (TO_RG) { const int x = e / (TY / V), yv = e % (TY / V); vstore(t + x * PITCH + yv * V, vload(in + plane + (size_t)(x0 + x) * Ny + y0 + yv * V)); }
+                else { const int sub = e % GV, x = (e / GV) % TX, yb = e / (GV * TX);
+                       vstore(t + x * PITCH + yb * G + sub * V, vload(in + plane + rg_index(x0 + x, y0 + yb * G + sub * V, Nx, G))); }
+            }
+        }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int e = tid; e < TX * TY / V; e += NT) {
+                if (TO_RG) { const int sub = e % GV, x = (e / GV) % TX, yb = e / (GV * TX);
+                             vstore(out + plane + rg_index(x0 + x, y0 + yb * G + sub * V, Nx, G), vload(t + x * PITCH + yb * G + sub * V)); }
+                else { const int x = e / (TY / V), yv = e % (TY / V); vstore(out + plane + (size_t)(x0 + x) * Ny + y0 + yv * V, vload(t + x * PITCH + yv * V)); }
+            }
+        }
+    }
+};
+
+// Values that a thread loads right BEFORE a barrier for use right after it (twiddles / multipliers of the next sweep) live
+// in registers across the barrier on the device; the host emulator runs the threads of a block one after another, so
+// there they are (re)loaded at the start of the consuming phase instead.
+#ifdef CMBL_EMU
+#define CMBL_PRE_END(stmt) ((void)0)
+#define CMBL_PRE_START(stmt) stmt
+#else
+#define CMBL_PRE_END(stmt) stmt
+#define CMBL_PRE_START(stmt) ((void)0)
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------
+// column kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, int LOGN, bool ADJ> struct FastColBody {
+    static constexpr int NT = 128, MINB = ADJ ? 2 : 3;
+    static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), CH = N / V;       // CH chunks per column
+    static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
+    static constexpr int S1 = N / R1, N2 = N / R1;                                   // pass-2 stride is 16
+    static constexpr int TILE = FAST_TILE_BYTES / (int)sizeof(T);                   // reals per tile buffer
+    static constexpr int L = TILE / (2 * N);                                         // complex lines (column pairs) per tile
+    static constexpr int NB1 = S1 / V, NB2 = N / (R2 * V);                           // bundles per line in pass 1 / pass 2
+    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2);
+    static const char* name() { return "flow_cols"; }
+
+    static constexpr int M = 2 * L, LGM = (M == 2 ? 1 : M == 4 ? 2 : M == 8 ? 3 : M == 16 ? 4 : M == 32 ? 5 : 6);
+    static_assert((1 << LGM) == M, "columns per tile must be a power of two <= 64");
+
+    const T* tw1; const T* tw2; const T* mult_d;
+    int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
+    const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
+    const T* ybase; const T* acc_in; T* acc_out; T* u_out; T ca, cb;
+
+    template <int R> struct Tw { Vec<T> r[R], i[R]; };
+
+    // shared-memory chunk position: XOR swizzle within the plane plus a per-plane rotation (epilogue / copies touch
+    // M planes at the same chunk index)
+    DEV int pxor(int p) const { return (p << lgGV) & 7; }
+    DEV int swzp(int ch, int p) const { return swz8(ch) ^ pxor(p); }
+    // k-th chunk of a tile in MEMORY order (row-grouped layout): plane (column) p, chunk ch along y, element offset in the plane
+    DEV void chunk_of(int k, int x0, int& p, int& ch, size_t& goff) const {
+        const int sub = k & ((1 << lgGV) - 1), yb = k >> (lgGV + LGM);
+        p = (k >> lgGV) & (M - 1); ch = (yb << lgGV) + sub;
+        goff = ((size_t)yb * Nx + x0 + p) * G + sub * V;
+    }
+    // ---- global -> shared (asynchronous) ------------------------------------------------------------------
+    DEV void issue_tile(const T* plane_base, int x0, T* buf, int tid) const {
+#pragma unroll 4
+        for (int k = tid; k < M * CH; k += NT) {
+            int p, ch; size_t goff; chunk_of(k, x0, p, ch, goff);
+            cp_async16(buf + p * N + swzp(ch, p) * V, plane_base + goff);
+        }
+    }
+    template <int R> DEV void load_tw(Tw<R>& w, const T* tw, int tws, int toff) const {
+#pragma unroll
+        for (int q = 1; q < R; ++q) { w.r[q] = vload_ldg(tw + ((q - 1) * 2) * tws + toff); w.i[q] = vload_ldg(tw + ((q - 1) * 2 + 1) * tws + toff); }
+    }
+    DEV void load_tw1(Tw<R1>& w, int task) const { load_tw<R1>(w, tw1, S1, V * (task % NB1)); }
+    DEV void load_tw2(Tw<R2>& w, int task) const { load_tw<R2>(w, tw2, 16, (V * (task % NB2)) & 15); }
+
+    // ---- twiddled pass on V adjacent butterflies: chunk index of element m = c0 + m*cs --------------------------
+    template <int R, bool INV> DEV void bundle_pass(T* re, T* im, int xr_, int xi_, int c0, int cs, const Tw<R>& w, const T* pre, const T* pim) const {
+        Vec<T> xr[R], xi[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int o = swz8(c0 + m * cs), oa = (o ^ xr_) * V, ob = (o ^ xi_) * V;
+            xr[m] = vload(re + oa); xi[m] = vload(im + ob);
+            if (pre) {
+                Vec<T> a = vload(pre + oa), b = vload(pim + ob);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { xr[m].v[e] *= a.v[e]; xi[m].v[e] *= b.v[e]; }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            C2<T> v[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) v[m] = mk<T>(xr[m].v[e], xi[m].v[e]);
+            if (!INV) {
+                dftR<T, R, false>(v);
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], mk<T>(w.r[q].v[e], w.i[q].v[e]));
+            } else {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], mk<T>(w.r[q].v[e], w.i[q].v[e]));
+                dftR<T, R, true>(v);
+            }
+#pragma unroll
+            for (int m = 0; m < R; ++m) { xr[m].v[e] = v[m].x; xi[m].v[e] = v[m].y; }
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int o = swz8(c0 + m * cs);
+            vstore(re + (o ^ xr_) * V, xr[m]); vstore(im + (o ^ xi_) * V, xi[m]);
+        }
+    }
+    template <bool INV> DEV void pass1(T* buf, const T* pbuf, int tid, Tw<R1>& w) const {
+        for (int task = tid; task < L * NB1; task += NT) {
+            const int l = task / NB1, b = task % NB1;
+            if (task != tid) load_tw1(w, task);
+            T* re = buf + (2 * l) * N; T* im = re + N;
+            const T* pre = (ADJ && !INV) ? pbuf + (2 * l) * N : nullptr;
+            bundle_pass<R1, INV>(re, im, pxor(2 * l), pxor(2 * l + 1), b, S1 / V, w, pre, pre ? pre + N : nullptr);
+        }
+    }
+    template <bool INV> DEV void pass2(T* buf, int tid, Tw<R2>& w) const {
+        for (int task = tid; task < L * NB2; task += NT) {
+            const int l = task / NB2, b = task % NB2;
+            if (task != tid) load_tw2(w, task);
+            const int j0 = V * b, jj0 = j0 & 15, a = j0 >> 4;
+            T* re = buf + (2 * l) * N; T* im = re + N;
+            bundle_pass<R2, INV>(re, im, pxor(2 * l), pxor(2 * l + 1), (a * N2 + jj0) / V, 16 / V, w, nullptr, nullptr);
+        }
+    }
+    // fused middle: forward radix 16, multiplier iℓ/N (tile order), Nyquist bookkeeping of the adjoint flow, inverse radix 16
+    DEV void middle(T* buf, int tid, T* macc_c, int x0) const {
+        constexpr int NB = N / 16, CPB = 16 / V;                    // butterflies per line, chunks per butterfly
+        for (int task = tid; task < L * NB; task += NT) {
+            const int l = task / NB, j = task % NB;
+            T* re = buf + (2 * l) * N; T* im = re + N;
+            T mlt[16];
+#pragma unroll
+            for (int cc = 0; cc < CPB; ++cc) { Vec<T> m4 = vload_ldg(mult_d + 16 * j + cc * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) mlt[cc * V + e] = m4.v[e]; }
+            C2<T> v[16];
+            const int xa = pxor(2 * l), xb = pxor(2 * l + 1);
+#pragma unroll
+            for (int cc = 0; cc < CPB; ++cc) {
+                const int o = swz8(j * CPB + cc);
+                Vec<T> a = vload(re + (o ^ xa) * V), b = vload(im + (o ^ xb) * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[cc * V + e] = mk<T>(a.v[e], b.v[e]);
+            }
+            dft16<T, false>(v);
+            if (ADJ && j == 0) { macc_c[x0 + 2 * l] += wgt * v[8].x; macc_c[x0 + 2 * l + 1] += wgt * v[8].y; }   // Nyquist coefficient: position 8
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = mk<T>(-mlt[q] * v[q].y, mlt[q] * v[q].x);
+            dft16<T, true>(v);
+#pragma unroll
+            for (int cc = 0; cc < CPB; ++cc) {
+                const int o = swz8(j * CPB + cc);
+                Vec<T> a, b;
+#pragma unroll
+                for (int e = 0; e < V; ++e) { a.v[e] = v[cc * V + e].x; b.v[e] = v[cc * V + e].y; }
+                vstore(re + (o ^ xa) * V, a); vstore(im + (o ^ xb) * V, b);
+            }
+        }
+    }
+
+    // ---- velocity + RK4 update (src/lenseflow.jl:150-174, src/numerical_algorithms.jl:11-24) --------------------------
+    //   forward: k = p₁·(tmp ± jn) + p₂·∂ᵧu          adjoint: k = tmp ± jn + ∂ᵧ(p₂·u)         (+ for even x, − for odd x)
+    //   acc_out = (acc_in ? acc_in : ybase) + cb·k ;  u_out = ybase + ca·k  (if u_out)
+    // KIND 0: first stage (no acc_in), 1: middle stages, 2: last stage (no ybase, no u_out).  One 16-byte chunk per thread
+    // and iteration, chunks taken in memory order; the global loads of UNR iterations are issued before the first use.
+    template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2) const {
+        constexpr bool YB = KIND != 2, AI = KIND != 0, UO = KIND != 2;
+        constexpr int ITER = M * CH / NT, UNR = 4;
+        static_assert(ITER % UNR == 0, "epilogue unroll");
+        const T* tc = tmp + pbase;
+        const T* yb = YB ? ybase + pbase : nullptr;
+        const T* ai = AI ? acc_in + pbase : nullptr;
+#pragma unroll 1
+        for (int it = 0; it < ITER; it += UNR) {
+            Vec<T> ta[UNR], p1a[UNR], p2a[UNR], ya[UNR], aa[UNR], jv[UNR];
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                int p, ch; size_t g; chunk_of(tid + (it + k) * NT, x0, p, ch, g);
+                ta[k] = vload_stream(tc + g);
+                if (!ADJ) { p1a[k] = vload_stream(p1 + g); p2a[k] = vload_stream(p2 + g); }
+                if (YB) ya[k] = vload_stream(yb + g);
+                if (AI) aa[k] = vload_stream(ai + g);
+                jv[k] = vload_ldg(jc + ch * V);
+            }
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                int p, ch; size_t g; chunk_of(tid + (it + k) * NT, x0, p, ch, g);
+                const Vec<T> z = vload(buf + p * N + swzp(ch, p) * V);
+                const T sgn = (p & 1) ? (T)-1 : (T)1;                  // x0 is even: + for even x, − for odd x
+                Vec<T> a0, u0;
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    const T kk = ADJ ? ta[k].v[q] + sgn * jv[k].v[q] + z.v[q] : p1a[k].v[q] * (ta[k].v[q] + sgn * jv[k].v[q]) + p2a[k].v[q] * z.v[q];
+                    const T y0 = YB ? ya[k].v[q] : (T)0;
+                    a0.v[q] = (AI ? aa[k].v[q] : y0) + cb * kk;
+                    u0.v[q] = y0 + ca * kk;
+                }
+                vstore(acc_out + pbase + g, a0);
+                if (UO) vstore(u_out + pbase + g, u0);
+            }
+        }
+    }
+
+    DEV void operator()(int blk, unsigned char* smem) const {
+        T* const sbase = reinterpret_cast<T*>(smem);                 // plain arithmetic on the shared base keeps LDS/STS (no generic LD/ST)
+        T* const pbuf = sbase + 2 * TILE;
+        const size_t nmap = (size_t)N * Nx;
+        const int kind = !acc_in ? 0 : (u_out ? 1 : 2);
+        auto plane_of = [&](int t) { return cbase + t / tiles_per_plane; };
+        auto x0_of = [&](int t) { return (t % tiles_per_plane) * M; };
+        Tw<R1> w1; Tw<R2> w2;
+        int tile = blk, cur = 0;
+        if (tile < ntiles) {
+            const int c = plane_of(tile);
+            CMBL_FOR_THREADS(tid, NT) {
+                issue_tile(u + (size_t)c * nmap, x0_of(tile), sbase, tid);
+                if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 1, nmap), x0_of(tile), pbuf, tid);
+                cp_async_commit();
+                CMBL_PRE_END(load_tw1(w1, tid));
+            }
+        }
+        for (; tile < ntiles; tile += nblocks, cur ^= 1) {
+            T* const buf = sbase + cur * TILE;
+            T* const nbuf = sbase + (cur ^ 1) * TILE;
+            const int c = plane_of(tile), x0 = x0_of(tile), next = tile + nblocks;
+            CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
+            CMBL_SYNC();
+            if (next < ntiles) {
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)plane_of(next) * nmap, x0_of(next), nbuf, tid); cp_async_commit(); }
+            }
+            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
+            CMBL_SYNC();
+            if (ADJ && next < ntiles) {
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, plane_of(next), Npol, Nbphi, 1, nmap), x0_of(next), pbuf, tid); cp_async_commit(); }
+            }
+            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) { middle(buf, tid, ADJ ? macc + (size_t)c * Nx : nullptr, x0); CMBL_PRE_END(load_tw2(w2, tid)); }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1); }
+            CMBL_SYNC();
+            const T* jc = jn + (size_t)c * N;
+            const T* p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
+            const T* p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
+            CMBL_FOR_THREADS(tid, NT) {
+                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
+                else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
+                else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
+                CMBL_PRE_END(load_tw1(w1, tid));                      // twiddles of the next tile's first sweep
+            }
+            // the next iteration's first barrier orders these shared-memory reads before the tile buffer is refilled
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// row kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, int LOGN, bool ADJ> struct FastRowBody {
+    static constexpr int NT = 128, MINB = ADJ ? 2 : 3;
+    static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), H = V / 2;          // H complex lines per chunk
+    static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
+    static constexpr int S1 = N / R1, N2 = N / R1, NB2 = N / R2, NBM = N / 16;
+    static constexpr int CPX = FAST_TILE_BYTES / (N * 16);                            // 16-byte chunks per x (even)
+    static constexpr int ROWS = CPX * V, L = ROWS / 2;                                // rows / complex lines per tile
+    static constexpr int TILE = FAST_TILE_BYTES / (int)sizeof(T);
+    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2) + 16;
+    static_assert(NT % S1 == 0 && NT % NB2 == 0 && NT % NBM == 0 && CPX % 2 == 0, "thread/butterfly mapping");
+    static_assert((CPX / 2) % (NT / S1) == 0 && (CPX / 2) % (NT / NB2) == 0 && CPX % (NT / NBM) == 0, "chunk-row mapping");
+    static const char* name() { return "flow_rows"; }
+
+    Fft1D<T> fx, fy; const T* mult; const T* mult_sign_y; T cN;
+    int Ny, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase;
+    const T* u; const T* pk; T* tmp; T* nline; T* jn; T* nacc; T wgt; int* counter;
+
+    struct Chunk { C2<T> c[H]; };
+    static DEV Chunk ld(const T* p) { Vec<T> v = vload(p); Chunk r; memcpy(&r, &v, 16); return r; }
+    static DEV void st(T* p, const Chunk& c) { Vec<T> v; memcpy(&v, &c, 16); vstore(p, v); }
+    static DEV Vec<T> asvec(const Chunk& c) { Vec<T> v; memcpy(&v, &c, 16); return v; }
+
+    DEV void issue_tile(const T* src /*the tile: one contiguous run in the row-grouped layout*/, T* buf, int tid) const {
+#pragma unroll 4
+        for (int k = tid; k < N * CPX; k += NT) {
+            const int x = k / CPX, cl = k % CPX;
+            cp_async16(buf + (cl * N + swzx(x)) * V, src + (size_t)k * V);
+        }
+    }
+    DEV void load_w1(int tid, C2<T>* w) const {
+        const int j = tid % S1;
+#pragma unroll
+        for (int q = 1; q < R1; ++q) w[q] = CMBL_LDG(&fx.W[j * q]);
+    }
+    DEV void load_w2(int tid, C2<T>* w) const {
+        const int jj = (tid % NB2) & 15;
+#pragma unroll
+        for (int q = 1; q < R2; ++q) w[q] = CMBL_LDG(&fx.W[jj * q * R1]);
+    }
+    DEV void load_mult(int tid, T* m) const {
+        const int j = tid % NBM;
+#pragma unroll
+        for (int cc = 0; cc < 16 / V; ++cc) { Vec<T> m4 = vload_ldg(mult + 16 * j + cc * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) m[cc * V + e] = m4.v[e]; }
+    }
+    // one twiddled radix-R sweep of one thread: butterfly index fixed (element m at x0 + m*xs), chunk-rows taken in adjacent
+    // pairs (cl, cl+1) so that the two butterflies overlap and, for the last sweep, leave as one 256-bit store
+    template <int R, bool INV, bool STORE_GLOBAL> DEV void pass(T* buf, const T* pbuf, int g0, int gs, int x0, int xs, const C2<T>* w, T* gdst) const {
+        for (int g = g0; g < CPX / 2; g += gs) {
+            Chunk x[2][R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int o = ((2 * g + s) * N + swzx(x0 + m * xs)) * V;
+                    x[s][m] = ld(buf + o);
+                    if (pbuf) {
+                        Vec<T> p = vload(pbuf + o); Vec<T> a = asvec(x[s][m]);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) a.v[e] *= p.v[e];
+                        memcpy(&x[s][m], &a, 16);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    C2<T> v[R];
+#pragma unroll
+                    for (int m = 0; m < R; ++m) v[m] = x[s][m].c[h];
+                    if (!INV) {
+                        dftR<T, R, false>(v);
+#pragma unroll
+                        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], w[q]);
+                        dftR<T, R, true>(v);
+                    }
+#pragma unroll
+                    for (int m = 0; m < R; ++m) x[s][m].c[h] = v[m];
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                if (STORE_GLOBAL) vstore2(gdst + ((size_t)(x0 + m * xs) * CPX + 2 * g) * V, asvec(x[0][m]), asvec(x[1][m]));
+                else {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) st(buf + ((2 * g + s) * N + swzx(x0 + m * xs)) * V, x[s][m]);
+                }
+            }
+        }
+    }
+    // fused middle: forward radix 16 · (Nyquist line N(y), src/proj_lambert.jl:63-64) · multiplier iℓx/N · inverse radix 16
+    static constexpr bool PRELOAD_MULT = sizeof(T) == 4;      // fp64: loading the 16 multipliers after the forward DFT avoids spills
+    DEV void middle(T* buf, int tid, const T* mlt_pre, T* nline_c, T* nacc_c, int y0) const {
+        const int j = tid % NBM;
+        for (int cl = tid / NBM; cl < CPX; cl += NT / NBM) {
+            Chunk x[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) x[q] = ld(buf + (cl * N + swzx(16 * j + q)) * V);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                C2<T> v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = x[q].c[h];
+                dft16<T, false>(v);
+                if (j == 0) {                                          // Nyquist coefficient sits at tile position 8
+                    const int y = y0 + 2 * (cl * H + h);
+                    nline_c[y] = v[8].x; nline_c[y + 1] = v[8].y;
+                    if (ADJ) { nacc_c[y] += wgt * v[8].x; nacc_c[y + 1] += wgt * v[8].y; }
+                }
+                if (PRELOAD_MULT) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = mk<T>(-mlt_pre[q] * v[q].y, mlt_pre[q] * v[q].x);
+                } else {
+                    T mlt[16];
+                    load_mult(tid, mlt);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = mk<T>(-mlt[q] * v[q].y, mlt[q] * v[q].x);
+                }
+                dft16<T, true>(v);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) x[q].c[h] = v[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) st(buf + (cl * N + swzx(16 * j + q)) * V, x[q]);
+        }
+    }
+
+    DEV void operator()(int blk, unsigned char* smem) const {
+        T* const sbase = reinterpret_cast<T*>(smem);
+        T* const pbuf = sbase + 2 * TILE;
+        int* flag = reinterpret_cast<int*>(smem + SMEM - 16);
+        const size_t nmap = (size_t)N * Ny;
+        C2<T> w1[R1], w2[R2]; T mlt[16];
+        int tile = blk, cur = 0;
+        if (tile < ntiles) {
+            const int c = cbase + tile / tiles_per_plane;
+            const size_t toff = (size_t)(tile % tiles_per_plane) * ROWS * N;
+            CMBL_FOR_THREADS(tid, NT) {
+                issue_tile(u + (size_t)c * nmap + toff, sbase, tid);
+                if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 0, nmap) + toff, pbuf, tid);
+                cp_async_commit();
+                CMBL_PRE_END(load_w1(tid, w1));
+            }
+        }
+        for (; tile < ntiles; tile += nblocks, cur ^= 1) {
+            T* const buf = sbase + cur * TILE;
+            T* const nbuf = sbase + (cur ^ 1) * TILE;
+            const int c = cbase + tile / tiles_per_plane, y0 = (tile % tiles_per_plane) * ROWS, next = tile + nblocks;
+            const int cn = cbase + next / tiles_per_plane;
+            const size_t toff = (size_t)(tile % tiles_per_plane) * ROWS * N, toffn = (size_t)(next % tiles_per_plane) * ROWS * N;
+            CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
+            CMBL_SYNC();
+            if (next < ntiles) {
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap + toffn, nbuf, tid); cp_async_commit(); }
+            }
+            CMBL_FOR_THREADS(tid, NT) {
+                CMBL_PRE_START(load_w1(tid, w1));
+                pass<R1, false, false>(buf, ADJ ? pbuf : nullptr, tid / S1, NT / S1, tid % S1, S1, w1, nullptr);
+                CMBL_PRE_END(load_w2(tid, w2));
+            }
+            CMBL_SYNC();
+            if (ADJ && next < ntiles) {
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 0, nmap) + toffn, pbuf, tid); cp_async_commit(); }
+            }
+            CMBL_FOR_THREADS(tid, NT) {
+                CMBL_PRE_START(load_w2(tid, w2));
+                const int j = tid % NB2;
+                pass<R2, false, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, w2, nullptr);
+                if (PRELOAD_MULT) { CMBL_PRE_END(load_mult(tid, mlt)); }
+            }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) {
+                if (PRELOAD_MULT) { CMBL_PRE_START(load_mult(tid, mlt)); }
+                middle(buf, tid, mlt, nline + (size_t)c * Ny, ADJ ? nacc + (size_t)c * Ny : nullptr, y0);
+                CMBL_PRE_END(load_w2(tid, w2));
+            }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) {
+                CMBL_PRE_START(load_w2(tid, w2));
+                const int j = tid % NB2;
+                pass<R2, true, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, w2, nullptr);
+                CMBL_PRE_END(load_w1(tid, w1));
+            }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) {
+                CMBL_PRE_START(load_w1(tid, w1));
+                pass<R1, true, true>(buf, nullptr, tid / S1, NT / S1, tid % S1, S1, w1, tmp + (size_t)c * nmap + toff);
+            }
+            // ---- the block that completes a plane turns its N(y) into jn = cN · J[N] -----------------------------------
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) {
+                if (tid == 0) *flag = (ticket_release(counter + c) == tiles_per_plane - 1) ? 1 : 0;
+            }
+            CMBL_SYNC();
+            if (*flag) {
+                Tile<T, false> t1 = line_tile<T>(reinterpret_cast<unsigned char*>(buf), 1, fy);
+                CMBL_FOR_THREADS(tid, NT) {
+                    for (int y = tid; y < Ny; y += NT) t1.at(0, y) = mk<T>(ld_cg(nline + (size_t)c * Ny + y), (T)0);
+                }
+                CMBL_SYNC();
+                SignMid<T> smid{mult_sign_y};
+                fft_spectral_op<T, false, NT>(t1, fy, smid);
+                CMBL_FOR_THREADS(tid, NT) {
+                    for (int y = tid; y < Ny; y += NT) jn[(size_t)c * Ny + y] = cN * t1.at(0, y).x;
+                    if (tid == 0) counter[c] = 0;
+                }
+            }
+            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_w1(tid, w1)); }
+        }
+    }
+};
+
+}  // namespace cmbl

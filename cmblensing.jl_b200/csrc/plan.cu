@@ -109,6 +109,16 @@ static void build_axis(std::vector<void*>& owned, AxisTables<T>& a, int N, T dl)
     a.mult_sign = upload_vec(owned, ms);
     a.ell_nyq = (T)(-(N / 2)) * dl;
     a.nyq_pos = pos[N / 2];
+    if (f.npass == 3 && f.radix[2] == 16) {
+        const int R1 = f.radix[0], R2 = f.radix[1], S1 = N / R1;
+        std::vector<T> t1((size_t)(R1 - 1) * 2 * S1), t2((size_t)(R2 - 1) * 2 * 16);
+        for (int q = 1; q < R1; ++q)
+            for (int j = 0; j < S1; ++j) { t1[((size_t)(q - 1) * 2) * S1 + j] = W[j * q].x; t1[((size_t)(q - 1) * 2 + 1) * S1 + j] = W[j * q].y; }
+        for (int q = 1; q < R2; ++q)
+            for (int jj = 0; jj < 16; ++jj) { t2[((size_t)(q - 1) * 2) * 16 + jj] = W[jj * q * R1].x; t2[((size_t)(q - 1) * 2 + 1) * 16 + jj] = W[jj * q * R1].y; }
+        a.ftw1 = upload_vec(owned, t1);
+        a.ftw2 = upload_vec(owned, t2);
+    }
 }
 
 template <class T> static std::unique_ptr<PlanBase> make_plan_t(int device, int Ny, int Nx, double theta_pix) {

@@ -14,6 +14,10 @@ template <class T> struct AxisTables {
     const T* mult_sign = nullptr;    // [N] tile order: sign(k(p)) / N      (DC and Nyquist 0)
     T ell_nyq = 0;                   // ℓ of the Nyquist frequency (negative, src/proj_lambert.jl:63-64)
     int nyq_pos = 0;                 // tile position of the Nyquist frequency after the forward passes
+    // fast path (flow_fast.cuh), only when the schedule is exactly [R1, R2, 16]: planar twiddle tables
+    //   ftw1[(q-1)][re|im][j]  = W_N^(j q),        j < N/R1, q = 1..R1-1     (first forward / last inverse pass)
+    //   ftw2[(q-1)][re|im][jj] = W_{N/R1}^(jj q),  jj < 16,  q = 1..R2-1     (second forward / first inverse pass)
+    const T* ftw1 = nullptr; const T* ftw2 = nullptr;
 };
 
 struct PlanBase {

@@ -93,6 +93,9 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
  * Nb_phi planes).  bug_compat != 0 reproduces the reference's aliased 2x2 product (src/lenseflow.jl:198-200). */
 int cmbl_lenseflow_grad(cmbl_flow* flow, int op, const void* f_out_map, const void* delta_four, void* dfield_four,
                         void* dphi_four, int bug_compat, void* stream);
+/* which stage kernels this flow runs (diagnostic): bit 0 = fast persistent row kernel, bit 1 = fast persistent column kernel
+ * (csrc/flow_fast.cuh; transform length 256/512/1024), 0 = generic kernels of csrc/flow.cuh */
+int cmbl_lenseflow_kernel_path(cmbl_flow* flow);
 /* read back one cached p map set for tests: out_host = p[k] as (Ny,Nx,2,Nb_phi) of the plan's dtype */
 int cmbl_lenseflow_get_p(cmbl_flow* flow, int k, void* out_host);
 
