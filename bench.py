@@ -239,14 +239,17 @@ def main():
         prof[nm] = (int(cnt), float(tot))
     peak, peak_src = measured_peak()
     tot_prof = sum(v[1] for v in prof.values())
-    cols_ms = prof["flow_cols"][1] / prof["flow_cols"][0]; rows_ms = prof["flow_rows"][1] / prof["flow_rows"][0]
-    dom = "flow_cols" if prof["flow_cols"][1] >= prof["flow_rows"][1] else "flow_rows"
-    dom_ms, dom_bytes = (cols_ms, AB["cols"]) if dom == "flow_cols" else (rows_ms, AB["rows"])
+    # algorithmic bytes per launch: row kernel 2C passes, column kernel 5C + 2Cϕ passes; the two layout
+    # conversions of an apply (2C passes each) are overhead outside the model
+    kbytes = {"flow_rows": AB["rows"], "flow_cols": AB["cols"], "layout_to_rg": 2 * NPOL * NB * AB["pass_bytes"], "layout_from_rg": 2 * NPOL * NB * AB["pass_bytes"]}
+    dom = max(("flow_cols", "flow_rows"), key=lambda k: prof[k][1])
+    dom_ms, dom_bytes = prof[dom][1] / prof[dom][0], kbytes[dom]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / dom_ms / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": dom_bytes / dom_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
                 "share_of_step": prof[dom][1] / tot_prof,
                 "algorithmic_bytes_per_launch": dom_bytes,
-                "kernels": {k: {"launches_per_step": v[0] // 2, "avg_ms": v[1] / v[0], "share": v[1] / tot_prof} for k, v in prof.items()}}
+                "kernels": {k: {"launches_per_step": v[0] // 2, "avg_ms": v[1] / v[0], "share": v[1] / tot_prof,
+                                "algorithmic_GBs": (kbytes[k] / (v[1] / v[0]) / 1e6 if k in kbytes else None)} for k, v in prof.items()}}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:

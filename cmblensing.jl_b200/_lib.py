@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_PATH = os.path.join(_HERE, "libcmbl_b200.so")
+DEFAULT_PATH = os.environ.get("CMBL_B200_LIB", os.path.join(_HERE, "libcmbl_b200.so"))      # override: kernel-variant experiments
 
 MAP, FOURIER = 0, 1
 OP_L, OP_LH, OP_LINV, OP_LHINV = 0, 1, 2, 3

@@ -35,7 +35,21 @@ template <class T> void flow_precompute(FlowT<T>& F, const void* phi, int phi_ba
 }
 
 static bool fast_enabled() { static const bool v = [] { const char* e = getenv("CMBL_FLOW_FAST"); return !e || atoi(e) != 0; }(); return v; }
-static int fast_pf() { static const int v = [] { const char* e = getenv("CMBL_FLOW_PF"); return e ? atoi(e) : 3; }(); return v; }
+static unsigned fast_stagger_ns() { static const unsigned v = [] { const char* e = getenv("CMBL_FLOW_STAGGER_NS"); return e ? (unsigned)atoi(e) : 0u; }(); return v; }
+static int device_sms() {
+#ifdef CMBL_EMU
+    return 2;
+#else
+    static thread_local int v = 0;
+    if (!v) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); }
+    return v;
+#endif
+}
+static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
+    static const int v = [] { const char* e = getenv("CMBL_FLOW_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
+    return v > 0 ? std::min(full, v * device_sms()) : full;
+}
+static int fast_pf() { static const int v = [] { const char* e = getenv("CMBL_FLOW_PF"); return e ? atoi(e) : 0; }(); return v; }
 
 template <class T, int LOGN, bool ADJ>
 static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cmblStream_t st) {
@@ -44,8 +58,8 @@ static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cm
     B b;
     b.fx = P.ax.fft; b.fy = P.ay.fft; b.mult = P.ax.mult_deriv; b.mult_sign_y = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
     b.Ny = P.Ny; b.tiles_per_plane = P.Ny / B::ROWS; b.ntiles = nC * b.tiles_per_plane;
-    b.nblocks = std::min(b.ntiles, persistent_blocks<B>(B::SMEM));
-    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
+    b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
+    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = reinterpret_cast<T*>(F.jn.p);
     b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt; b.counter = reinterpret_cast<int*>(F.counter.p);
     launch(b, b.nblocks, B::SMEM, st);
@@ -57,8 +71,8 @@ static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, co
     B b;
     b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv;
     b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / (2 * B::L); b.ntiles = nC * b.tiles_per_plane;
-    b.nblocks = std::min(b.ntiles, persistent_blocks<B>(B::SMEM));
-    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf();
+    b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
+    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.jn = reinterpret_cast<T*>(F.jn.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
     launch(b, b.nblocks, B::SMEM, st);

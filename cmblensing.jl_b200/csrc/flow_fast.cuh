@@ -52,6 +52,13 @@ DEV void l2_prefetch(const void* p, unsigned bytes) {
     (void)p; (void)bytes;
 #endif
 }
+DEV void l2_prefetch_line(const void* p) {                 // one 128-byte line
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
+#else
+    (void)p;
+#endif
+}
 // streaming 128-bit global load that does not allocate in L1 (L1 is kept for the twiddle / multiplier tables)
 template <class T> DEV Vec<T> vload_stream(const T* p);
 template <> DEV Vec<float> vload_stream<float>(const float* p) {
@@ -72,6 +79,23 @@ template <> DEV Vec<double> vload_stream<double>(const double* p) {
 #endif
     return r;
 }
+// two adjacent 16-byte chunks as one 256-bit streaming load (sm_100: ld.global.v8.f32 / v4.f64); p must be 32-byte aligned
+template <class T> DEV void vload_stream2(const T* p, Vec<T>& a, Vec<T>& b);
+template <> DEV void vload_stream2<float>(const float* p, Vec<float>& a, Vec<float>& b) {
+#ifdef __CUDA_ARCH__
+    asm("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3]),
+        "=f"(b.v[0]), "=f"(b.v[1]), "=f"(b.v[2]), "=f"(b.v[3]) : "l"(p));
+#else
+    a = vload(p); b = vload(p + 4);
+#endif
+}
+template <> DEV void vload_stream2<double>(const double* p, Vec<double>& a, Vec<double>& b) {
+#ifdef __CUDA_ARCH__
+    asm("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.v[0]), "=d"(a.v[1]), "=d"(b.v[0]), "=d"(b.v[1]) : "l"(p));
+#else
+    a = vload(p); b = vload(p + 2);
+#endif
+}
 // two adjacent 16-byte chunks as one 256-bit store (sm_100: st.global.v8.f32 / v4.f64); p must be 32-byte aligned
 template <class T> DEV void vstore2(T* p, const Vec<T>& a, const Vec<T>& b);
 template <> DEV void vstore2<float>(float* p, const Vec<float>& a, const Vec<float>& b) {
@@ -90,13 +114,22 @@ template <> DEV void vstore2<double>(double* p, const Vec<double>& a, const Vec<
 #endif
 }
 // ticket with release semantics only (MEMBAR.ALL.GPU + ATOMG): unlike __threadfence() it does not invalidate L1
-DEV int ticket_release(int* p) {
+// start-up stagger of the co-resident persistent blocks of an SM (blocks b, b+#SM, b+2·#SM share an SM): identical blocks
+// that start together stay phase-locked, so their shared-memory sweeps and their arithmetic collide instead of overlapping
+DEV void stagger_start(int blk, int sms, unsigned ns) {
+#ifdef __CUDA_ARCH__
+    if (ns) { const unsigned k = (unsigned)(blk / sms); if (k) __nanosleep(k * ns); }
+#else
+    (void)blk; (void)sms; (void)ns;
+#endif
+}
+DEV int ticket_release(int* p, int n) {
 #ifdef __CUDA_ARCH__
     unsigned old;
-    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"((unsigned)n) : "memory");
     return (int)old;
 #else
-    return __atomic_fetch_add(p, 1, __ATOMIC_ACQ_REL);
+    return __atomic_fetch_add(p, n, __ATOMIC_ACQ_REL);
 #endif
 }
 template <class T> DEV Vec<T> vload_ldg(const T* p) {        // cached read-only 128-bit load (tables)
@@ -181,6 +214,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
 
     const T* tw1; const T* tw2; const T* mult_d;
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
+    int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
     const T* ybase; const T* acc_in; T* acc_out; T* u_out; T ca, cb;
 
@@ -304,43 +338,66 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     // ---- velocity + RK4 update (src/lenseflow.jl:150-174, src/numerical_algorithms.jl:11-24) --------------------------
     //   forward: k = p₁·(tmp ± jn) + p₂·∂ᵧu          adjoint: k = tmp ± jn + ∂ᵧ(p₂·u)         (+ for even x, − for odd x)
     //   acc_out = (acc_in ? acc_in : ybase) + cb·k ;  u_out = ybase + ca·k  (if u_out)
-    // KIND 0: first stage (no acc_in), 1: middle stages, 2: last stage (no ybase, no u_out).  One 16-byte chunk per thread
-    // and iteration, chunks taken in memory order; the global loads of UNR iterations are issued before the first use.
+    // KIND 0: first stage (no acc_in), 1: middle stages, 2: last stage (no ybase, no u_out).  One 32-byte unit (two adjacent
+    // chunks of one column) per thread and iteration, units taken in memory order (256-bit accesses); the global loads of
+    // UNR iterations are issued before the first use.
+    DEV void unit_of(int k, int x0, int& p, int& ch, size_t& goff) const {          // k-th 32-byte unit of the tile
+        const int lgU = lgGV - 1, h = k & ((1 << lgU) - 1), yb = k >> (lgU + LGM);
+        p = (k >> lgU) & (M - 1); ch = (yb << lgGV) + 2 * h;
+        goff = ((size_t)yb * Nx + x0 + p) * G + 2 * h * V;
+    }
     template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2) const {
         constexpr bool YB = KIND != 2, AI = KIND != 0, UO = KIND != 2;
-        constexpr int ITER = M * CH / NT, UNR = 4;
+        constexpr int ITER = M * CH / 2 / NT, UNR = 2;
         static_assert(ITER % UNR == 0, "epilogue unroll");
         const T* tc = tmp + pbase;
         const T* yb = YB ? ybase + pbase : nullptr;
         const T* ai = AI ? acc_in + pbase : nullptr;
 #pragma unroll 1
         for (int it = 0; it < ITER; it += UNR) {
-            Vec<T> ta[UNR], p1a[UNR], p2a[UNR], ya[UNR], aa[UNR], jv[UNR];
+            Vec<T> ta[UNR][2], p1a[UNR][2], p2a[UNR][2], ya[UNR][2], aa[UNR][2], jv[UNR][2];
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
-                int p, ch; size_t g; chunk_of(tid + (it + k) * NT, x0, p, ch, g);
-                ta[k] = vload_stream(tc + g);
-                if (!ADJ) { p1a[k] = vload_stream(p1 + g); p2a[k] = vload_stream(p2 + g); }
-                if (YB) ya[k] = vload_stream(yb + g);
-                if (AI) aa[k] = vload_stream(ai + g);
-                jv[k] = vload_ldg(jc + ch * V);
+                int p, ch; size_t g; unit_of(tid + (it + k) * NT, x0, p, ch, g);
+                vload_stream2(tc + g, ta[k][0], ta[k][1]);
+                if (!ADJ) { vload_stream2(p1 + g, p1a[k][0], p1a[k][1]); vload_stream2(p2 + g, p2a[k][0], p2a[k][1]); }
+                if (YB) vload_stream2(yb + g, ya[k][0], ya[k][1]);
+                if (AI) vload_stream2(ai + g, aa[k][0], aa[k][1]);
+                jv[k][0] = vload_ldg(jc + ch * V); jv[k][1] = vload_ldg(jc + (ch + 1) * V);
             }
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
-                int p, ch; size_t g; chunk_of(tid + (it + k) * NT, x0, p, ch, g);
-                const Vec<T> z = vload(buf + p * N + swzp(ch, p) * V);
+                int p, ch; size_t g; unit_of(tid + (it + k) * NT, x0, p, ch, g);
                 const T sgn = (p & 1) ? (T)-1 : (T)1;                  // x0 is even: + for even x, − for odd x
-                Vec<T> a0, u0;
+                Vec<T> a0[2], u0[2];
 #pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    const T kk = ADJ ? ta[k].v[q] + sgn * jv[k].v[q] + z.v[q] : p1a[k].v[q] * (ta[k].v[q] + sgn * jv[k].v[q]) + p2a[k].v[q] * z.v[q];
-                    const T y0 = YB ? ya[k].v[q] : (T)0;
-                    a0.v[q] = (AI ? aa[k].v[q] : y0) + cb * kk;
-                    u0.v[q] = y0 + ca * kk;
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const Vec<T> z = vload(buf + p * N + swzp(ch + s2, p) * V);
+#pragma unroll
+                    for (int q = 0; q < V; ++q) {
+                        const T kk = ADJ ? ta[k][s2].v[q] + sgn * jv[k][s2].v[q] + z.v[q]
+                                         : p1a[k][s2].v[q] * (ta[k][s2].v[q] + sgn * jv[k][s2].v[q]) + p2a[k][s2].v[q] * z.v[q];
+                        const T y0 = YB ? ya[k][s2].v[q] : (T)0;
+                        a0[s2].v[q] = (AI ? aa[k][s2].v[q] : y0) + cb * kk;
+                        u0[s2].v[q] = y0 + ca * kk;
+                    }
                 }
-                vstore(acc_out + pbase + g, a0);
-                if (UO) vstore(u_out + pbase + g, u0);
+                vstore2(acc_out + pbase + g, a0[0], a0[1]);
+                if (UO) vstore2(u_out + pbase + g, u0[0], u0[1]);
             }
+        }
+    }
+    // pull the epilogue operands of this tile into L2 (one bulk prefetch per contiguous run of M columns x G rows)
+    DEV void prefetch_epilogue(int tid, size_t pbase, int x0, const T* p1, const T* p2) const {
+        constexpr int LINE = 128 / (int)sizeof(T);                 // elements per 128-byte line
+        const int lines_per_run = M * G / LINE;                   // a run = M columns x G rows, contiguous
+        for (int i = tid; i < (N / G) * lines_per_run; i += NT) {
+            const int yb = i / lines_per_run, ln = i % lines_per_run;
+            const size_t g = ((size_t)yb * Nx + x0) * G + (size_t)ln * LINE;
+            l2_prefetch_line(tmp + pbase + g);
+            if (!ADJ) { l2_prefetch_line(p1 + g); l2_prefetch_line(p2 + g); }
+            if (ybase) l2_prefetch_line(ybase + pbase + g);
+            if (acc_in) l2_prefetch_line(acc_in + pbase + g);
         }
     }
 
@@ -352,6 +409,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         auto plane_of = [&](int t) { return cbase + t / tiles_per_plane; };
         auto x0_of = [&](int t) { return (t % tiles_per_plane) * M; };
         Tw<R1> w1; Tw<R2> w2;
+        stagger_start(blk, sms, stagger_ns);
         int tile = blk, cur = 0;
         if (tile < ntiles) {
             const int c = plane_of(tile);
@@ -376,17 +434,17 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             if (ADJ && next < ntiles) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, plane_of(next), Npol, Nbphi, 1, nmap), x0_of(next), pbuf, tid); cp_async_commit(); }
             }
-            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
-            CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) { middle(buf, tid, ADJ ? macc + (size_t)c * Nx : nullptr, x0); CMBL_PRE_END(load_tw2(w2, tid)); }
-            CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
-            CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1); }
-            CMBL_SYNC();
             const T* jc = jn + (size_t)c * N;
             const T* p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
             const T* p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 2) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); middle(buf, tid, ADJ ? macc + (size_t)c * Nx : nullptr, x0); CMBL_PRE_END(load_tw2(w2, tid)); }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 3) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1); }
+            CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
                 if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
                 else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
@@ -401,8 +459,14 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
 // ---------------------------------------------------------------------------------------------------------------
 // row kernel
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef CMBL_ROW_F64_MINB
+#define CMBL_ROW_F64_MINB 2          // fp64 row kernel: 2 blocks/SM at 255 registers (no spills) beat 3 blocks/SM at 168 (measured 128 vs 140 us)
+#endif
+#ifndef CMBL_ROW_PAIR
+#define CMBL_ROW_PAIR 1          // 1: two chunk-rows per butterfly step in every sweep; 0: only in the last (256-bit stores)
+#endif
 template <class T, int LOGN, bool ADJ> struct FastRowBody {
-    static constexpr int NT = 128, MINB = ADJ ? 2 : 3;
+    static constexpr int NT = 128, MINB = ADJ ? 2 : (sizeof(T) == 8 ? CMBL_ROW_F64_MINB : 3);
     static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), H = V / 2;          // H complex lines per chunk
     static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
     static constexpr int S1 = N / R1, N2 = N / R1, NB2 = N / R2, NBM = N / 16;
@@ -416,6 +480,7 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
 
     Fft1D<T> fx, fy; const T* mult; const T* mult_sign_y; T cN;
     int Ny, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase;
+    int sms; unsigned stagger_ns;
     const T* u; const T* pk; T* tmp; T* nline; T* jn; T* nacc; T wgt; int* counter;
 
     struct Chunk { C2<T> c[H]; };
@@ -450,48 +515,52 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
     // one twiddled radix-R sweep of one thread: butterfly index fixed (element m at x0 + m*xs), chunk-rows taken in adjacent
     // pairs (cl, cl+1) so that the two butterflies overlap and, for the last sweep, leave as one 256-bit store
     template <int R, bool INV, bool STORE_GLOBAL> DEV void pass(T* buf, const T* pbuf, int g0, int gs, int x0, int xs, const C2<T>* w, T* gdst) const {
+        constexpr int PW = (STORE_GLOBAL || CMBL_ROW_PAIR) ? 2 : 1;      // chunk-rows handled together
         for (int g = g0; g < CPX / 2; g += gs) {
-            Chunk x[2][R];
 #pragma unroll
-            for (int m = 0; m < R; ++m) {
+            for (int s0 = 0; s0 < 2; s0 += PW) {
+                Chunk x[PW][R];
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int o = ((2 * g + s) * N + swzx(x0 + m * xs)) * V;
-                    x[s][m] = ld(buf + o);
-                    if (pbuf) {
-                        Vec<T> p = vload(pbuf + o); Vec<T> a = asvec(x[s][m]);
+                for (int m = 0; m < R; ++m) {
 #pragma unroll
-                        for (int e = 0; e < V; ++e) a.v[e] *= p.v[e];
-                        memcpy(&x[s][m], &a, 16);
+                    for (int s = 0; s < PW; ++s) {
+                        const int o = ((2 * g + s0 + s) * N + swzx(x0 + m * xs)) * V;
+                        x[s][m] = ld(buf + o);
+                        if (pbuf) {
+                            Vec<T> p = vload(pbuf + o); Vec<T> a = asvec(x[s][m]);
+#pragma unroll
+                            for (int e = 0; e < V; ++e) a.v[e] *= p.v[e];
+                            memcpy(&x[s][m], &a, 16);
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+                for (int s = 0; s < PW; ++s) {
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    C2<T> v[R];
+                    for (int h = 0; h < H; ++h) {
+                        C2<T> v[R];
 #pragma unroll
-                    for (int m = 0; m < R; ++m) v[m] = x[s][m].c[h];
-                    if (!INV) {
-                        dftR<T, R, false>(v);
+                        for (int m = 0; m < R; ++m) v[m] = x[s][m].c[h];
+                        if (!INV) {
+                            dftR<T, R, false>(v);
 #pragma unroll
-                        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
-                    } else {
+                            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+                        } else {
 #pragma unroll
-                        for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], w[q]);
-                        dftR<T, R, true>(v);
+                            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], w[q]);
+                            dftR<T, R, true>(v);
+                        }
+#pragma unroll
+                        for (int m = 0; m < R; ++m) x[s][m].c[h] = v[m];
                     }
-#pragma unroll
-                    for (int m = 0; m < R; ++m) x[s][m].c[h] = v[m];
                 }
-            }
 #pragma unroll
-            for (int m = 0; m < R; ++m) {
-                if (STORE_GLOBAL) vstore2(gdst + ((size_t)(x0 + m * xs) * CPX + 2 * g) * V, asvec(x[0][m]), asvec(x[1][m]));
-                else {
+                for (int m = 0; m < R; ++m) {
+                    if (STORE_GLOBAL) vstore2(gdst + ((size_t)(x0 + m * xs) * CPX + 2 * g) * V, asvec(x[0][m]), asvec(x[PW - 1][m]));
+                    else {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) st(buf + ((2 * g + s) * N + swzx(x0 + m * xs)) * V, x[s][m]);
+                        for (int s = 0; s < PW; ++s) st(buf + ((2 * g + s0 + s) * N + swzx(x0 + m * xs)) * V, x[s][m]);
+                    }
                 }
             }
         }
@@ -533,32 +602,51 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
         }
     }
 
+    // jn = cN · J[N] for plane c (executed once per plane and launch by the block that completes the plane; kept out of
+    // line so that its register needs do not leak into the tile loop)
+    DEV void jn_line(unsigned char* smem_line, int c) const {
+        Tile<T, false> tl = line_tile<T>(smem_line, 1, fy);
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int y = tid; y < Ny; y += NT) tl.at(0, y) = mk<T>(ld_cg(nline + (size_t)c * Ny + y), (T)0);
+        }
+        CMBL_SYNC();
+        SignMid<T> smid{mult_sign_y};
+        fft_spectral_op<T, false, NT>(tl, fy, smid);
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int y = tid; y < Ny; y += NT) jn[(size_t)c * Ny + y] = cN * tl.at(0, y).x;
+            if (tid == 0) counter[c] = 0;
+        }
+    }
+
     DEV void operator()(int blk, unsigned char* smem) const {
         T* const sbase = reinterpret_cast<T*>(smem);
         T* const pbuf = sbase + 2 * TILE;
         int* flag = reinterpret_cast<int*>(smem + SMEM - 16);
         const size_t nmap = (size_t)N * Ny;
         C2<T> w1[R1], w2[R2]; T mlt[16];
-        int tile = blk, cur = 0;
-        if (tile < ntiles) {
+        // block b owns the contiguous tile range [tbeg, tend): at most a few planes per block, so the per-plane completion
+        // ticket (a release atomic that has to wait for the block's stores) is paid once per plane, not once per tile
+        stagger_start(blk, sms, stagger_ns);
+        const int tbeg = (int)((long long)blk * ntiles / nblocks), tend = (int)((long long)(blk + 1) * ntiles / nblocks);
+        int tile = tbeg, cur = 0, done_in_plane = 0;
+        if (tile < tend) {
             const int c = cbase + tile / tiles_per_plane;
             const size_t toff = (size_t)(tile % tiles_per_plane) * ROWS * N;
             CMBL_FOR_THREADS(tid, NT) {
                 issue_tile(u + (size_t)c * nmap + toff, sbase, tid);
                 if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 0, nmap) + toff, pbuf, tid);
                 cp_async_commit();
-                CMBL_PRE_END(load_w1(tid, w1));
             }
         }
-        for (; tile < ntiles; tile += nblocks, cur ^= 1) {
+        for (; tile < tend; ++tile, cur ^= 1) {
             T* const buf = sbase + cur * TILE;
             T* const nbuf = sbase + (cur ^ 1) * TILE;
-            const int c = cbase + tile / tiles_per_plane, y0 = (tile % tiles_per_plane) * ROWS, next = tile + nblocks;
+            const int c = cbase + tile / tiles_per_plane, y0 = (tile % tiles_per_plane) * ROWS, next = tile + 1;
             const int cn = cbase + next / tiles_per_plane;
             const size_t toff = (size_t)(tile % tiles_per_plane) * ROWS * N, toffn = (size_t)(next % tiles_per_plane) * ROWS * N;
-            CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
+            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_w1(tid, w1)); cp_async_wait_all(); }
             CMBL_SYNC();
-            if (next < ntiles) {
+            if (next < tend) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap + toffn, nbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) {
@@ -567,7 +655,7 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
                 CMBL_PRE_END(load_w2(tid, w2));
             }
             CMBL_SYNC();
-            if (ADJ && next < ntiles) {
+            if (ADJ && next < tend) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 0, nmap) + toffn, pbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) {
@@ -595,25 +683,15 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
                 pass<R1, true, true>(buf, nullptr, tid / S1, NT / S1, tid % S1, S1, w1, tmp + (size_t)c * nmap + toff);
             }
             // ---- the block that completes a plane turns its N(y) into jn = cN · J[N] -----------------------------------
+            ++done_in_plane;
+            if (next < tend && cn == c) continue;                        // more tiles of this plane follow in this block
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
-                if (tid == 0) *flag = (ticket_release(counter + c) == tiles_per_plane - 1) ? 1 : 0;
+                if (tid == 0) *flag = (ticket_release(counter + c, done_in_plane) + done_in_plane == tiles_per_plane) ? 1 : 0;
             }
+            done_in_plane = 0;
             CMBL_SYNC();
-            if (*flag) {
-                Tile<T, false> t1 = line_tile<T>(reinterpret_cast<unsigned char*>(buf), 1, fy);
-                CMBL_FOR_THREADS(tid, NT) {
-                    for (int y = tid; y < Ny; y += NT) t1.at(0, y) = mk<T>(ld_cg(nline + (size_t)c * Ny + y), (T)0);
-                }
-                CMBL_SYNC();
-                SignMid<T> smid{mult_sign_y};
-                fft_spectral_op<T, false, NT>(t1, fy, smid);
-                CMBL_FOR_THREADS(tid, NT) {
-                    for (int y = tid; y < Ny; y += NT) jn[(size_t)c * Ny + y] = cN * t1.at(0, y).x;
-                    if (tid == 0) counter[c] = 0;
-                }
-            }
-            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_w1(tid, w1)); }
+            if (*flag) jn_line(reinterpret_cast<unsigned char*>(buf), c);
         }
     }
 };
