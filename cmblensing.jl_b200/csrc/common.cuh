@@ -168,6 +168,9 @@ template <class Body> struct KernelName { static const char* get() { return Body
 #ifndef CMBL_EMU
 template <class Body, class = void> struct MinBlocks { static constexpr int value = 1; };
 template <class Body> struct MinBlocks<Body, decltype((void)Body::MINB)> { static constexpr int value = Body::MINB; };
+template <class Body, class = void> struct UsesPdl { static constexpr bool value = false; };
+template <class Body> struct UsesPdl<Body, decltype((void)Body::PDL)> { static constexpr bool value = Body::PDL; };
+inline bool pdl_enabled() { static const bool v = [] { const char* e = getenv("CMBL_PDL"); return e && atoi(e) != 0; }(); return v; }
 template <class Body> __global__ void __launch_bounds__(Body::NT, MinBlocks<Body>::value) kern(const Body b) {
     extern __shared__ __align__(16) unsigned char cmbl_smem[];
     b((int)blockIdx.x, cmbl_smem);
@@ -181,6 +184,8 @@ template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStre
     (void)st;
     int nthr = (int)std::thread::hardware_concurrency(); if (nthr < 1) nthr = 1; if (nthr > grid) nthr = grid;
     if (const char* e = getenv("CMBL_EMU_THREADS")) { nthr = atoi(e); if (nthr < 1) nthr = 1; }
+    if (grid <= 64) nthr = grid;       // small (persistent) grids: every block gets its own host thread — blocks of a persistent
+                                       // kernel may wait for each other (flags), so all of them must be running
     std::atomic<int> next(0);
     auto worker = [&]() {
         std::vector<unsigned char> buf(smem + 64);
@@ -197,7 +202,14 @@ template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStre
         configured = true;
     }
     if (g_profiling) prof_before(Body::name(), st);
-    kern<Body><<<grid, Body::NT, smem, st>>>(b);
+    if (UsesPdl<Body>::value && pdl_enabled() && !g_profiling) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Body::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CMBL_CUDA(cudaLaunchKernelEx(&cfg, kern<Body>, b));
+    } else kern<Body><<<grid, Body::NT, smem, st>>>(b);
     if (g_profiling) prof_after(st);
     CMBL_CUDA(cudaGetLastError());
 #endif

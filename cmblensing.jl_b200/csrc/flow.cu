@@ -56,12 +56,12 @@ static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cm
     PlanT<T>& P = *F.P;
     typedef FastRowBody<T, LOGN, ADJ> B;
     B b;
-    b.fx = P.ax.fft; b.fy = P.ay.fft; b.mult = P.ax.mult_deriv; b.mult_sign_y = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
+    b.fx = P.ax.fft; b.mult = P.ax.mult_deriv;
     b.Ny = P.Ny; b.tiles_per_plane = P.Ny / B::ROWS; b.ntiles = nC * b.tiles_per_plane;
     b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
     b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
-    b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = reinterpret_cast<T*>(F.jn.p);
-    b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt; b.counter = reinterpret_cast<int*>(F.counter.p);
+    b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.nline = reinterpret_cast<T*>(F.nline.p);
+    b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
     launch(b, b.nblocks, B::SMEM, st);
 }
 template <class T, int LOGN, bool ADJ>
@@ -69,11 +69,14 @@ static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, co
     PlanT<T>& P = *F.P;
     typedef FastColBody<T, LOGN, ADJ> B;
     B b;
-    b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv;
+    b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv; b.mult_sign = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
     b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / (2 * B::L); b.ntiles = nC * b.tiles_per_plane;
     b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
     b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
-    b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.jn = reinterpret_cast<T*>(F.jn.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
+    b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
+    b.nline = reinterpret_cast<T*>(F.nline.p); b.jn_blk = reinterpret_cast<T*>(F.jn.p); b.jn = nullptr;
+    if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
+    b.jn_flag = reinterpret_cast<int*>(F.jnflag.p); b.epoch = ++F.jn_epoch;
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
     launch(b, b.nblocks, B::SMEM, st);
 }

@@ -329,6 +329,7 @@ template <class T> struct FlowT : FlowBase {
     bool have_p = false, have_minv = false;
     int pcache_G = 0;                    // layout of pcache / minv: 0 = reference layout, else rows per row group
     DevBuf yrg;                          // row-grouped copy of the ODE state
+    DevBuf jnflag; int jn_epoch = 0;     // per-plane publication flags of J[N] inside the fast column kernel (value = launch epoch)
     DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, jn, counter, nacc, macc, rows0, spec, gh;
     size_t nmap() const { return P->map_elems(); }
     const T* pk(int k) const { return reinterpret_cast<T*>(pcache.p) + (size_t)k * Nbphi * 2 * nmap(); }

@@ -123,6 +123,39 @@ DEV void stagger_start(int blk, int sms, unsigned ns) {
     (void)blk; (void)sms; (void)ns;
 #endif
 }
+// programmatic dependent launch: the stage kernels are launched back to back on one stream with programmatic stream
+// serialization, so the next kernel's blocks are scheduled (and load their constant tables) while the previous one drains;
+// pdl_wait() blocks until the previous kernel has completed and its writes are visible
+DEV void pdl_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+DEV void pdl_launch_dependents() {
+#ifdef __CUDA_ARCH__
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// publish / await a per-plane flag inside one persistent launch (all blocks are resident, so the producer always runs)
+DEV void flag_publish(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#endif
+}
+DEV void flag_await(const int* p, int v) {
+#ifdef __CUDA_ARCH__
+    int got;
+    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p) : "memory"); if (got != v) __nanosleep(200); } while (got != v);
+#else
+    while (__atomic_load_n(p, __ATOMIC_ACQUIRE) != v) {
+#ifdef CMBL_EMU
+        std::this_thread::yield();
+#endif
+    }
+#endif
+}
 DEV int ticket_release(int* p, int n) {
 #ifdef __CUDA_ARCH__
     unsigned old;
@@ -130,6 +163,13 @@ DEV int ticket_release(int* p, int n) {
     return (int)old;
 #else
     return __atomic_fetch_add(p, n, __ATOMIC_ACQ_REL);
+#endif
+}
+template <class T> DEV Vec<T> vload_cg(const T* p) {         // 128-bit load that bypasses L1 (data published by another block)
+#ifdef __CUDA_ARCH__
+    Vec<T> r; const float4 q = __ldcg(reinterpret_cast<const float4*>(p)); memcpy(&r, &q, 16); return r;
+#else
+    return vload(p);
 #endif
 }
 template <class T> DEV Vec<T> vload_ldg(const T* p) {        // cached read-only 128-bit load (tables)
@@ -207,12 +247,15 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     static constexpr int L = TILE / (2 * N);                                         // complex lines (column pairs) per tile
     static constexpr int NB1 = S1 / V, NB2 = N / (R2 * V);                           // bundles per line in pass 1 / pass 2
     static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2);
+    static constexpr bool PDL = true;
     static const char* name() { return "flow_cols"; }
 
     static constexpr int M = 2 * L, LGM = (M == 2 ? 1 : M == 4 ? 2 : M == 8 ? 3 : M == 16 ? 4 : M == 32 ? 5 : 6);
     static_assert((1 << LGM) == M, "columns per tile must be a power of two <= 64");
 
-    const T* tw1; const T* tw2; const T* mult_d;
+    const T* tw1; const T* tw2; const T* mult_d; const T* mult_sign; T cN;     // mult_sign, cN: the Nyquist line operator J (flow.cuh)
+    const T* nline; T* jn_blk;                       // N(y) per plane (row kernel); J[N] lines: [plane][N] (shared by a plane's blocks)
+    int* jn_flag; int epoch;                         // jn_flag[plane] == epoch  <=>  this launch's J[N] of the plane is published
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
@@ -281,8 +324,8 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             vstore(re + (o ^ xr_) * V, xr[m]); vstore(im + (o ^ xi_) * V, xi[m]);
         }
     }
-    template <bool INV> DEV void pass1(T* buf, const T* pbuf, int tid, Tw<R1>& w) const {
-        for (int task = tid; task < L * NB1; task += NT) {
+    template <bool INV> DEV void pass1(T* buf, const T* pbuf, int tid, Tw<R1>& w, int nl = L) const {
+        for (int task = tid; task < nl * NB1; task += NT) {
             const int l = task / NB1, b = task % NB1;
             if (task != tid) load_tw1(w, task);
             T* re = buf + (2 * l) * N; T* im = re + N;
@@ -290,8 +333,8 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             bundle_pass<R1, INV>(re, im, pxor(2 * l), pxor(2 * l + 1), b, S1 / V, w, pre, pre ? pre + N : nullptr);
         }
     }
-    template <bool INV> DEV void pass2(T* buf, int tid, Tw<R2>& w) const {
-        for (int task = tid; task < L * NB2; task += NT) {
+    template <bool INV> DEV void pass2(T* buf, int tid, Tw<R2>& w, int nl = L) const {
+        for (int task = tid; task < nl * NB2; task += NT) {
             const int l = task / NB2, b = task % NB2;
             if (task != tid) load_tw2(w, task);
             const int j0 = V * b, jj0 = j0 & 15, a = j0 >> 4;
@@ -300,14 +343,14 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         }
     }
     // fused middle: forward radix 16, multiplier iℓ/N (tile order), Nyquist bookkeeping of the adjoint flow, inverse radix 16
-    DEV void middle(T* buf, int tid, T* macc_c, int x0) const {
+    DEV void middle(T* buf, int tid, T* macc_c, int x0, const T* mtab, int nl = L) const {
         constexpr int NB = N / 16, CPB = 16 / V;                    // butterflies per line, chunks per butterfly
-        for (int task = tid; task < L * NB; task += NT) {
+        for (int task = tid; task < nl * NB; task += NT) {
             const int l = task / NB, j = task % NB;
             T* re = buf + (2 * l) * N; T* im = re + N;
             T mlt[16];
 #pragma unroll
-            for (int cc = 0; cc < CPB; ++cc) { Vec<T> m4 = vload_ldg(mult_d + 16 * j + cc * V);
+            for (int cc = 0; cc < CPB; ++cc) { Vec<T> m4 = vload_ldg(mtab + 16 * j + cc * V);
 #pragma unroll
                 for (int e = 0; e < V; ++e) mlt[cc * V + e] = m4.v[e]; }
             C2<T> v[16];
@@ -320,7 +363,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
                 for (int e = 0; e < V; ++e) v[cc * V + e] = mk<T>(a.v[e], b.v[e]);
             }
             dft16<T, false>(v);
-            if (ADJ && j == 0) { macc_c[x0 + 2 * l] += wgt * v[8].x; macc_c[x0 + 2 * l + 1] += wgt * v[8].y; }   // Nyquist coefficient: position 8
+            if (ADJ && macc_c && j == 0) { macc_c[x0 + 2 * l] += wgt * v[8].x; macc_c[x0 + 2 * l + 1] += wgt * v[8].y; }   // Nyquist coefficient: position 8
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = mk<T>(-mlt[q] * v[q].y, mlt[q] * v[q].x);
             dft16<T, true>(v);
@@ -363,7 +406,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
                 if (!ADJ) { vload_stream2(p1 + g, p1a[k][0], p1a[k][1]); vload_stream2(p2 + g, p2a[k][0], p2a[k][1]); }
                 if (YB) vload_stream2(yb + g, ya[k][0], ya[k][1]);
                 if (AI) vload_stream2(ai + g, aa[k][0], aa[k][1]);
-                jv[k][0] = vload_ldg(jc + ch * V); jv[k][1] = vload_ldg(jc + (ch + 1) * V);
+                jv[k][0] = vload(jc + ch * V); jv[k][1] = vload(jc + (ch + 1) * V);   // published by a peer block before this block's first read (flag), L1 starts empty
             }
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
@@ -401,54 +444,100 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         }
     }
 
+    // jn = cN · J[N] of plane c into this block's scratch line: one more spectral operator on a single (real) line, done in
+    // the tile buffer that is not in use (block start: while the first tile is in flight; later: only when the plane changes).
+    DEV void jn_line(T* ws, int c, T* jdst, Tw<R1>& w1, Tw<R2>& w2) const {
+        const T* nl = nline + (size_t)c * N;
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int ch = tid; ch < CH; ch += NT) {
+                Vec<T> z; for (int e = 0; e < V; ++e) z.v[e] = 0;
+                vstore(ws + swzp(ch, 0) * V, vload(nl + ch * V)); vstore(ws + N + swzp(ch, 1) * V, z);
+            }
+            load_tw1(w1, tid);
+        }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(ws, nullptr, tid, w1, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(ws, tid, w2, 1); }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) { middle(ws, tid, nullptr, 0, mult_sign, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(ws, tid, w2, 1); CMBL_PRE_END(load_tw1(w1, tid)); }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(ws, nullptr, tid, w1, 1); }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) {
+            for (int ch = tid; ch < CH; ch += NT) {
+                Vec<T> z = vload(ws + swzp(ch, 0) * V);
+                for (int e = 0; e < V; ++e) z.v[e] *= cN;
+                vstore(jdst + ch * V, z);
+            }
+        }
+        CMBL_SYNC();
+    }
+
     DEV void operator()(int blk, unsigned char* smem) const {
         T* const sbase = reinterpret_cast<T*>(smem);                 // plain arithmetic on the shared base keeps LDS/STS (no generic LD/ST)
         T* const pbuf = sbase + 2 * TILE;
         const size_t nmap = (size_t)N * Nx;
         const int kind = !acc_in ? 0 : (u_out ? 1 : 2);
-        auto plane_of = [&](int t) { return cbase + t / tiles_per_plane; };
-        auto x0_of = [&](int t) { return (t % tiles_per_plane) * M; };
         Tw<R1> w1; Tw<R2> w2;
-        stagger_start(blk, sms, stagger_ns);
-        int tile = blk, cur = 0;
+        pdl_launch_dependents();
+        pdl_wait();
+        // Tile assignment: round-robin over all tiles of the launch (neighbouring blocks work on neighbouring column tiles at
+        // the same time: their 128/256-byte runs share DRAM pages; the launch sweeps through the planes in order).
+        // J[N] of every plane is computed at the start of the launch by the blocks with the highest indices (they have the
+        // fewest tiles) and published through a per-plane flag; a block waits for the flag of a plane (only thread 0 polls)
+        // right before the first epilogue it runs on that plane — by then the line has normally long been published.
+        const int nC = ntiles / tiles_per_plane;
+        int tile = blk, cur = 0, cj = -1;
         if (tile < ntiles) {
-            const int c = plane_of(tile);
+            const int c = cbase + tile / tiles_per_plane, x0 = (tile % tiles_per_plane) * M;
             CMBL_FOR_THREADS(tid, NT) {
-                issue_tile(u + (size_t)c * nmap, x0_of(tile), sbase, tid);
-                if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 1, nmap), x0_of(tile), pbuf, tid);
+                issue_tile(u + (size_t)c * nmap, x0, sbase, tid);
+                if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 1, nmap), x0, pbuf, tid);
                 cp_async_commit();
-                CMBL_PRE_END(load_tw1(w1, tid));
             }
         }
+        for (int i = nblocks - 1 - blk; i < nC; i += nblocks) {       // while the first tile is in flight
+            jn_line(sbase + TILE, cbase + i, jn_blk + (size_t)(cbase + i) * N, w1, w2);
+            CMBL_FOR_THREADS(tid, NT) { if (tid == 0) flag_publish(jn_flag + cbase + i, epoch); }
+        }
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
         for (; tile < ntiles; tile += nblocks, cur ^= 1) {
             T* const buf = sbase + cur * TILE;
             T* const nbuf = sbase + (cur ^ 1) * TILE;
-            const int c = plane_of(tile), x0 = x0_of(tile), next = tile + nblocks;
+            const int c = cbase + tile / tiles_per_plane, x0 = (tile % tiles_per_plane) * M, next = tile + nblocks;
+            const int cn = cbase + next / tiles_per_plane, x0n = (next % tiles_per_plane) * M;
+            const T* const p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
+            const T* const p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
+            const T* const jline = jn_blk + (size_t)c * N;
             CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
             CMBL_SYNC();
             if (next < ntiles) {
-                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)plane_of(next) * nmap, x0_of(next), nbuf, tid); cp_async_commit(); }
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
             if (ADJ && next < ntiles) {
-                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, plane_of(next), Npol, Nbphi, 1, nmap), x0_of(next), pbuf, tid); cp_async_commit(); }
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0n, pbuf, tid); cp_async_commit(); }
             }
-            const T* jc = jn + (size_t)c * N;
-            const T* p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
-            const T* p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
             CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
             CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) { if (pf == 2) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); middle(buf, tid, ADJ ? macc + (size_t)c * Nx : nullptr, x0); CMBL_PRE_END(load_tw2(w2, tid)); }
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 2) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); middle(buf, tid, ADJ ? macc + (size_t)c * Nx : nullptr, x0, mult_d); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) { if (pf == 3) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
             CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) { if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1); }
+            CMBL_FOR_THREADS(tid, NT) {
+                if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1);
+                if (c != cj && tid == 0) flag_await(jn_flag + c, epoch);
+            }
+            cj = c;
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
-                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
-                else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
-                else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jc, p1, p2);
+                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
+                else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
+                else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
                 CMBL_PRE_END(load_tw1(w1, tid));                      // twiddles of the next tile's first sweep
             }
             // the next iteration's first barrier orders these shared-memory reads before the tile buffer is refilled
@@ -459,6 +548,14 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
 // ---------------------------------------------------------------------------------------------------------------
 // row kernel
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef CMBL_ABLATE
+#define CMBL_ABLATE 0            // experiments only: 1 = row kernel without butterfly arithmetic, 2 = without inter-sweep barriers
+#endif
+#if CMBL_ABLATE == 2
+#define ROW_SWEEP_SYNC() ((void)0)
+#else
+#define ROW_SWEEP_SYNC() CMBL_SYNC()
+#endif
 #ifndef CMBL_ROW_F64_MINB
 #define CMBL_ROW_F64_MINB 2          // fp64 row kernel: 2 blocks/SM at 255 registers (no spills) beat 3 blocks/SM at 168 (measured 128 vs 140 us)
 #endif
@@ -473,15 +570,16 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
     static constexpr int CPX = FAST_TILE_BYTES / (N * 16);                            // 16-byte chunks per x (even)
     static constexpr int ROWS = CPX * V, L = ROWS / 2;                                // rows / complex lines per tile
     static constexpr int TILE = FAST_TILE_BYTES / (int)sizeof(T);
-    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2) + 16;
+    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2);
     static_assert(NT % S1 == 0 && NT % NB2 == 0 && NT % NBM == 0 && CPX % 2 == 0, "thread/butterfly mapping");
     static_assert((CPX / 2) % (NT / S1) == 0 && (CPX / 2) % (NT / NB2) == 0 && CPX % (NT / NBM) == 0, "chunk-row mapping");
+    static constexpr bool PDL = true;
     static const char* name() { return "flow_rows"; }
 
-    Fft1D<T> fx, fy; const T* mult; const T* mult_sign_y; T cN;
+    Fft1D<T> fx; const T* mult;
     int Ny, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase;
     int sms; unsigned stagger_ns;
-    const T* u; const T* pk; T* tmp; T* nline; T* jn; T* nacc; T wgt; int* counter;
+    const T* u; const T* pk; T* tmp; T* nline; T* nacc; T wgt;
 
     struct Chunk { C2<T> c[H]; };
     static DEV Chunk ld(const T* p) { Vec<T> v = vload(p); Chunk r; memcpy(&r, &v, 16); return r; }
@@ -489,6 +587,7 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
     static DEV Vec<T> asvec(const Chunk& c) { Vec<T> v; memcpy(&v, &c, 16); return v; }
 
     DEV void issue_tile(const T* src /*the tile: one contiguous run in the row-grouped layout*/, T* buf, int tid) const {
+        if (CMBL_ABLATE == 6) return;
 #pragma unroll 4
         for (int k = tid; k < N * CPX; k += NT) {
             const int x = k / CPX, cl = k % CPX;
@@ -541,6 +640,7 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
                         C2<T> v[R];
 #pragma unroll
                         for (int m = 0; m < R; ++m) v[m] = x[s][m].c[h];
+#if CMBL_ABLATE != 1
                         if (!INV) {
                             dftR<T, R, false>(v);
 #pragma unroll
@@ -550,13 +650,17 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
                             for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], w[q]);
                             dftR<T, R, true>(v);
                         }
+#else
+                        v[0].x += w[1].x;          // ablation: data movement only
+#endif
 #pragma unroll
                         for (int m = 0; m < R; ++m) x[s][m].c[h] = v[m];
                     }
                 }
 #pragma unroll
                 for (int m = 0; m < R; ++m) {
-                    if (STORE_GLOBAL) vstore2(gdst + ((size_t)(x0 + m * xs) * CPX + 2 * g) * V, asvec(x[0][m]), asvec(x[PW - 1][m]));
+                    if (STORE_GLOBAL && CMBL_ABLATE == 5) { if (x[0][m].c[0].x == (T)1.2345e-30) vstore2(gdst + ((size_t)(x0 + m * xs) * CPX + 2 * g) * V, asvec(x[0][m]), asvec(x[PW - 1][m])); }
+                    else if (STORE_GLOBAL) vstore2(gdst + ((size_t)(x0 + m * xs) * CPX + 2 * g) * V, asvec(x[0][m]), asvec(x[PW - 1][m]));
                     else {
 #pragma unroll
                         for (int s = 0; s < PW; ++s) st(buf + ((2 * g + s0 + s) * N + swzx(x0 + m * xs)) * V, x[s][m]);
@@ -566,7 +670,7 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
         }
     }
     // fused middle: forward radix 16 · (Nyquist line N(y), src/proj_lambert.jl:63-64) · multiplier iℓx/N · inverse radix 16
-    static constexpr bool PRELOAD_MULT = sizeof(T) == 4;      // fp64: loading the 16 multipliers after the forward DFT avoids spills
+    static constexpr bool PRELOAD_MULT = true;
     DEV void middle(T* buf, int tid, const T* mlt_pre, T* nline_c, T* nacc_c, int y0) const {
         const int j = tid % NBM;
         for (int cl = tid / NBM; cl < CPX; cl += NT / NBM) {
@@ -578,7 +682,9 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
                 C2<T> v[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = x[q].c[h];
+#if CMBL_ABLATE != 1
                 dft16<T, false>(v);
+#endif
                 if (j == 0) {                                          // Nyquist coefficient sits at tile position 8
                     const int y = y0 + 2 * (cl * H + h);
                     nline_c[y] = v[8].x; nline_c[y + 1] = v[8].y;
@@ -593,7 +699,9 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) v[q] = mk<T>(-mlt[q] * v[q].y, mlt[q] * v[q].x);
                 }
+#if CMBL_ABLATE != 1
                 dft16<T, true>(v);
+#endif
 #pragma unroll
                 for (int q = 0; q < 16; ++q) x[q].c[h] = v[q];
             }
@@ -602,33 +710,19 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
         }
     }
 
-    // jn = cN · J[N] for plane c (executed once per plane and launch by the block that completes the plane; kept out of
-    // line so that its register needs do not leak into the tile loop)
-    DEV void jn_line(unsigned char* smem_line, int c) const {
-        Tile<T, false> tl = line_tile<T>(smem_line, 1, fy);
-        CMBL_FOR_THREADS(tid, NT) {
-            for (int y = tid; y < Ny; y += NT) tl.at(0, y) = mk<T>(ld_cg(nline + (size_t)c * Ny + y), (T)0);
-        }
-        CMBL_SYNC();
-        SignMid<T> smid{mult_sign_y};
-        fft_spectral_op<T, false, NT>(tl, fy, smid);
-        CMBL_FOR_THREADS(tid, NT) {
-            for (int y = tid; y < Ny; y += NT) jn[(size_t)c * Ny + y] = cN * tl.at(0, y).x;
-            if (tid == 0) counter[c] = 0;
-        }
-    }
-
     DEV void operator()(int blk, unsigned char* smem) const {
         T* const sbase = reinterpret_cast<T*>(smem);
         T* const pbuf = sbase + 2 * TILE;
-        int* flag = reinterpret_cast<int*>(smem + SMEM - 16);
         const size_t nmap = (size_t)N * Ny;
+        // the thread's butterfly indices never change: its twiddles and multipliers stay in registers for the whole launch
         C2<T> w1[R1], w2[R2]; T mlt[16];
+        pdl_launch_dependents();
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_w1(tid, w1)); CMBL_PRE_END(load_w2(tid, w2)); CMBL_PRE_END(load_mult(tid, mlt)); }
+        pdl_wait();
         // block b owns the contiguous tile range [tbeg, tend): at most a few planes per block, so the per-plane completion
         // ticket (a release atomic that has to wait for the block's stores) is paid once per plane, not once per tile
-        stagger_start(blk, sms, stagger_ns);
         const int tbeg = (int)((long long)blk * ntiles / nblocks), tend = (int)((long long)(blk + 1) * ntiles / nblocks);
-        int tile = tbeg, cur = 0, done_in_plane = 0;
+        int tile = tbeg, cur = 0;
         if (tile < tend) {
             const int c = cbase + tile / tiles_per_plane;
             const size_t toff = (size_t)(tile % tiles_per_plane) * ROWS * N;
@@ -644,7 +738,7 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
             const int c = cbase + tile / tiles_per_plane, y0 = (tile % tiles_per_plane) * ROWS, next = tile + 1;
             const int cn = cbase + next / tiles_per_plane;
             const size_t toff = (size_t)(tile % tiles_per_plane) * ROWS * N, toffn = (size_t)(next % tiles_per_plane) * ROWS * N;
-            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_w1(tid, w1)); cp_async_wait_all(); }
+            CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
             CMBL_SYNC();
             if (next < tend) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap + toffn, nbuf, tid); cp_async_commit(); }
@@ -652,46 +746,34 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
             CMBL_FOR_THREADS(tid, NT) {
                 CMBL_PRE_START(load_w1(tid, w1));
                 pass<R1, false, false>(buf, ADJ ? pbuf : nullptr, tid / S1, NT / S1, tid % S1, S1, w1, nullptr);
-                CMBL_PRE_END(load_w2(tid, w2));
             }
-            CMBL_SYNC();
+            ROW_SWEEP_SYNC();
             if (ADJ && next < tend) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 0, nmap) + toffn, pbuf, tid); cp_async_commit(); }
             }
+#if CMBL_ABLATE < 3 || CMBL_ABLATE == 7
             CMBL_FOR_THREADS(tid, NT) {
                 CMBL_PRE_START(load_w2(tid, w2));
                 const int j = tid % NB2;
                 pass<R2, false, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, w2, nullptr);
-                if (PRELOAD_MULT) { CMBL_PRE_END(load_mult(tid, mlt)); }
             }
-            CMBL_SYNC();
+            ROW_SWEEP_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
-                if (PRELOAD_MULT) { CMBL_PRE_START(load_mult(tid, mlt)); }
+                CMBL_PRE_START(load_mult(tid, mlt));
                 middle(buf, tid, mlt, nline + (size_t)c * Ny, ADJ ? nacc + (size_t)c * Ny : nullptr, y0);
-                CMBL_PRE_END(load_w2(tid, w2));
             }
-            CMBL_SYNC();
+            ROW_SWEEP_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
                 CMBL_PRE_START(load_w2(tid, w2));
                 const int j = tid % NB2;
                 pass<R2, true, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, w2, nullptr);
-                CMBL_PRE_END(load_w1(tid, w1));
             }
-            CMBL_SYNC();
+            ROW_SWEEP_SYNC();
+#endif
             CMBL_FOR_THREADS(tid, NT) {
                 CMBL_PRE_START(load_w1(tid, w1));
                 pass<R1, true, true>(buf, nullptr, tid / S1, NT / S1, tid % S1, S1, w1, tmp + (size_t)c * nmap + toff);
             }
-            // ---- the block that completes a plane turns its N(y) into jn = cN · J[N] -----------------------------------
-            ++done_in_plane;
-            if (next < tend && cn == c) continue;                        // more tiles of this plane follow in this block
-            CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) {
-                if (tid == 0) *flag = (ticket_release(counter + c, done_in_plane) + done_in_plane == tiles_per_plane) ? 1 : 0;
-            }
-            done_in_plane = 0;
-            CMBL_SYNC();
-            if (*flag) jn_line(reinterpret_cast<unsigned char*>(buf), c);
         }
     }
 };

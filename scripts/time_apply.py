@@ -9,7 +9,7 @@ pkg = g.load_package()
 dtype = sys.argv[1] if len(sys.argv) > 1 else "f64"
 op = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 tT = torch.float64 if dtype == "f64" else torch.float32
-N, NB = 1024, 8
+N, NB = 1024, int(os.environ.get("NB", "8"))
 proj = pkg.ProjLambert(N, N, 2.0, tT, "cuda:0")
 gen = torch.Generator(device="cuda:0").manual_seed(1)
 k = torch.fft.fftfreq(N, device="cuda:0")
@@ -35,7 +35,7 @@ for _ in range(10): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 s = 8 if dtype == "f64" else 4
-AL = 28 * (7 * 16 + 2 * 8) * N * N * s
+AL = 28 * (7 * 2 * NB + 2 * NB) * N * N * s
 print(f"{dtype} op{op} chunk={os.environ.get('CMBL_FLOW_CHUNK','all')} tile={os.environ.get('CMBL_TILE_KB','70')}KB: {ms:.3f} ms/apply  alg {AL/ms/1e6:.0f} GB/s  frac {AL/ms/1e6/6552.6:.3f}  finite={bool(torch.isfinite(out).all())}")
 lib.cdll.cmbl_profile_begin.restype = ctypes.c_int
 lib.cdll.cmbl_profile_begin()
