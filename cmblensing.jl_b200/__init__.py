@@ -321,6 +321,19 @@ class CachedLenseFlow:
         p.lib.call("cmbl_lenseflow_apply", self.handle, op, _ptr(f.arr), _ptr(out), _stream(out))
         return f._like(out)
 
+    def pullback(self, op: int, f_out: Field, Δ: Field, bug_compat: bool = True):
+        """Pullback of `Lϕ*f` (op = OP_L) or `Lϕ\\f` (op = OP_LINV) — the Zygote rule of src/flowops.jl:40-68 integrating
+        negδvelocityᴴ (src/lenseflow.jl:176-214).  `f_out` is the forward result, `Δ` the cotangent; returns (δf, δϕ) in the
+        Fourier basis (δϕ has one plane per batch item).  `bug_compat=True` reproduces the reference's aliased 2×2 product."""
+        if not self.with_minv:
+            raise CmblError("pullback needs LenseFlow(...).cache(f, with_minv=True)")
+        p = self.proj
+        f_out, Δ = LenseBasis(f_out), DerivBasis(Δ)
+        δf = torch.empty_like(Δ.arr)
+        δϕ = torch.empty((self.Nb_f, 1) + tuple(Δ.arr.shape[2:]), dtype=Δ.arr.dtype, device=Δ.arr.device)
+        p.lib.call("cmbl_lenseflow_grad", self.handle, op, _ptr(f_out.arr), _ptr(Δ.arr), _ptr(δf), _ptr(δϕ), 1 if bug_compat else 0, _stream(δf))
+        return Δ._like(δf), Field("Fourier", δϕ, p)
+
 
 class LenseFlow:
     """LenseFlow(ϕ, n=7): lazy wrapper; the cache is (re)built when first applied to a field of a new shape

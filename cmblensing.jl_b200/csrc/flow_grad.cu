@@ -1,9 +1,207 @@
-// Pullback through LenseFlow (negδvelocityᴴ, src/lenseflow.jl:176-214) — implemented in a later step.
+// Pullback through LenseFlow: the transpose flow negδvelocityᴴ (src/lenseflow.jl:176-214) integrated by RK4
+// (src/numerical_algorithms.jl:11-24) on the joint state (f Map, δf Fourier, δϕ Fourier), as the reference's Zygote
+// rule does (src/flowops.jl:40-68).
+//
+// One velocity evaluation at stage k (t = k/2n), written with the batched 2-D transforms of fft2d.cuh:
+//     Łδf = irfft2(δf)                                   F = rfft2(f),  ∂ₓf = irfft2(iℓₓF),  ∂ᵧf = irfft2(iℓᵧF)
+//     df/dt   = p₁∂ₓf + p₂∂ᵧf                             (velocity)
+//     dδf/dt  = iℓₓ·rfft2(p₁Łδf) + iℓᵧ·rfft2(p₂Łδf)       (velocityᴴ)
+//     w_i = Σ_pol Łδf·∂_i f          (src/proj_lambert.jl:423-430)
+//     m = M⁻¹w   — reference: m₁ = M₁₁w₁+M₁₂w₂ ; m₂ = M₂₁·m₁+M₂₂w₂ (aliased in-place product, src/lenseflow.jl:198-200 with
+//                  src/field_vectors.jl:48-49).  bug_compat = false uses the exact m₂ = M₂₁w₁+M₂₂w₂.
+//     dδϕ/dt = iℓₓ·rfft2(m₁) + iℓᵧ·rfft2(m₂) + Σ_ij (−iℓ_i)(−iℓ_j)·rfft2(t·p_j·m_i)
+// M⁻¹₁₂ ≡ M⁻¹₂₁ (the reference reads [2,1] twice, src/field_vectors.jl:87), so the cache holds 3 maps per time.
+// This path is not on the headline roofline: it is built from the library's general transforms plus
+// three fused pointwise kernels; the caches may be in the row-grouped layout of the fast stage kernels (index remap).
 #include "flow.cuh"
+#include "../../include/cmbl_b200.h"
+
 namespace cmbl {
-template <class T> void flow_grad(FlowT<T>&, int, const T*, const C2<T>*, C2<T>*, C2<T>*, bool, cmblStream_t) {
-    throw Error("cmbl_lenseflow_grad: not implemented yet");
+
+// spectra of the two derivatives of f: GX = iℓₓF, GY = iℓᵧF
+template <class T> struct GradSpecBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "grad_spec"; }
+    int Nx, Nyh; const T* lx; const T* ly; const C2<T>* F; C2<T>* GX; C2<T>* GY; size_t total;     // total = C*Nx*Nyh
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < total) {
+                size_t r = e % ((size_t)Nx * Nyh);
+                int kx = (int)(r / Nyh), ky = (int)(r - (size_t)kx * Nyh);
+                C2<T> f = F[e];
+                GX[e] = cmul(mk<T>((T)0, lx[kx]), f);
+                GY[e] = cmul(mk<T>((T)0, ly[ky]), f);
+            }
+        }
+    }
+};
+
+// pointwise part of negδvelocityᴴ; one thread per pixel and batch item
+template <class T> struct DeltaPointBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "delta_point"; }
+    int Npol, Nb, Nbphi, Nx, Ny, G; bool bug_compat; T t;
+    const T* ldf; const T* gx; const T* gy;          // [Nb][Npol] maps (reference layout)
+    const T* pk; const T* mk3;                        // p[k]: [Nbphi][2] maps, M⁻¹[k]: [Nbphi][3] maps (layout G)
+    T* dfdt; T* a1; T* a2;                            // [Nb][Npol] maps
+    T* six;                                           // [Nb][6] maps: m1, m2, t p1 m1, t p2 m1, t p1 m2, t p2 m2
+    DEV void operator()(int blk, unsigned char*) const {
+        const size_t nmap = (size_t)Nx * Ny;
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < nmap * Nb) {
+                const size_t b = e / nmap, r = e - b * nmap;
+                size_t rc = r;                                                          // index inside the caches
+                if (G > 0) { const int x = (int)(r / Ny), y = (int)(r - (size_t)x * Ny); rc = ((size_t)(y / G) * Nx + x) * G + (y % G); }
+                const size_t bp = (Nbphi == 1) ? 0 : b;
+                const T p1 = pk[(bp * 2 + 0) * nmap + rc], p2 = pk[(bp * 2 + 1) * nmap + rc];
+                const T m11 = mk3[(bp * 3 + 0) * nmap + rc], m21 = mk3[(bp * 3 + 1) * nmap + rc], m22 = mk3[(bp * 3 + 2) * nmap + rc];
+                T w1 = 0, w2 = 0;
+                for (int pol = 0; pol < Npol; ++pol) {
+                    const size_t i = (b * Npol + pol) * nmap + r;
+                    const T l = ldf[i], dx = gx[i], dy = gy[i];
+                    dfdt[i] = p1 * dx + p2 * dy;
+                    a1[i] = p1 * l; a2[i] = p2 * l;
+                    w1 += l * dx; w2 += l * dy;
+                }
+                const T m1 = m11 * w1 + m21 * w2;                                      // M₁₂ ≡ M₂₁
+                const T m2 = bug_compat ? (m21 * m1 + m22 * w2) : (m21 * w1 + m22 * w2);
+                T* s = six + b * 6 * nmap + r;
+                s[0] = m1; s[nmap] = m2;
+                s[2 * nmap] = t * p1 * m1; s[3 * nmap] = t * p2 * m1; s[4 * nmap] = t * p1 * m2; s[5 * nmap] = t * p2 * m2;
+            }
+        }
+    }
+};
+
+// spectral part: dδf/dt = iℓₓA1 + iℓᵧA2 ;  dδϕ/dt = iℓₓM1 + iℓᵧM2 + Σ_ij (−iℓ_i)(−iℓ_j) R_ij
+template <class T> struct DeltaSpecBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "delta_spec"; }
+    int Nx, Nyh, C, Nb; const T* lx; const T* ly;
+    const C2<T>* A1; const C2<T>* A2; const C2<T>* S6; C2<T>* ddf; C2<T>* ddphi;
+    DEV void operator()(int blk, unsigned char*) const {
+        const size_t nf = (size_t)Nx * Nyh;
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < nf * (size_t)(C + Nb)) {
+                const size_t pl = e / nf, r = e - pl * nf;
+                const int kx = (int)(r / Nyh), ky = (int)(r - (size_t)kx * Nyh);
+                const C2<T> d1 = mk<T>((T)0, lx[kx]), d2 = mk<T>((T)0, ly[ky]);
+                if (pl < (size_t)C) ddf[e] = cmul(d1, A1[e]) + cmul(d2, A2[e]);
+                else {
+                    const size_t b = pl - C;
+                    const C2<T>* s = S6 + b * 6 * nf + r;
+                    const C2<T> n1 = mk<T>((T)0, -lx[kx]), n2 = mk<T>((T)0, -ly[ky]);
+                    C2<T> v = cmul(d1, s[0]) + cmul(d2, s[nf]);
+                    v = v + cmul(n1, cmul(n1, s[2 * nf]));       // i=1 (m1), j=1 (p1)
+                    v = v + cmul(n1, cmul(n2, s[3 * nf]));       // i=1, j=2
+                    v = v + cmul(n2, cmul(n1, s[4 * nf]));       // i=2 (m2), j=1
+                    v = v + cmul(n2, cmul(n2, s[5 * nf]));       // i=2, j=2
+                    ddphi[b * nf + r] = v;
+                }
+            }
+        }
+    }
+};
+
+// out = (x ? x : 0) + s*k on real arrays (complex arrays are passed as reals of twice the length); out may alias x or k
+template <class T> struct AxpyBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "axpy"; }
+    size_t n; const T* x; const T* k; T s; T* out;
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < n) out[e] = (x ? x[e] : (T)0) + s * k[e];
+        }
+    }
+};
+template <class T> static void axpy(size_t n, const T* x, const T* k, T s, T* out, cmblStream_t st) {
+    AxpyBody<T> b{n, x, k, s, out};
+    launch(b, (int)((n + b.NT - 1) / b.NT), 0, st);
 }
+
+template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,
+                                  bool bug_compat, cmblStream_t st) {
+    CMBL_REQUIRE(F.have_p && F.have_minv, "cmbl_lenseflow_grad needs cmbl_lenseflow_precompute(..., with_minv = 1)");
+    PlanT<T>& P = *F.P;
+    const size_t nmap = P.map_elems(), nf = P.four_elems();
+    const int C = F.C, Nb = F.Nb, n = F.nsteps;
+    const size_t mC = nmap * C, fC = nf * C, fB = nf * Nb;
+    // scratch: state copies (y: f, δf, δϕ), stage inputs u, accumulators acc, velocities k, and the work arrays of one evaluation
+    auto R = [&](DevBuf& b, size_t bytes) { return b.reserve(bytes); };
+    T* yf = (T*)R(F.g_yf, sizeof(T) * mC);           C2<T>* yd = (C2<T>*)R(F.g_yd, sizeof(C2<T>) * fC);   C2<T>* yp = (C2<T>*)R(F.g_yp, sizeof(C2<T>) * fB);
+    T* uf = (T*)R(F.g_uf, sizeof(T) * mC);           C2<T>* ud = (C2<T>*)R(F.g_ud, sizeof(C2<T>) * fC);   C2<T>* up = (C2<T>*)R(F.g_up, sizeof(C2<T>) * fB);
+    T* af = (T*)R(F.g_af, sizeof(T) * mC);           C2<T>* ad = (C2<T>*)R(F.g_ad, sizeof(C2<T>) * fC);   C2<T>* ap = (C2<T>*)R(F.g_ap, sizeof(C2<T>) * fB);
+    T* kf = (T*)R(F.g_kf, sizeof(T) * mC);           C2<T>* kd = (C2<T>*)R(F.g_kd, sizeof(C2<T>) * fC);   C2<T>* kp = (C2<T>*)R(F.g_kp, sizeof(C2<T>) * fB);
+    T* ldf = (T*)R(F.g_ldf, sizeof(T) * mC);         T* gxy = (T*)R(F.g_gxy, sizeof(T) * 2 * mC);         T* a12 = (T*)R(F.g_a12, sizeof(T) * 2 * mC);
+    T* six = (T*)R(F.g_six, sizeof(T) * 6 * nmap * Nb);
+    C2<T>* spec = (C2<T>*)R(F.g_spec, sizeof(C2<T>) * (2 * fC > 6 * fB ? 2 * fC : 6 * fB));
+    C2<T>* spec2 = (C2<T>*)R(F.g_spec2, sizeof(C2<T>) * 2 * fC);
+
+    auto velocity = [&](int k, const T* f, const C2<T>* df, T* of, C2<T>* od, C2<T>* ophi) {
+        const T t = (T)((double)k / (double)(2 * n));
+        irfft2<T>(P, df, ldf, C, st);
+        rfft2<T>(P, f, spec, C, st);
+        {
+            GradSpecBody<T> b{P.Nx, P.Nyh, P.lx, P.ly, spec, spec2, spec2 + fC, fC};
+            launch(b, (int)((fC + b.NT - 1) / b.NT), 0, st);
+        }
+        irfft2<T>(P, spec2, gxy, 2 * C, st);
+        {
+            DeltaPointBody<T> b;
+            b.Npol = F.Npol; b.Nb = Nb; b.Nbphi = F.Nbphi; b.Nx = P.Nx; b.Ny = P.Ny; b.G = F.pcache_G; b.bug_compat = bug_compat; b.t = t;
+            b.ldf = ldf; b.gx = gxy; b.gy = gxy + mC;
+            b.pk = F.pk(k); b.mk3 = reinterpret_cast<T*>(F.minv.p) + (size_t)k * F.Nbphi * 3 * nmap;
+            b.dfdt = of; b.a1 = a12; b.a2 = a12 + mC; b.six = six;
+            launch(b, (int)((nmap * Nb + b.NT - 1) / b.NT), 0, st);
+        }
+        rfft2<T>(P, a12, spec2, 2 * C, st);
+        rfft2<T>(P, six, spec, 6 * Nb, st);
+        {
+            DeltaSpecBody<T> b{P.Nx, P.Nyh, C, Nb, P.lx, P.ly, spec2, spec2 + fC, spec, od, ophi};
+            launch(b, (int)((nf * (size_t)(C + Nb) + b.NT - 1) / b.NT), 0, st);
+        }
+    };
+
+    dev_copy(yf, fout, sizeof(T) * mC, st);
+    dev_copy(yd, delta, sizeof(C2<T>) * fC, st);
+    dev_zero(yp, sizeof(C2<T>) * fB, st);
+    const int k0 = (op == CMBL_OP_L) ? 2 * n : 0, k1 = (op == CMBL_OP_L) ? 0 : 2 * n;
+    const int sgn = k1 > k0 ? 1 : -1;
+    const double h = (double)sgn / n;
+    const T h2 = (T)(h / 2), h1 = (T)h, h6 = (T)(h / 6), h3 = (T)(h / 3);
+    auto rr = [](C2<T>* p) { return reinterpret_cast<T*>(p); };
+    int kk = k0;
+    for (int step = 0; step < n; ++step) {
+        for (int s = 0; s < 4; ++s) {
+            const int kq = kk + (s == 0 ? 0 : (s < 3 ? sgn : 2 * sgn));
+            const T* f_in = (s == 0) ? yf : uf; const C2<T>* d_in = (s == 0) ? yd : ud;
+            velocity(kq, f_in, d_in, kf, kd, kp);
+            const T cb = (s == 0 || s == 3) ? h6 : h3, ca = (s < 2) ? h2 : h1;
+            if (s < 3) {
+                // acc = (s == 0 ? y : acc) + cb k ;  u = y + ca k
+                axpy<T>(mC, s == 0 ? yf : af, kf, cb, af, st);
+                axpy<T>(2 * fC, s == 0 ? rr(yd) : rr(ad), rr(kd), cb, rr(ad), st);
+                axpy<T>(2 * fB, s == 0 ? rr(yp) : rr(ap), rr(kp), cb, rr(ap), st);
+                axpy<T>(mC, yf, kf, ca, uf, st);
+                axpy<T>(2 * fC, rr(yd), rr(kd), ca, rr(ud), st);
+                axpy<T>(2 * fB, rr(yp), rr(kp), ca, rr(up), st);       // δϕ does not feed the velocity, kept for symmetry of the state
+            } else {
+                axpy<T>(mC, af, kf, cb, yf, st);
+                axpy<T>(2 * fC, rr(ad), rr(kd), cb, rr(yd), st);
+                axpy<T>(2 * fB, rr(ap), rr(kp), cb, rr(yp), st);
+            }
+        }
+        kk += 2 * sgn;
+    }
+    dev_copy(dfield, yd, sizeof(C2<T>) * fC, st);
+    dev_copy(dphi, yp, sizeof(C2<T>) * fB, st);
+}
+
 template void flow_grad<float>(FlowT<float>&, int, const float*, const C2<float>*, C2<float>*, C2<float>*, bool, cmblStream_t);
 template void flow_grad<double>(FlowT<double>&, int, const double*, const C2<double>*, C2<double>*, C2<double>*, bool, cmblStream_t);
-}
+
+}  // namespace cmbl

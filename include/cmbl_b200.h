@@ -90,7 +90,9 @@ int cmbl_lenseflow_apply(cmbl_flow* flow, int op, const void* in, void* out, voi
 int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream);
 /* pullback through Lϕ*f (op 0) or Lϕ\f (op 2): negδvelocityᴴ transpose flow (src/lenseflow.jl:176-214, src/flowops.jl:40-68).
  * f_out_map = the forward result (Map), delta = cotangent (Fourier). Outputs: dfield (Fourier, C planes), dphi (Fourier,
- * Nb_phi planes).  bug_compat != 0 reproduces the reference's aliased 2x2 product (src/lenseflow.jl:198-200). */
+ * Nb_f planes: one per batch item, also when a single ϕ is shared by the batch — sum them for the gradient w.r.t. the
+ * shared ϕ).  Needs cmbl_lenseflow_precompute(..., with_minv = 1).  bug_compat != 0 reproduces the reference's aliased
+ * 2x2 product (src/lenseflow.jl:198-200 with src/field_vectors.jl:48-49). */
 int cmbl_lenseflow_grad(cmbl_flow* flow, int op, const void* f_out_map, const void* delta_four, void* dfield_four,
                         void* dphi_four, int bug_compat, void* stream);
 /* which stage kernels this flow runs (diagnostic): bit 0 = fast persistent row kernel, bit 1 = fast persistent column kernel

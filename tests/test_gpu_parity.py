@@ -80,6 +80,56 @@ def test_lenseflow_fast_path(cuda_pkg, Ny, Nx, pol, nb, nbphi, path, dtype):
     assert relerr(L.H.ldiv(ffour).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LHINV, Fn)) < tol
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(128, 64, "P", 2, 2), (64, 64, "I", 3, 1), (256, 256, "P", 2, 2)])
+def test_lenseflow_pullback(cuda_pkg, Ny, Nx, pol, nb, nbphi, dtype):
+    """negδvelocityᴴ (src/lenseflow.jl:176-214, src/flowops.jl:40-68) on the device against the oracle, with the reference's
+    aliased 2×2 product (bug_compat) and the exact one; (256,256) exercises the row-grouped p / M⁻¹ caches."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=4, mask=False, seed=17, device=DEV)
+    L = pkg.LenseFlow(pr["phi"], 4)
+    Lo, oproj = pr["Lo"], pr["oproj"]
+    rng = np.random.default_rng(6)
+    fm = O.to_lense_basis(pol, oproj, pr["sim"]["f"])
+    out_o = O.lenseflow_apply(Lo, O.OP_L, fm)
+    D0 = O.rfft2(rng.standard_normal(fm.shape)).astype(oproj.cT)
+    fmap = pr["F"](fm, pr["lense"])
+    cache = L.cache(fmap, with_minv=True)
+    out = cache.apply(pkg.OP_L, fmap)
+    Δ = pr["F"](D0, "Fourier" if pol == "I" else "QUFourier")
+    tol = 1e-10 if dtype == "f64" else 5e-4
+    for bug in (True, False):
+        δf, δϕ = cache.pullback(pkg.OP_L, out, Δ, bug_compat=bug)
+        gf, gphi = O.lenseflow_grad(Lo, O.OP_L, out_o, D0, bug_compat=bug)
+        assert relerr(δf.cpu_numpy(), gf) < tol and relerr(δϕ.cpu_numpy(), gphi) < tol
+
+
+def test_lenseflow_gradient_finite_difference(cuda_pkg):
+    """Finite-difference check of the pullback through the device forward map (runtests.jl:559,573):
+    d/dα ‖L(ϕ+αδϕ)(f+αδf)‖ at α=0 vs ⟨δf, ∇f⟩ + ⟨δϕ, ∇ϕ⟩; exact variant to 1e-5, reference-compatible one within its rtol 1e-3."""
+    pkg = cuda_pkg
+    N = 256
+    pr = make_problem(pkg, N, N, "P", "f64", nb=1, nsteps=7, mask=False, seed=21, device=DEV)
+    pr2 = make_problem(pkg, N, N, "P", "f64", nb=1, nsteps=7, mask=False, seed=22, device=DEV)
+    ϕ, δϕ_dir = pr["phi"], pr2["phi"]
+    f, δf_dir = pkg.LenseBasis(pr["f"]), pkg.LenseBasis(pr2["f"])
+
+    def fwd(a):
+        L = pkg.LenseFlow(ϕ + δϕ_dir * a, 7)
+        return L, L * (f + δf_dir * a)
+
+    obj = lambda a: float(np.sqrt(pkg.dot(*(2 * [fwd(a)[1]]))[0]))
+    eps = 1e-4
+    fd = (obj(eps) - obj(-eps)) / (2 * eps)
+    L, out = fwd(0.0)
+    Δ = pkg.DerivBasis(out * (1.0 / obj(0.0)))
+    cache = L.cache(f, with_minv=True)
+    for bug, tol in ((False, 1e-5), (True, 1e-3)):
+        gf, gphi = cache.pullback(pkg.OP_L, out, Δ, bug_compat=bug)
+        an = float(pkg.dot(gf, pkg.DerivBasis(δf_dir))[0] + pkg.dot(gphi, pkg.Fourier(δϕ_dir))[0])
+        assert abs(an - fd) <= tol * abs(fd) + 1e-9, (bug, an, fd)
+
+
 def test_golden_fixture(cuda_pkg):
     """Committed golden vectors (tests/golden/make_golden.py; generated by the oracle in the build container)."""
     pkg = cuda_pkg

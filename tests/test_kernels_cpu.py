@@ -142,6 +142,32 @@ def test_lenseflow_adjoint_identity(pkg, emu, pol, dtype):
     assert np.allclose(lhs, rhs, rtol=1e-11 if dtype == "f64" else 5e-4)
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(16, 32, "I", 1, 1), (32, 16, "P", 2, 2), (256, 256, "P", 1, 1)])
+def test_lenseflow_pullback(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
+    """negδvelocityᴴ transpose flow (src/lenseflow.jl:176-214) against the oracle, reference-compatible (aliased) and exact."""
+    nst = 3 if Ny < 256 else 1
+    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=nst, mask=False, seed=17, lib=emu)
+    L = pkg.LenseFlow(pr["phi"], nst)
+    Lo, oproj = pr["Lo"], pr["oproj"]
+    rng = np.random.default_rng(6)
+    fm = O.to_lense_basis(pol, oproj, pr["sim"]["f"])
+    out_o = O.lenseflow_apply(Lo, O.OP_L, fm)
+    D0 = O.rfft2(rng.standard_normal(fm.shape)).astype(oproj.cT)
+    fmap = pr["F"](fm, pr["lense"])
+    cache = L.cache(fmap, with_minv=True)
+    out = cache.apply(pkg.OP_L, fmap)
+    Δ = pr["F"](D0, "Fourier" if pol == "I" else "QUFourier")
+    tol = 1e-10 if dtype == "f64" else 5e-4
+    for bug in (True, False):
+        δf, δϕ = cache.pullback(pkg.OP_L, out, Δ, bug_compat=bug)
+        gf, gphi = O.lenseflow_grad(Lo, O.OP_L, out_o, D0, bug_compat=bug)
+        assert relerr(δf.cpu_numpy(), gf) < tol and relerr(δϕ.cpu_numpy(), gphi) < tol
+    δf, δϕ = cache.pullback(pkg.OP_LINV, fmap, Δ)
+    gf, gphi = O.lenseflow_grad(Lo, O.OP_LINV, fm, D0)
+    assert relerr(δf.cpu_numpy(), gf) < tol and relerr(δϕ.cpu_numpy(), gphi) < tol
+
+
 @pytest.mark.parametrize("dtype,pol,mask", [("f64", "I", False), ("f64", "P", True), ("f64", "I", True), ("f32", "P", True)])
 def test_gradientf_and_cg(pkg, emu, dtype, pol, mask):
     pr = make_problem(pkg, 32, 32, pol, dtype, nb=2, nsteps=3, mask=mask, seed=7, theta=3.0, lib=emu)
