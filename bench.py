@@ -275,6 +275,21 @@ def main():
                "sample": f"{nit} of {NB} batch items of the same workload, one apply, time scaled x{NB // nit}; NumPy + scipy.fft(pocketfft) workers={cores}",
                "seconds_sample": dt, "gpu_vs_oracle_rel_l2": err}
 
+    # ---- the same apply in the other precision (context for the headline; Float32 is what the reference runs on GPUs) ----
+    other = None
+    if rank == 0 and world == 1:
+        oT, odt, osz = (torch.float32, "f32", 4) if args.dtype == "f64" else (torch.float64, "f64", 8)
+        proj2 = pkg.ProjLambert(NSIDE, NSIDE, THETA, oT, dev)
+        ϕ2 = pkg.Field("Fourier", ϕ.arr.to(torch.complex64 if oT == torch.float32 else torch.complex128), proj2)
+        f2 = pkg.Field("QUMap", fmap.arr.to(oT), proj2)
+        c2 = pkg.LenseFlow(ϕ2, NSTEPS_RK).cache(f2)
+        out2 = torch.empty_like(f2.arr)
+        ms2, _ = timed(lambda: lib.call("cmbl_lenseflow_apply", c2.handle, 0, P(f2.arr), P(out2), st), args.steps, 3)
+        AB2 = algorithmic_bytes(osz)
+        other = {"dtype": odt, "value": 1e3 / ms2, "unit": "applies/s", "ms_per_step": ms2, "apply_algorithmic_GBs": AB2["apply"] / ms2 / 1e6,
+                 "apply_frac_of_measured_peak": AB2["apply"] / ms2 / 1e6 / peak}
+        del c2, out2, f2, ϕ2
+
     if rank == 0:
         nbytes = fmap.arr.numel() * fmap.arr.element_size()
         line = {
@@ -292,6 +307,7 @@ def main():
             "roofline_apply": {"bound": "hbm", "achieved": apply_gbs, "peak": peak, "unit": "GB/s", "frac": apply_gbs / peak, "frac_of_8TBs_nominal": apply_gbs / 8000.0,
                                "algorithmic_bytes_per_apply": AB["apply"]},
             "cpu_baseline": cpu,
+            "other_precision": other,
             "cg": {"metric": "cg_wiener_iters_per_sec", "value": world * 1e3 / ms_cg, "unit": "iters/s", "ms_per_iter": ms_cg, "iters_timed": args.cg_iters,
                    "gpu_launches": launches_cg, "algorithmic_GBs": AB["cg_iter"] / ms_cg / 1e6, "frac": AB["cg_iter"] / ms_cg / 1e6 / peak,
                    "res_first": res0[0], "res_last": res1[0]},

@@ -25,7 +25,7 @@ __all__ = [
     "ProjLambert", "Field", "FlatMap", "FlatFourier", "FlatQUMap", "FlatQUFourier", "FlatEBMap", "FlatEBFourier",
     "Map", "Fourier", "QUMap", "QUFourier", "EBMap", "EBFourier", "LenseBasis", "DerivBasis", "HarmonicBasis",
     "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "dot", "BaseDataSet", "gradientf_logpdf",
-    "Hessian_logpdf_preconditioner", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
+    "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
     "CmblError", "load",
 ]
 
@@ -371,9 +371,11 @@ class BaseDataSet:
     Diagonals are DiagOps over real harmonic-basis fields with batch 1; `Mpix` is a Map-basis DiagOp or None."""
 
     def __init__(self, d: Field, Cf: DiagOp, Cn: DiagOp, B: DiagOp, Mf: DiagOp, Mpix: DiagOp | None = None,
-                 Cnhat: DiagOp | None = None, Bhat: DiagOp | None = None, L=LenseFlow, nsteps: int = 7):
+                 Cnhat: DiagOp | None = None, Bhat: DiagOp | None = None, L=LenseFlow, nsteps: int = 7,
+                 D: DiagOp | None = None, G: DiagOp | None = None):
         self.d, self.Cf, self.Cn, self.B, self.Mf, self.Mpix = HarmonicBasis(d), Cf, Cn, B, Mf, Mpix
         self.Cnhat, self.Bhat, self.L, self.nsteps = Cnhat or Cn, Bhat or B, L, nsteps
+        self.D, self.G = D, G                      # mixing matrices of the Mixed parametrisation (src/dataset.jl:96-117); None = identity
         self._cg = {}
 
     def _solver(self, ϕ: Field):
@@ -391,6 +393,21 @@ class BaseDataSet:
         self._cg.clear()
         self._cg[key] = (h, cache, L, ϕ)
         return self._cg[key]
+
+
+def mix(ds: BaseDataSet, f: Field, ϕ: Field):
+    """mix(ds; f, ϕ) (src/dataset.jl:96-101): f° = L(ϕ)·D·f (Map basis, like the reference's L*f), ϕ° = G·ϕ."""
+    L = ds.L(ϕ, ds.nsteps) if isinstance(ds.L, type) else ds.L
+    Df = ds.D * f if ds.D is not None else f
+    return L * Df, (ds.G * ϕ if ds.G is not None else ϕ)
+
+
+def unmix(ds: BaseDataSet, f_mixed: Field, ϕ_mixed: Field):
+    """unmix(ds; f°, ϕ°) (src/dataset.jl:111-116): ϕ = G \\ ϕ°, f = D \\ (L(ϕ) \\ f°)."""
+    ϕ = ds.G.ldiv(ϕ_mixed) if ds.G is not None else ϕ_mixed
+    L = ds.L(ϕ, ds.nsteps) if isinstance(ds.L, type) else LenseFlow(ϕ, ds.nsteps)
+    f = L.ldiv(f_mixed)
+    return (ds.D.ldiv(f) if ds.D is not None else f), ϕ
 
 
 def gradientf_logpdf(ds: BaseDataSet, f: Field, ϕ: Field, d: Field | None = None, d_zero=False) -> Field:

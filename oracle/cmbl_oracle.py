@@ -469,6 +469,21 @@ def gradientf_logpdf(ds: DataSet, f_harm: np.ndarray, d: np.ndarray) -> np.ndarr
     return (y - pinv_diag(ds.Cf) * f_harm).astype(proj.cT)
 
 
+def mix(ds: DataSet, proj: ProjLambert, pol: str, f_harm: np.ndarray, phi_four: np.ndarray, D=None, G=None, nsteps: int = 7):
+    """mix(ds; f, ϕ) (src/dataset.jl:96-101): f° = L(ϕ)·D·f (returned in the Map/QUMap basis), ϕ° = G·ϕ."""
+    L = precompute(proj, phi_four, nsteps, phi_is_fourier=True)
+    Df = f_harm if D is None else diag_mul(D, f_harm)
+    return lenseflow_apply(L, OP_L, to_lense_basis(pol, proj, Df)), (phi_four if G is None else diag_mul(G, phi_four))
+
+
+def unmix(ds: DataSet, proj: ProjLambert, pol: str, f_mixed_map: np.ndarray, phi_mixed: np.ndarray, D=None, G=None, nsteps: int = 7):
+    """unmix(ds; f°, ϕ°) (src/dataset.jl:111-116): ϕ = G \\ ϕ°, f = D \\ (L(ϕ) \\ f°) (harmonic basis)."""
+    phi = phi_mixed if G is None else diag_ldiv(G, phi_mixed)
+    L = precompute(proj, phi, nsteps, phi_is_fourier=True)
+    f = to_harmonic_basis(pol, proj, lenseflow_apply(L, OP_LINV, f_mixed_map))
+    return (f if D is None else diag_ldiv(D, f)), phi
+
+
 def hess_preconditioner(ds: DataSet) -> np.ndarray:
     """Hessian_logpdf_preconditioner(:f) (src/dataset.jl:129-132): pinv(Cf) + B̂'M̂'pinv(Cn̂)M̂B̂."""
     return (pinv_diag(ds.Cf) + ds.Bhat * ds.Mf * pinv_diag(ds.Cnhat) * ds.Mf * ds.Bhat).astype(ds.proj.T)

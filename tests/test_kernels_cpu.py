@@ -187,6 +187,24 @@ def test_gradientf_and_cg(pkg, emu, dtype, pol, mask):
     assert relerr(x.cpu_numpy(), xo) < (1e-9 if dtype == "f64" else 2e-3)
 
 
+@pytest.mark.parametrize("pol", ["I", "P"])
+def test_mix_unmix(pkg, emu, pol):
+    """mix / unmix (src/dataset.jl:96-117) with diagonal mixing matrices D, G: parity with the oracle and round trip."""
+    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=5, mask=False, seed=23, theta=3.0, lib=emu)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    rng = np.random.default_rng(8)
+    Dn = (1.0 + rng.random(dso.Cf.shape)).astype(np.float64)
+    Gn = (1.0 + rng.random(pr["sim"]["phi"].shape[1:])).astype(np.float64)[None]
+    ds.D = pkg.DiagOp(pr["F"](Dn, pr["harm"])); ds.G = pkg.DiagOp(pr["F"](Gn, "Fourier"))
+    fm, pm = pkg.mix(ds, pr["f"], pr["phi"])
+    fo, po = O.mix(dso, oproj, pol, pr["sim"]["f"], pr["sim"]["phi"], D=Dn, G=Gn, nsteps=5)
+    assert relerr(fm.cpu_numpy(), fo) < 1e-11 and relerr(pm.cpu_numpy(), po) < 1e-13
+    f2, p2 = pkg.unmix(ds, fm, pm)
+    fo2, po2 = O.unmix(dso, oproj, pol, fo, po, D=Dn, G=Gn, nsteps=5)
+    assert relerr(pkg.HarmonicBasis(f2).cpu_numpy(), fo2) < 1e-10 and relerr(p2.cpu_numpy(), po2) < 1e-13
+    assert relerr(pkg.HarmonicBasis(f2).cpu_numpy(), pr["sim"]["f"]) < 0.3           # coarse grid: L\\(L f) only approximately f (Nyquist modes)
+
+
 def test_cg_stops_on_tol_like_reference(pkg, emu):
     pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=emu)
     _, h0 = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=0.0)
