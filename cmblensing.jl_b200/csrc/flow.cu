@@ -54,6 +54,19 @@ static int fast_pf() { static const int v = [] { const char* e = getenv("CMBL_FL
 template <class T, int LOGN, bool ADJ>
 static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cmblStream_t st) {
     PlanT<T>& P = *F.P;
+    static const bool use_tma = [] { const char* e = getenv("CMBL_ROW_TMA"); return !e || atoi(e) != 0; }();
+    if (use_tma) {
+        typedef TmaRowBody<T, LOGN, ADJ> B;
+        B b;
+        b.fx = P.ax.fft; b.mult = P.ax.mult_deriv;
+        b.Ny = P.Ny; b.tiles_per_plane = P.Ny / B::ROWS; b.ntiles = nC * b.tiles_per_plane;
+        b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
+        b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
+        b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.nline = reinterpret_cast<T*>(F.nline.p);
+        b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
+        launch(b, b.nblocks, B::SMEM, st);
+        return;
+    }
     typedef FastRowBody<T, LOGN, ADJ> B;
     B b;
     b.fx = P.ax.fft; b.mult = P.ax.mult_deriv;

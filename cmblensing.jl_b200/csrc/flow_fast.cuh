@@ -238,8 +238,14 @@ template <class T, bool TO_RG> struct LayoutBody {
 // ---------------------------------------------------------------------------------------------------------------
 // column kernel
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef CMBL_COL_MINB
+#define CMBL_COL_MINB 3
+#endif
+#ifndef CMBL_COL_UNR
+#define CMBL_COL_UNR 2
+#endif
 template <class T, int LOGN, bool ADJ> struct FastColBody {
-    static constexpr int NT = 128, MINB = ADJ ? 2 : 3;
+    static constexpr int NT = 128, MINB = ADJ ? 2 : CMBL_COL_MINB;
     static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), CH = N / V;       // CH chunks per column
     static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
     static constexpr int S1 = N / R1, N2 = N / R1;                                   // pass-2 stride is 16
@@ -391,7 +397,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     }
     template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2) const {
         constexpr bool YB = KIND != 2, AI = KIND != 0, UO = KIND != 2;
-        constexpr int ITER = M * CH / 2 / NT, UNR = 2;
+        constexpr int ITER = M * CH / 2 / NT, UNR = (ITER % CMBL_COL_UNR == 0) ? CMBL_COL_UNR : 2;
         static_assert(ITER % UNR == 0, "epilogue unroll");
         const T* tc = tmp + pbase;
         const T* yb = YB ? ybase + pbase : nullptr;
@@ -485,14 +491,18 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         pdl_launch_dependents();
         pdl_wait();
         // Tile assignment: round-robin over all tiles of the launch (neighbouring blocks work on neighbouring column tiles at
-        // the same time: their 128/256-byte runs share DRAM pages; the launch sweeps through the planes in order).
+        // the same time: their 128/256-byte runs share DRAM pages; the launch sweeps through the batch items in order).
+        // The polarisation index runs fastest: the Q and U (I, Q, U) tiles of the same columns are in flight together, so
+        // the p maps they share are fetched from DRAM once.
         // J[N] of every plane is computed at the start of the launch by the blocks with the highest indices (they have the
         // fewest tiles) and published through a per-plane flag; a block waits for the flag of a plane (only thread 0 polls)
         // right before the first epilogue it runs on that plane — by then the line has normally long been published.
         const int nC = ntiles / tiles_per_plane;
+        auto plane_of = [&](int t) { return cbase + ((t / Npol) / tiles_per_plane) * Npol + t % Npol; };
+        auto x0_of = [&](int t) { return ((t / Npol) % tiles_per_plane) * M; };
         int tile = blk, cur = 0, cj = -1;
         if (tile < ntiles) {
-            const int c = cbase + tile / tiles_per_plane, x0 = (tile % tiles_per_plane) * M;
+            const int c = plane_of(tile), x0 = x0_of(tile);
             CMBL_FOR_THREADS(tid, NT) {
                 issue_tile(u + (size_t)c * nmap, x0, sbase, tid);
                 if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 1, nmap), x0, pbuf, tid);
@@ -507,8 +517,8 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         for (; tile < ntiles; tile += nblocks, cur ^= 1) {
             T* const buf = sbase + cur * TILE;
             T* const nbuf = sbase + (cur ^ 1) * TILE;
-            const int c = cbase + tile / tiles_per_plane, x0 = (tile % tiles_per_plane) * M, next = tile + nblocks;
-            const int cn = cbase + next / tiles_per_plane, x0n = (next % tiles_per_plane) * M;
+            const int c = plane_of(tile), x0 = x0_of(tile), next = tile + nblocks;
+            const int cn = plane_of(next), x0n = x0_of(next);
             const T* const p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
             const T* const p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
             const T* const jline = jn_blk + (size_t)c * N;
@@ -775,6 +785,315 @@ template <class T, int LOGN, bool ADJ> struct FastRowBody {
                 pass<R1, true, true>(buf, nullptr, tid / S1, NT / S1, tid % S1, S1, w1, tmp + (size_t)c * nmap + toff);
             }
         }
+    }
+};
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// bulk asynchronous copies (the TMA engine; no tensor map: one contiguous run) with mbarrier completion.  They move the row
+// kernel's tiles without occupying the LSU / L1TEX data path, which the five FFT sweeps need (measured: scattered
+// cp.async landing and 256-bit STG cost as much L1TEX time as three sweeps).  Plain memcpy in the host emulator.
+// ---------------------------------------------------------------------------------------------------------------
+DEV void mbar_init(uint64_t* b, int count) {
+#ifdef __CUDA_ARCH__
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+#else
+    (void)b; (void)count;
+#endif
+}
+DEV void mbar_init_fence() {
+#ifdef __CUDA_ARCH__
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+DEV void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+#ifdef __CUDA_ARCH__
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+#else
+    (void)b; (void)bytes;
+#endif
+}
+DEV void mbar_wait(uint64_t* b, unsigned parity) {
+#ifdef __CUDA_ARCH__
+    asm volatile("{\n.reg .pred p;\nMBW_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MBD_%=;\nbra MBW_%=;\nMBD_%=:\n}"
+                 ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+#else
+    (void)b; (void)parity;
+#endif
+}
+DEV void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+#else
+    (void)b; memcpy(smem_dst, gsrc, bytes);
+#endif
+}
+DEV void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#else
+    memcpy(gdst, smem_src, bytes);
+#endif
+}
+DEV void bulk_wait_read_all() {                 // all bulk stores of this thread have finished READING shared memory
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+DEV void bulk_wait_all() {                      // ... and have completed
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+}
+DEV void fence_proxy_async() {                  // make this thread's shared-memory writes visible to the bulk-copy engine
+#ifdef __CUDA_ARCH__
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// row kernel, bulk-copy version: the tile arrives and leaves as ONE contiguous 32 KB bulk copy each way (row-grouped
+// layout = chunk order [x][cl]); the first sweep reads that linear order and writes the swizzled [cl][x] work layout in
+// place, the last sweep does the reverse (a block holds a whole tile in registers during a sweep, so "read all — barrier —
+// write all" makes the in-place permutation safe).  Two tile buffers: while tile t is transformed in one, tile t+1 lands
+// in the other, which is also where tile t-1's result is read from by its outgoing copy.
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, int LOGN, bool ADJ> struct TmaRowBody {
+    static constexpr int NT = 128, MINB = ADJ ? 2 : (sizeof(T) == 8 ? CMBL_ROW_F64_MINB : 3);
+    static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), H = V / 2;
+    static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
+    static constexpr int S1 = N / R1, N2 = N / R1, NB2 = N / R2, NBM = N / 16;
+    static constexpr int CPX = FAST_TILE_BYTES / (N * 16);
+    static constexpr int ROWS = CPX * V;
+    static constexpr int TILE = FAST_TILE_BYTES / (int)sizeof(T);
+    static constexpr int NP1 = (CPX / 2) / (NT / S1), NP2 = (CPX / 2) / (NT / NB2);      // chunk-row pairs per thread and sweep
+    static_assert(NT % S1 == 0 && NT % NB2 == 0 && NT % NBM == 0 && CPX % 2 == 0 && NP1 >= 1 && NP2 >= 1, "thread/butterfly mapping");
+#ifdef CMBL_EMU
+    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2) + 64 + FAST_TILE_BYTES;   // + snapshot for the serial emulation
+#else
+    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2) + 64;
+#endif
+    static constexpr bool PDL = true;
+    static const char* name() { return "flow_rows"; }
+
+    Fft1D<T> fx; const T* mult;
+    int Ny, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase;
+    const T* u; const T* pk; T* tmp; T* nline; T* nacc; T wgt;
+
+    struct Chunk { C2<T> c[H]; };
+    static DEV Chunk ld(const T* p) { Vec<T> v = vload(p); Chunk r; memcpy(&r, &v, 16); return r; }
+    static DEV void st(T* p, const Chunk& c) { Vec<T> v; memcpy(&v, &c, 16); vstore(p, v); }
+    template <bool LIN> static DEV int off(int cl, int x) { return LIN ? (x * CPX + cl) * V : (cl * N + swzx(x)) * V; }
+
+    DEV void load_w1(int tid, C2<T>* w) const {
+        const int j = tid % S1;
+#pragma unroll
+        for (int q = 1; q < R1; ++q) w[q] = CMBL_LDG(&fx.W[j * q]);
+    }
+    DEV void load_w2(int tid, C2<T>* w) const {
+        const int jj = (tid % NB2) & 15;
+#pragma unroll
+        for (int q = 1; q < R2; ++q) w[q] = CMBL_LDG(&fx.W[jj * q * R1]);
+    }
+    DEV void load_mult(int tid, T* m) const {
+        const int j = tid % NBM;
+#pragma unroll
+        for (int cc = 0; cc < 16 / V; ++cc) { Vec<T> m4 = vload_ldg(mult + 16 * j + cc * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) m[cc * V + e] = m4.v[e]; }
+    }
+    // the three parts of one twiddled radix-R sweep of one thread (butterfly index fixed: element m at x0 + m*xs; chunk-row
+    // pairs g0, g0+gs, ...)
+    template <int R, int NP, bool LIN> DEV void sw_load(const T* buf, const T* pbuf, int g0, int gs, int x0, int xs, Chunk (&x)[NP][2][R]) const {
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int o = off<LIN>(2 * (g0 + i * gs) + s, x0 + m * xs);
+                    x[i][s][m] = ld(buf + o);
+                    if (pbuf) {
+                        Vec<T> p = vload(pbuf + o), a; memcpy(&a, &x[i][s][m], 16);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) a.v[e] *= p.v[e];
+                        memcpy(&x[i][s][m], &a, 16);
+                    }
+                }
+    }
+    template <int R, int NP, bool INV> DEV void sw_compute(Chunk (&x)[NP][2][R], const C2<T>* w) const {
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    C2<T> v[R];
+#pragma unroll
+                    for (int m = 0; m < R; ++m) v[m] = x[i][s][m].c[h];
+                    if (!INV) {
+                        dftR<T, R, false>(v);
+#pragma unroll
+                        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], w[q]);
+                        dftR<T, R, true>(v);
+                    }
+#pragma unroll
+                    for (int m = 0; m < R; ++m) x[i][s][m].c[h] = v[m];
+                }
+    }
+    template <int R, int NP, bool LIN> DEV void sw_store(T* buf, int g0, int gs, int x0, int xs, const Chunk (&x)[NP][2][R]) const {
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) st(buf + off<LIN>(2 * (g0 + i * gs) + s, x0 + m * xs), x[i][s][m]);
+    }
+    DEV void middle(T* buf, int tid, const T* mlt, T* nline_c, T* nacc_c, int y0) const {
+        const int j = tid % NBM;
+        for (int cl = tid / NBM; cl < CPX; cl += NT / NBM) {
+            Chunk x[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) x[q] = ld(buf + off<false>(cl, 16 * j + q));
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                C2<T> v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = x[q].c[h];
+                dft16<T, false>(v);
+                if (j == 0) {                                          // Nyquist coefficient sits at tile position 8
+                    const int y = y0 + 2 * (cl * H + h);
+                    nline_c[y] = v[8].x; nline_c[y + 1] = v[8].y;
+                    if (ADJ) { nacc_c[y] += wgt * v[8].x; nacc_c[y + 1] += wgt * v[8].y; }
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = mk<T>(-mlt[q] * v[q].y, mlt[q] * v[q].x);
+                dft16<T, true>(v);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) x[q].c[h] = v[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) st(buf + off<false>(cl, 16 * j + q), x[q]);
+        }
+    }
+
+    DEV void operator()(int blk, unsigned char* smem) const {
+        T* const sbase = reinterpret_cast<T*>(smem);
+        T* const pbuf = sbase + 2 * TILE;
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2));   // [0],[1]: tile buffers, [2]: p tile
+#ifdef CMBL_EMU
+        T* const snap = reinterpret_cast<T*>(smem + (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2) + 64);
+#endif
+        const size_t nmap = (size_t)N * Ny;
+        constexpr unsigned TB = FAST_TILE_BYTES;
+        C2<T> w1[R1], w2[R2]; T mlt[16];
+        pdl_launch_dependents();
+        CMBL_FOR_THREADS(tid, NT) {
+            CMBL_PRE_END(load_w1(tid, w1)); CMBL_PRE_END(load_w2(tid, w2)); CMBL_PRE_END(load_mult(tid, mlt));
+            if (tid == 0) { mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init_fence(); }
+        }
+        CMBL_SYNC();
+        pdl_wait();
+        const int tbeg = (int)((long long)blk * ntiles / nblocks), tend = (int)((long long)(blk + 1) * ntiles / nblocks);
+        auto tile_ptr = [&](const T* base, int t) { return base + (size_t)(cbase + t / tiles_per_plane) * nmap + (size_t)(t % tiles_per_plane) * ROWS * N; };
+        auto p_ptr = [&](int t) { return p_plane(pk, cbase + t / tiles_per_plane, Npol, Nbphi, 0, nmap) + (size_t)(t % tiles_per_plane) * ROWS * N; };
+        if (tbeg < tend) {
+            CMBL_FOR_THREADS(tid, NT) {
+                if (tid == 0) {
+                    mbar_expect_tx(bars + 0, TB); bulk_load(sbase, tile_ptr(u, tbeg), TB, bars + 0);
+                    if (ADJ) { mbar_expect_tx(bars + 2, TB); bulk_load(pbuf, p_ptr(tbeg), TB, bars + 2); }
+                }
+            }
+        }
+        int it = 0;
+        for (int tile = tbeg; tile < tend; ++tile, ++it) {
+            const int cur = it & 1;
+            T* const buf = sbase + cur * TILE;
+            T* const nbuf = sbase + (cur ^ 1) * TILE;
+            const int c = cbase + tile / tiles_per_plane, y0 = (tile % tiles_per_plane) * ROWS, next = tile + 1;
+            // ---- first sweep: linear landing order -> swizzled work layout, in place ------------------------------------
+#ifdef CMBL_EMU
+            memcpy(snap, buf, TB);
+            CMBL_FOR_THREADS(tid, NT) {
+                load_w1(tid, w1);
+                Chunk x[NP1][2][R1];
+                sw_load<R1, NP1, true>(snap, ADJ ? pbuf : nullptr, tid / S1, NT / S1, tid % S1, S1, x);
+                sw_compute<R1, NP1, false>(x, w1);
+                sw_store<R1, NP1, false>(buf, tid / S1, NT / S1, tid % S1, S1, x);
+            }
+#else
+            {
+                mbar_wait(bars + cur, (unsigned)((it >> 1) & 1));
+                if (ADJ) mbar_wait(bars + 2, (unsigned)(it & 1));
+                Chunk x[NP1][2][R1];
+                sw_load<R1, NP1, true>(buf, ADJ ? pbuf : nullptr, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+                __syncthreads();
+                sw_compute<R1, NP1, false>(x, w1);
+                sw_store<R1, NP1, false>(buf, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+            }
+#endif
+            CMBL_SYNC();
+            if (next < tend) {                                         // the other buffer: its outgoing copy (tile-1) must have read it
+                CMBL_FOR_THREADS(tid, NT) {
+                    if (tid == 0) {
+                        bulk_wait_read_all();
+                        mbar_expect_tx(bars + (cur ^ 1), TB); bulk_load(nbuf, tile_ptr(u, next), TB, bars + (cur ^ 1));
+                        if (ADJ) { mbar_expect_tx(bars + 2, TB); bulk_load(pbuf, p_ptr(next), TB, bars + 2); }
+                    }
+                }
+            }
+            CMBL_FOR_THREADS(tid, NT) {
+                CMBL_PRE_START(load_w2(tid, w2));
+                const int j = tid % NB2;
+                Chunk x[NP2][2][R2];
+                sw_load<R2, NP2, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+                sw_compute<R2, NP2, false>(x, w2);
+                sw_store<R2, NP2, false>(buf, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+            }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) {
+                CMBL_PRE_START(load_mult(tid, mlt));
+                middle(buf, tid, mlt, nline + (size_t)c * Ny, ADJ ? nacc + (size_t)c * Ny : nullptr, y0);
+            }
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) {
+                CMBL_PRE_START(load_w2(tid, w2));
+                const int j = tid % NB2;
+                Chunk x[NP2][2][R2];
+                sw_load<R2, NP2, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+                sw_compute<R2, NP2, true>(x, w2);
+                sw_store<R2, NP2, false>(buf, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+            }
+            CMBL_SYNC();
+            // ---- last sweep: swizzled work layout -> linear order, in place; then one outgoing bulk copy ----------------
+#ifdef CMBL_EMU
+            memcpy(snap, buf, TB);
+            CMBL_FOR_THREADS(tid, NT) {
+                load_w1(tid, w1);
+                Chunk x[NP1][2][R1];
+                sw_load<R1, NP1, false>(snap, nullptr, tid / S1, NT / S1, tid % S1, S1, x);
+                sw_compute<R1, NP1, true>(x, w1);
+                sw_store<R1, NP1, true>(buf, tid / S1, NT / S1, tid % S1, S1, x);
+            }
+#else
+            {
+                Chunk x[NP1][2][R1];
+                sw_load<R1, NP1, false>(buf, nullptr, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+                __syncthreads();
+                sw_compute<R1, NP1, true>(x, w1);
+                sw_store<R1, NP1, true>(buf, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+                fence_proxy_async();
+            }
+#endif
+            CMBL_SYNC();
+            CMBL_FOR_THREADS(tid, NT) { if (tid == 0) bulk_store(const_cast<T*>(tile_ptr(tmp, tile)), buf, TB); }
+        }
+        CMBL_FOR_THREADS(tid, NT) { if (tid == 0) bulk_wait_all(); }
     }
 };
 
