@@ -23,8 +23,10 @@ from ._lib import CmblError, DatasetDesc, FOURIER, MAP, OP_L, OP_LH, OP_LHINV, O
 
 __all__ = [
     "ProjLambert", "Field", "FlatMap", "FlatFourier", "FlatQUMap", "FlatQUFourier", "FlatEBMap", "FlatEBFourier",
-    "Map", "Fourier", "QUMap", "QUFourier", "EBMap", "EBFourier", "LenseBasis", "DerivBasis", "HarmonicBasis",
-    "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "dot", "BaseDataSet", "gradientf_logpdf",
+    "FlatIQUMap", "FlatIQUFourier", "FlatIEBMap", "FlatIEBFourier",
+    "Map", "Fourier", "QUMap", "QUFourier", "EBMap", "EBFourier", "IQUMap", "IQUFourier", "IEBMap", "IEBFourier",
+    "LenseBasis", "DerivBasis", "HarmonicBasis",
+    "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "BlockDiagIEB", "dot", "BaseDataSet", "gradientf_logpdf",
     "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
     "CmblError", "load",
 ]
@@ -99,7 +101,8 @@ class ProjLambert:
 # Fields (src/base_fields.jl:14-21; bases src/generic.jl:9-16)
 # ------------------------------------------------------------------------------------------------------------------
 _BASES = {"Map": (1, False, None), "Fourier": (1, True, None), "QUMap": (2, False, "QU"), "QUFourier": (2, True, "QU"),
-          "EBMap": (2, False, "EB"), "EBFourier": (2, True, "EB")}
+          "EBMap": (2, False, "EB"), "EBFourier": (2, True, "EB"),
+          "IQUMap": (3, False, "IQU"), "IQUFourier": (3, True, "IQU"), "IEBMap": (3, False, "IEB"), "IEBFourier": (3, True, "IEB")}
 
 
 class Field:
@@ -178,6 +181,7 @@ def _mk(basis):
 
 FlatMap, FlatFourier, FlatQUMap, FlatQUFourier, FlatEBMap, FlatEBFourier = (
     _mk(b) for b in ("Map", "Fourier", "QUMap", "QUFourier", "EBMap", "EBFourier"))
+FlatIQUMap, FlatIQUFourier, FlatIEBMap, FlatIEBFourier = (_mk(b) for b in ("IQUMap", "IQUFourier", "IEBMap", "IEBFourier"))
 
 
 def batch(fields):
@@ -205,7 +209,9 @@ def _fft(f: Field, inverse: bool) -> torch.Tensor:
 def _rot(f: Field, to_eb: bool) -> torch.Tensor:
     p = f.proj
     out = torch.empty_like(f.arr)
-    p.lib.call("cmbl_qu_eb", p.handle, 1 if to_eb else 0, _ptr(f.arr), _ptr(out), f.Nbatch, 2, 0, _stream(out))
+    if f.Npol == 3:                                   # IQU <-> IEB: I is copied, the rotation acts on planes 2:3 (src/proj_lambert.jl:284,292)
+        out[:, 0] = f.arr[:, 0]
+    p.lib.call("cmbl_qu_eb", p.handle, 1 if to_eb else 0, _ptr(f.arr), _ptr(out), f.Nbatch, f.Npol, f.Npol - 2, _stream(out))
     return out
 
 
@@ -220,7 +226,7 @@ def convert(f: Field, basis: str) -> Field:
     if pb != cur_pb:                                  # the rotation lives in Fourier space
         if not cur.is_fourier:
             cur = cur._like(_fft(cur, False), cur_pb + "Fourier")
-        cur = cur._like(_rot(cur, to_eb=(pb == "EB")), pb + "Fourier")
+        cur = cur._like(_rot(cur, to_eb=pb.endswith("EB")), pb + "Fourier")
     if cur.is_fourier != four:
         name = (pb or "") + ("Fourier" if four else "Map")
         cur = cur._like(_fft(cur, inverse=not four), name)
@@ -233,9 +239,13 @@ def QUMap(f): return convert(f, "QUMap")
 def QUFourier(f): return convert(f, "QUFourier")
 def EBMap(f): return convert(f, "EBMap")
 def EBFourier(f): return convert(f, "EBFourier")
-def LenseBasis(f): return convert(f, "Map" if f.Npol == 1 else "QUMap")                      # Ł, src/generic.jl:88-93
-def DerivBasis(f): return convert(f, "Fourier" if f.Npol == 1 else "QUFourier")               # Ð
-def HarmonicBasis(f): return convert(f, "Fourier" if f.Npol == 1 else "EBFourier")
+def IQUMap(f): return convert(f, "IQUMap")
+def IQUFourier(f): return convert(f, "IQUFourier")
+def IEBMap(f): return convert(f, "IEBMap")
+def IEBFourier(f): return convert(f, "IEBFourier")
+def LenseBasis(f): return convert(f, ("Map", "QUMap", "IQUMap")[f.Npol - 1])                  # Ł, src/generic.jl:88-93
+def DerivBasis(f): return convert(f, ("Fourier", "QUFourier", "IQUFourier")[f.Npol - 1])      # Ð
+def HarmonicBasis(f): return convert(f, ("Fourier", "EBFourier", "IEBFourier")[f.Npol - 1])
 
 
 def dot(a: Field, b: Field) -> np.ndarray:
@@ -288,6 +298,39 @@ class DiagOp:
 
 
 Diagonal = DiagOp
+
+
+class BlockDiagIEB:
+    """BlockDiagIEB(ΣTE, ΣB) (src/specialops.jl:61-118): [ΣTT ΣTE; ΣTE ΣEE] ⊕ ΣBB acting on IEBFourier fields.  Built from
+    four real Fourier-basis half-planes (what Cℓ_to_Cov(:IP) produces, src/proj_lambert.jl:368-371); `L * f`, `L.ldiv(f)`
+    (= pinv(L) * f, :78) and `L.sqrt_mul(f)` (simulate, :94) run on the device."""
+
+    def __init__(self, ΣTT, ΣTE, ΣEE, ΣBB, proj: ProjLambert | None = None):
+        planes = []
+        for a in (ΣTT, ΣTE, ΣEE, ΣBB):
+            if isinstance(a, DiagOp):
+                proj = proj or a.diag.proj
+                a = a._real
+            if isinstance(a, np.ndarray):
+                a = torch.from_numpy(np.ascontiguousarray(a))
+            planes.append(a.reshape(a.shape[-2], a.shape[-1]))
+        if proj is None:
+            raise CmblError("BlockDiagIEB from raw arrays needs proj=")
+        self.proj = proj
+        self._real = torch.stack(planes)[None].to(device=proj.device, dtype=proj.T).contiguous()      # [1, 4, Nx, Nyh]
+        if tuple(self._real.shape) != (1, 4, proj.Nx, proj.Nyh):
+            raise CmblError("BlockDiagIEB planes must be (Ny÷2+1, Nx) half-planes")
+
+    def _apply(self, f: Field, mode: int) -> Field:
+        f = convert(f, "IEBFourier")                                          # L * IEBFourier(f), :77
+        p = f.proj
+        out = torch.empty_like(f.arr)
+        p.lib.call("cmbl_blockdiag_ieb", p.handle, mode, _ptr(self._real), _ptr(f.arr), _ptr(out), f.Nbatch, _stream(out))
+        return f._like(out)
+
+    def __mul__(self, f): return self._apply(f, 0)
+    def ldiv(self, f): return self._apply(f, 1)
+    def sqrt_mul(self, f): return self._apply(f, 2)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -368,7 +411,8 @@ class _AdjointFlow:
 # ------------------------------------------------------------------------------------------------------------------
 class BaseDataSet:
     """The fields of BaseDataSet used by argmaxf_logpdf: d, Cf, Cn, Cn̂, B, B̂, M = Mf∘Mpix, M̂ = Mf, L (src/dataset.jl:37-57).
-    Diagonals are DiagOps over real harmonic-basis fields with batch 1; `Mpix` is a Map-basis DiagOp or None."""
+    For pol = I / P the operators are DiagOps over real harmonic-basis fields with batch 1; for pol = IP (IEBFourier data) they
+    are BlockDiagIEBs, as load_sim builds them (src/dataset.jl:262-301).  `Mpix` is a Map-basis DiagOp or None."""
 
     def __init__(self, d: Field, Cf: DiagOp, Cn: DiagOp, B: DiagOp, Mf: DiagOp, Mpix: DiagOp | None = None,
                  Cnhat: DiagOp | None = None, Bhat: DiagOp | None = None, L=LenseFlow, nsteps: int = 7,
@@ -386,6 +430,10 @@ class BaseDataSet:
         p = d.proj
         L = self.L(ϕ, self.nsteps) if isinstance(self.L, type) else self.L
         cache = L.cache(d)                                                    # keyed on (Npol, Nbatch)
+        want = BlockDiagIEB if d.Npol == 3 else DiagOp
+        for nm in ("Cf", "Cn", "Cnhat", "B", "Bhat", "Mf"):
+            if not isinstance(getattr(self, nm), want):
+                raise CmblError(f"BaseDataSet.{nm} must be a {want.__name__} for {d.basis} data")
         desc = DatasetDesc(d.Npol, d.Nbatch, *(c_void_p(D._real.data_ptr()) for D in (self.Cf, self.Cn, self.Cnhat, self.B, self.Bhat, self.Mf)),
                            c_void_p(self.Mpix._real.data_ptr()) if self.Mpix is not None else c_void_p(0), _ptr(d.arr))
         h = c_void_p()
@@ -421,9 +469,21 @@ def gradientf_logpdf(ds: BaseDataSet, f: Field, ϕ: Field, d: Field | None = Non
     return f._like(out)
 
 
-def Hessian_logpdf_preconditioner(ds: BaseDataSet) -> DiagOp:
-    """pinv(Cf) + B̂'M̂'pinv(Cn̂)M̂B̂ (src/dataset.jl:129-132)."""
+def Hessian_logpdf_preconditioner(ds: BaseDataSet):
+    """pinv(Cf) + B̂'M̂'pinv(Cn̂)M̂B̂ (src/dataset.jl:129-132); a DiagOp, or a BlockDiagIEB for pol = IP (operator algebra of
+    src/specialops.jl:88,99-102 — setup-time host mirror; the solver forms the same block on the device in cg_setup)."""
     pinv = lambda t: torch.where(t == 0, torch.zeros_like(t), 1 / t)
+    if isinstance(ds.Cf, BlockDiagIEB):
+        full = lambda L: (L._real[0, 0], L._real[0, 1], L._real[0, 1], L._real[0, 2], L._real[0, 3])          # [a b; c d] ⊕ e
+        def inv(m):
+            a, _, c, d, e = m
+            idet = pinv(a * d - c * c)
+            return (d * idet, -(c * idet), -(c * idet), a * idet, pinv(e))
+        mm = lambda x, y: (x[0] * y[0] + x[1] * y[2], x[0] * y[1] + x[1] * y[3], x[2] * y[0] + x[3] * y[2], x[2] * y[1] + x[3] * y[3], x[4] * y[4])
+        bh, mf = full(ds.Bhat), full(ds.Mf)
+        h, icf = mm(mm(mm(mm(bh, mf), inv(full(ds.Cnhat))), mf), bh), inv(full(ds.Cf))
+        s = tuple(u + v for u, v in zip(icf, h))
+        return BlockDiagIEB(s[0], s[2], s[3], s[4], proj=ds.Cf.proj)
     r = pinv(ds.Cf._real) + ds.Bhat._real * ds.Mf._real * pinv(ds.Cnhat._real) * ds.Mf._real * ds.Bhat._real
     return DiagOp(Field(ds.Cf.diag.basis, r.to(ds.Cf.diag.arr.dtype), ds.Cf.diag.proj))
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "cmbl_irfft2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cmbl_diag_mul": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cmbl_qu_eb": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cmbl_blockdiag_ieb": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cmbl_dot": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, POINTER(c_double), c_void_p]),
     "cmbl_lenseflow_create": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int]),
     "cmbl_lenseflow_destroy": (c_int, [c_void_p]),

@@ -24,6 +24,13 @@ int cmbl_qu_eb(cmbl_plan* plan, int dir, const void* in, void* out, int Nb, int 
     CMBL_API_END
 }
 
+int cmbl_blockdiag_ieb(cmbl_plan* plan, int mode, const void* block, const void* in, void* out, int Nb, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan && plan->p && block && in && out, "NULL argument");
+    CMBL_DISPATCH(plan->p.get(), cmbl::blockdiag_ieb<T>(P, mode, (const T*)block, (const cmbl::C2<T>*)in, (cmbl::C2<T>*)out, Nb, as_stream(stream)));
+    CMBL_API_END
+}
+
 int cmbl_dot(cmbl_plan* plan, int basis, const void* a, const void* b, int Npol, int Nb, double* out_host, void* stream) {
     CMBL_API_BEGIN
     CMBL_REQUIRE(plan && plan->p && a && b && out_host, "NULL argument");

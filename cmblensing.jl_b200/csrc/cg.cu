@@ -23,18 +23,52 @@ template <class T> struct DerivedDiagBody {
     }
 };
 
+// Npol = 3 (pol = :IP): every harmonic operator is a BlockDiagIEB of 4 planes [ΣTE[1,1], ΣTE[2,1], ΣTE[2,2], ΣB]
+// (src/specialops.jl:61-118).  2×2 pinv as src/field_vectors.jl:74-78 (the off-diagonal is read from [2,1] twice);
+// the preconditioner pinv(Cf) + B̂'M̂'pinv(Cn̂)M̂B̂ is formed with full 2×2 products, left to right (src/specialops.jl:101-102).
+template <class T> struct DerivedBlockBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "derived_block"; }
+    size_t nf; const T *Cf, *Cn, *Cnhat, *Bhat, *Mf;
+    T *inv_Cf, *inv_Cn, *inv_precond;
+    struct M2 { T a, b, c, d, e; };                   // [a b; c d] ⊕ e
+    HD static T pinv(T v) { return v == (T)0 ? (T)0 : (T)1 / v; }
+    HD M2 ld(const T* A, size_t r) const { return M2{A[r], A[nf + r], A[nf + r], A[2 * nf + r], A[3 * nf + r]}; }
+    HD void st4(T* A, size_t r, const M2& m) const { A[r] = m.a; A[nf + r] = m.c; A[2 * nf + r] = m.d; A[3 * nf + r] = m.e; }
+    HD static M2 inv(const M2& m) { const T id = pinv(m.a * m.d - m.c * m.c); return M2{m.d * id, -(m.c * id), -(m.c * id), m.a * id, pinv(m.e)}; }
+    HD static M2 mul(const M2& x, const M2& y) { return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d, x.e * y.e}; }
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t r = (size_t)blk * NT + tid;
+            if (r < nf) {
+                const M2 icf = inv(ld(Cf, r)), icn = inv(ld(Cn, r)), icnh = inv(ld(Cnhat, r)), bh = ld(Bhat, r), mf = ld(Mf, r);
+                st4(inv_Cf, r, icf); st4(inv_Cn, r, icn);
+                const M2 h = mul(mul(mul(mul(bh, mf), icnh), mf), bh);
+                st4(inv_precond, r, inv(M2{icf.a + h.a, icf.b + h.b, icf.c + h.c, icf.d + h.d, icf.e + h.e}));
+            }
+        }
+    }
+};
+
 template <class T> void cg_setup(CgT<T>& G, const cmbl_dataset_desc& ds, cmblStream_t st) {
-    CMBL_REQUIRE(ds.Npol == 1 || ds.Npol == 2, "CG Wiener filter supports Npol = 1 (I) or 2 (P); IQU needs BlockDiagIEB");
+    CMBL_REQUIRE(ds.Npol >= 1 && ds.Npol <= 3, "CG Wiener filter supports Npol = 1 (I), 2 (P) or 3 (IP, BlockDiagIEB operators)");
     CMBL_REQUIRE(ds.Npol == G.F->Npol && ds.Nb == G.F->Nb, "dataset Npol/Nb must match the LenseFlow handle");
     CMBL_REQUIRE(ds.Cf && ds.Cn && ds.Cnhat && ds.B && ds.Bhat && ds.Mf && ds.d, "NULL dataset diagonal");
     G.Npol = ds.Npol; G.Nb = ds.Nb; G.C = ds.Npol * ds.Nb;
     G.Cf = (const T*)ds.Cf; G.Cn = (const T*)ds.Cn; G.Cnhat = (const T*)ds.Cnhat; G.B = (const T*)ds.B; G.Bhat = (const T*)ds.Bhat;
     G.Mf = (const T*)ds.Mf; G.mask = (const T*)ds.mask_pix; G.d = (const C2<T>*)ds.d;
-    const size_t n = G.nf() * G.Npol;
-    DerivedDiagBody<T> b{n, G.Cf, G.Cn, G.Cnhat, G.B, G.Bhat, G.Mf,
-        (T*)G.inv_Cf.reserve(n * sizeof(T)), (T*)G.inv_Cn.reserve(n * sizeof(T)), (T*)G.inv_Cn_Mf.reserve(n * sizeof(T)),
-        (T*)G.precond.reserve(n * sizeof(T))};
-    launch(b, (int)((n + b.NT - 1) / b.NT), 0, st);
+    if (G.Npol == 3) {
+        const size_t n4 = G.nf() * 4;
+        DerivedBlockBody<T> b{G.nf(), G.Cf, G.Cn, G.Cnhat, G.Bhat, G.Mf,
+            (T*)G.inv_Cf.reserve(n4 * sizeof(T)), (T*)G.inv_Cn.reserve(n4 * sizeof(T)), (T*)G.precond.reserve(n4 * sizeof(T))};
+        launch(b, (int)((G.nf() + b.NT - 1) / b.NT), 0, st);
+    } else {
+        const size_t n = G.nf() * G.Npol;
+        DerivedDiagBody<T> b{n, G.Cf, G.Cn, G.Cnhat, G.B, G.Bhat, G.Mf,
+            (T*)G.inv_Cf.reserve(n * sizeof(T)), (T*)G.inv_Cn.reserve(n * sizeof(T)), (T*)G.inv_Cn_Mf.reserve(n * sizeof(T)),
+            (T*)G.precond.reserve(n * sizeof(T))};
+        launch(b, (int)((n + b.NT - 1) / b.NT), 0, st);
+    }
     const size_t vb = sizeof(C2<T>) * G.nf() * G.C;
     for (DevBuf* v : {&G.x, &G.r, &G.z, &G.p, &G.Ap, &G.b, &G.bestx, &G.w1, &G.w2}) v->reserve(vb);
     G.m1.reserve(sizeof(T) * G.nmap() * G.C);
@@ -45,12 +79,12 @@ template <class T> void cg_setup(CgT<T>& G, const cmbl_dataset_desc& ds, cmblStr
 
 template <class T>
 static void chain(CgT<T>& G, const C2<T>* in, const T* din, const C2<T>* d, bool neg, const T* pre, int rot, const T* post,
-                  const T* sdiag, const C2<T>* sub, C2<T>* out, cmblStream_t st) {
+                  const T* sdiag, const C2<T>* sub, C2<T>* out, cmblStream_t st, const T* pre2 = nullptr) {
     FourierChainBody<T> b;
-    b.Npol = G.Npol; b.Nb = G.Nb; b.nf = G.nf(); b.rot = (G.Npol == 2) ? rot : 0; b.neg = neg;
+    b.Npol = G.Npol; b.Nb = G.Nb; b.nf = G.nf(); b.rot = (G.Npol >= 2) ? rot : 0; b.neg = neg;
     b.sin2phi = G.P->sin2phi; b.cos2phi = G.P->cos2phi;
-    b.in = in; b.din = din; b.d = d; b.pre = pre; b.post = post; b.sdiag = sdiag; b.sub = sub; b.out = out;
-    size_t threads = (G.Npol == 2) ? b.nf * G.Nb : b.nf * G.Nb * G.Npol;
+    b.in = in; b.din = din; b.d = d; b.pre = pre; b.pre2 = pre2; b.post = post; b.sdiag = sdiag; b.sub = sub; b.out = out;
+    size_t threads = (G.Npol >= 2) ? b.nf * G.Nb : b.nf * G.Nb * G.Npol;
     launch(b, (int)((threads + b.NT - 1) / b.NT), 0, st);
 }
 
@@ -61,6 +95,9 @@ template <class T> void cg_gradientf(CgT<T>& G, const C2<T>* f, const C2<T>* d, 
     const int C = G.C, n = F.nsteps;
     const T* none = nullptr; const C2<T>* cnone = nullptr;
     if (!d && !d_zero) d = G.d;
+    // Mf'·pinv(Cn): one fused diagonal for Npol ≤ 2, two block operators (pinv(Cn) then Mf) for Npol = 3
+    const T* const icn1 = G.Npol == 3 ? (const T*)G.inv_Cn.p : (const T*)G.inv_Cn_Mf.p;
+    const T* const icn2 = G.Npol == 3 ? G.Mf : nullptr;
     // Ł(f): EB→QU, irfft2 ; Lϕ* in map space
     chain<T>(G, f, none, cnone, false, none, 1, none, none, cnone, w1, st);
     irfft2<T>(P, w1, m1, C, st);
@@ -75,7 +112,7 @@ template <class T> void cg_gradientf(CgT<T>& G, const C2<T>* f, const C2<T>* d, 
         rfft2<T>(P, m1, w1, C, st);
         chain<T>(G, w1, none, cnone, false, none, 2, G.Mf, none, cnone, w2, st);
         // pinv(Cn)(d − ·), then M' = Mpix'∘Mf': ×(Mf·pinv(Cn)), EB→QU | irfft2 | ×Mpix | rfft2 | QU→EB, ×B', EB→QU
-        chain<T>(G, w2, none, d, d == nullptr, (const T*)G.inv_Cn_Mf.p, 1, none, none, cnone, w1, st);
+        chain<T>(G, w2, none, d, d == nullptr, icn1, 1, none, none, cnone, w1, st, icn2);
         irfft2<T>(P, w1, m1, C, st);
         diag_mul<T>(P, CMBL_MAP, G.mask, G.Npol, m1, m1, C, false, st);
         rfft2<T>(P, m1, w1, C, st);
@@ -84,7 +121,7 @@ template <class T> void cg_gradientf(CgT<T>& G, const C2<T>* f, const C2<T>* d, 
     } else {
         // everything between Lϕ and Lϕ' is diagonal in the harmonic basis: B'·Mf·pinv(Cn)·(d − Mf·B·f̃)
         chain<T>(G, w1, none, cnone, false, none, 2, G.B, none, cnone, w2, st);
-        chain<T>(G, w2, G.Mf, d, d == nullptr, (const T*)G.inv_Cn_Mf.p, 0, G.B, none, cnone, w1, st);
+        chain<T>(G, w2, G.Mf, d, d == nullptr, icn1, 0, G.B, none, cnone, w1, st, icn2);
         chain<T>(G, w1, none, cnone, false, none, 1, none, none, cnone, w1, st);
     }
     // Lϕ' (Fourier QU state), back to the harmonic basis, − pinv(Cf) f
@@ -116,6 +153,7 @@ template <class T> void cg_begin(CgT<T>& G, const C2<T>* fstart, bool offset, do
     }
     CgInitBody<T> k{G.nf() * G.Npol, P.Nyh, P.lam, 1.0 / ((double)P.Ny * (double)P.Nx), (const T*)G.precond.p,
                     b, Ax, (C2<T>*)G.r.p, (C2<T>*)G.z.p, (C2<T>*)G.p.p, G.res_part()};
+    if (G.Npol == 3) k.nf_block = G.nf();
     launch(k, G.Nb * RED_BLOCKS, sizeof(double) * k.NT, st);
     G.flip = 0;
     SumPartialsBody s{G.Nb, G.res_part(), G.res_cur()};

@@ -172,7 +172,7 @@ template <class Body, class = void> struct UsesPdl { static constexpr bool value
 template <class Body> struct UsesPdl<Body, decltype((void)Body::PDL)> { static constexpr bool value = Body::PDL; };
 inline bool pdl_enabled() { static const bool v = [] { const char* e = getenv("CMBL_PDL"); return e && atoi(e) != 0; }(); return v; }
 template <class Body> __global__ void __launch_bounds__(Body::NT, MinBlocks<Body>::value) kern(const Body b) {
-    extern __shared__ __align__(16) unsigned char cmbl_smem[];
+    extern __shared__ __align__(1024) unsigned char cmbl_smem[];   // 1024: tensor-map copies with the 128-byte swizzle
     b((int)blockIdx.x, cmbl_smem);
 }
 #endif

@@ -21,6 +21,12 @@ template <class T> void qu_eb(PlanT<T>& P, int dir, const C2<T>* in, C2<T>* out,
     launch(b, (int)((b.nf * Nb + b.NT - 1) / b.NT), 0, st);
 }
 
+template <class T> void blockdiag_ieb(PlanT<T>& P, int mode, const T* block, const C2<T>* in, C2<T>* out, int Nb, cmblStream_t st) {
+    CMBL_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (L*f), 1 (L\\f) or 2 (sqrt(L)*f)");
+    BlockIebBody<T> b{P.four_elems(), Nb, mode, block, in, out};
+    launch(b, (int)((b.nf * Nb + b.NT - 1) / b.NT), 0, st);
+}
+
 template <class T> void dot_partials(PlanT<T>& P, int basis, const void* a, const void* b, int Npol, int Nb, double* partial, cmblStream_t st) {
     if (basis == CMBL_FOURIER) {
         DotBody<T, true> k{P.four_elems() * (size_t)Npol, P.Nyh, P.lam, 1.0 / ((double)P.Ny * (double)P.Nx), a, b, partial};
@@ -34,6 +40,7 @@ template <class T> void dot_partials(PlanT<T>& P, int basis, const void* a, cons
 #define INST(T)                                                                                                   \
     template void diag_mul<T>(PlanT<T>&, int, const T*, int, const void*, void*, int, bool, cmblStream_t);        \
     template void qu_eb<T>(PlanT<T>&, int, const C2<T>*, C2<T>*, int, int, int, cmblStream_t);                    \
+    template void blockdiag_ieb<T>(PlanT<T>&, int, const T*, const C2<T>*, C2<T>*, int, cmblStream_t);            \
     template void dot_partials<T>(PlanT<T>&, int, const void*, const void*, int, int, double*, cmblStream_t);
 INST(float)
 INST(double)

@@ -42,9 +42,12 @@ template <class T, bool CPLX> struct DiagMulBody {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// fused Fourier-space chain on harmonic-basis fields (Npol = 1: no rotation; Npol = 2: planes (E,B) / (Q,U)):
-//   v = in;  v *= din;  v = d − v (or −v when neg);  v *= pre;  v = Rot(v);  v *= post;  v −= sdiag·sub;  out = v
-// every diagonal is REAL with Npol planes shared across the batch (NULL = skip).
+// fused Fourier-space chain on harmonic-basis fields (Npol = 1: no rotation; Npol = 2: planes (E,B) / (Q,U);
+// Npol = 3: planes (I,E,B) / (I,Q,U), the rotation acts on planes 2:3, src/proj_lambert.jl:284,292):
+//   v = in;  v *= din;  v = d − v (or −v when neg);  v *= pre;  v *= pre2;  v = Rot(v);  v *= post;  v −= sdiag·sub;  out = v
+// Npol ≤ 2: every diagonal is REAL with Npol planes shared across the batch (NULL = skip).
+// Npol = 3: every operator is a BlockDiagIEB (src/specialops.jl:61-82) of 4 REAL planes [ΣTE[1,1], ΣTE[2,1], ΣTE[2,2], ΣB]
+//           applied to (I,E,B):  i′ = A11 i + A21 e,  e′ = A21 i + A22 e,  b′ = ΣB b   (the 2×2 block is symmetric).
 // rot: 0 none, 1 EB→QU, 2 QU→EB  (src/proj_lambert.jl:253-271)
 // ---------------------------------------------------------------------------------------------------------------
 template <class T> struct FourierChainBody {
@@ -53,6 +56,25 @@ template <class T> struct FourierChainBody {
     int Npol, Nb; size_t nf; int rot; bool neg;
     const T *sin2phi, *cos2phi;
     const C2<T>* in; const T* din; const C2<T>* d; const T* pre; const T* post; const T* sdiag; const C2<T>* sub; C2<T>* out;
+    const T* pre2 = nullptr;                          // second pre-rotation operator (Npol = 3 only; diagonals are fused instead)
+    HD void block(const T* A, size_t r, C2<T>& i, C2<T>& e, C2<T>& b) const {
+        const T a11 = A[r], a21 = A[nf + r], a22 = A[2 * nf + r], bb = A[3 * nf + r];
+        const C2<T> ni = mk<T>(a11 * i.x + a21 * e.x, a11 * i.y + a21 * e.y);
+        const C2<T> ne = mk<T>(a21 * i.x + a22 * e.x, a21 * i.y + a22 * e.y);
+        i = ni; e = ne; b = cscale(b, bb);
+    }
+    HD void rotate(int dir, size_t r, C2<T>& a, C2<T>& c) const {
+        const T s = sin2phi[r], co = cos2phi[r];
+        C2<T> na, nc;
+        if (dir == 1) {      // Q = −E c + B s ; U = −E s − B c
+            na = mk<T>(-a.x * co + c.x * s, -a.y * co + c.y * s);
+            nc = mk<T>(-a.x * s - c.x * co, -a.y * s - c.y * co);
+        } else {             // E = −Q c − U s ; B = Q s − U c
+            na = mk<T>(-a.x * co - c.x * s, -a.y * co - c.y * s);
+            nc = mk<T>(a.x * s - c.x * co, a.y * s - c.y * co);
+        }
+        a = na; c = nc;
+    }
     HD C2<T> head(C2<T> v, size_t r, int pol, size_t e) const {
         if (din) v = cscale(v, din[pol * nf + r]);
         if (d) v = d[e] - v; else if (neg) v = mk<T>(-v.x, -v.y);
@@ -72,19 +94,27 @@ template <class T> struct FourierChainBody {
                     size_t b = t / nf, r = t - b * nf;
                     size_t e0 = (b * 2) * nf + r, e1 = e0 + nf;
                     C2<T> a = head(in[e0], r, 0, e0), c = head(in[e1], r, 1, e1);
-                    if (rot) {
-                        T s = sin2phi[r], co = cos2phi[r];
-                        C2<T> na, nc;
-                        if (rot == 1) {      // Q = −E c + B s ; U = −E s − B c
-                            na = mk<T>(-a.x * co + c.x * s, -a.y * co + c.y * s);
-                            nc = mk<T>(-a.x * s - c.x * co, -a.y * s - c.y * co);
-                        } else {             // E = −Q c − U s ; B = Q s − U c
-                            na = mk<T>(-a.x * co - c.x * s, -a.y * co - c.y * s);
-                            nc = mk<T>(a.x * s - c.x * co, a.y * s - c.y * co);
-                        }
-                        a = na; c = nc;
-                    }
+                    if (rot) rotate(rot, r, a, c);
                     out[e0] = tail(a, r, 0, e0); out[e1] = tail(c, r, 1, e1);
+                }
+            } else if (Npol == 3) {
+                if (t < nf * Nb) {
+                    size_t b = t / nf, r = t - b * nf;
+                    size_t e0 = (b * 3) * nf + r, e1 = e0 + nf, e2 = e1 + nf;
+                    C2<T> i = in[e0], a = in[e1], c = in[e2];
+                    if (din) block(din, r, i, a, c);
+                    if (d) { i = d[e0] - i; a = d[e1] - a; c = d[e2] - c; }
+                    else if (neg) { i = mk<T>(-i.x, -i.y); a = mk<T>(-a.x, -a.y); c = mk<T>(-c.x, -c.y); }
+                    if (pre) block(pre, r, i, a, c);
+                    if (pre2) block(pre2, r, i, a, c);
+                    if (rot) rotate(rot, r, a, c);
+                    if (post) block(post, r, i, a, c);
+                    if (sub) {
+                        C2<T> si = sub[e0], sa = sub[e1], sc = sub[e2];
+                        block(sdiag, r, si, sa, sc);
+                        i = i - si; a = a - sa; c = c - sc;
+                    }
+                    out[e0] = i; out[e1] = a; out[e2] = c;
                 }
             } else {
                 if (t < nf * Nb * Npol) {
@@ -92,6 +122,35 @@ template <class T> struct FourierChainBody {
                     int pol = (int)(cpl % Npol);
                     out[t] = tail(head(in[t], r, pol, t), r, pol, t);
                 }
+            }
+        }
+    }
+};
+
+// BlockDiagIEB applied to an IEBFourier field (src/specialops.jl:77-82,87-88): mode 0  L*f, 1  L\f = pinv(L)*f, 2  sqrt(L)*f.
+// block = 4 REAL half-planes [ΣTE[1,1], ΣTE[2,1], ΣTE[2,2], ΣB]; the 2×2 pinv / sqrt follow src/field_vectors.jl:62-78
+// (the off-diagonal is read from [2,1] for both positions).
+template <class T> struct BlockIebBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "blockdiag_ieb"; }
+    size_t nf; int Nb, mode; const T* A; const C2<T>* in; C2<T>* out;
+    HD static T pinv(T v) { return v == (T)0 ? (T)0 : (T)1 / v; }
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t t = (size_t)blk * NT + tid;
+            if (t < nf * Nb) {
+                size_t b = t / nf, r = t - b * nf;
+                T a = A[r], c = A[nf + r], d = A[2 * nf + r], e = A[3 * nf + r];
+                if (mode == 1) { const T id = pinv(a * d - c * c); const T na = d * id, nc = -(c * id), nd = a * id; a = na; c = nc; d = nd; e = pinv(e); }
+                else if (mode == 2) {
+                    const T s = sqrt(a * d - c * c), tt = pinv(sqrt(a + (d + 2 * s)));
+                    const T na = tt * (a + s), nc = tt * c, nd = tt * (d + s); a = na; c = nc; d = nd; e = sqrt(e);
+                }
+                const size_t e0 = (b * 3) * nf + r, e1 = e0 + nf, e2 = e1 + nf;
+                const C2<T> i = in[e0], ee = in[e1], bb = in[e2];
+                out[e0] = mk<T>(a * i.x + c * ee.x, a * i.y + c * ee.y);
+                out[e1] = mk<T>(c * i.x + d * ee.x, c * i.y + d * ee.y);
+                out[e2] = cscale(bb, e);
             }
         }
     }
@@ -167,6 +226,25 @@ template <class T> struct CgUpdate1Body {
         CMBL_FOR_THREADS(tid, NT) {
             const T alpha = (T)(res[bi] / sum_partials(pAp_part + (size_t)bi * RED_BLOCKS));
             double s = 0;
+            if (Npol == 3) {
+                // BlockDiagIEB preconditioner: z = pinv(M) * r (src/specialops.jl:78); Mdiag = the 4 planes of pinv(M)
+                for (size_t e = (size_t)j * NT + tid; e < nf; e += (size_t)RED_BLOCKS * NT) {
+                    C2<T> rv[3];
+                    for (int c = 0; c < 3; ++c) {
+                        const size_t g = base + c * nf + e;
+                        C2<T> pv = p[g], av = Ap[g], xv = x[g], rr = r[g];
+                        x[g] = mk<T>(xv.x + alpha * pv.x, xv.y + alpha * pv.y);
+                        rv[c] = mk<T>(rr.x - alpha * av.x, rr.y - alpha * av.y);
+                        r[g] = rv[c];
+                    }
+                    const T a11 = Mdiag[e], a21 = Mdiag[nf + e], a22 = Mdiag[2 * nf + e], bb = Mdiag[3 * nf + e];
+                    C2<T> zv[3] = {mk<T>(a11 * rv[0].x + a21 * rv[1].x, a11 * rv[0].y + a21 * rv[1].y),
+                                   mk<T>(a21 * rv[0].x + a22 * rv[1].x, a21 * rv[0].y + a22 * rv[1].y), cscale(rv[2], bb)};
+                    double q = 0;
+                    for (int c = 0; c < 3; ++c) { z[base + c * nf + e] = zv[c]; q += (double)rv[c].x * (double)zv[c].x + (double)rv[c].y * (double)zv[c].y; }
+                    s += q * (double)lam[e % Nyh];
+                }
+            } else
             for (size_t e = (size_t)j * NT + tid; e < per_batch; e += (size_t)RED_BLOCKS * NT) {
                 C2<T> pv = p[base + e], av = Ap[base + e], xv = x[base + e], rv = r[base + e];
                 xv = mk<T>(xv.x + alpha * pv.x, xv.y + alpha * pv.y);
@@ -212,12 +290,31 @@ template <class T> struct CgInitBody {
     static const char* name() { return "cg_init"; }
     size_t per_batch; int Nyh; const T* lam; double scale; const T* Mdiag;
     const C2<T>* b; const C2<T>* Ax; C2<T>* r; C2<T>* z; C2<T>* p; double* res_part;
+    size_t nf_block = 0;                              // > 0: BlockDiagIEB preconditioner (Npol = 3), Mdiag = 4 planes of pinv(M)
     DEV void operator()(int blk, unsigned char* smem) const {
         double* sm = reinterpret_cast<double*>(smem);
         const int bi = blk / RED_BLOCKS, j = blk % RED_BLOCKS;
         const size_t base = (size_t)bi * per_batch;
         CMBL_FOR_THREADS(tid, NT) {
             double s = 0;
+            if (nf_block) {
+                const size_t nf = nf_block;
+                for (size_t e = (size_t)j * NT + tid; e < nf; e += (size_t)RED_BLOCKS * NT) {
+                    C2<T> rv[3];
+                    for (int c = 0; c < 3; ++c) {
+                        const size_t g = base + c * nf + e;
+                        rv[c] = b[g];
+                        if (Ax) rv[c] = rv[c] - Ax[g];
+                        r[g] = rv[c];
+                    }
+                    const T a11 = Mdiag[e], a21 = Mdiag[nf + e], a22 = Mdiag[2 * nf + e], bb = Mdiag[3 * nf + e];
+                    C2<T> zv[3] = {mk<T>(a11 * rv[0].x + a21 * rv[1].x, a11 * rv[0].y + a21 * rv[1].y),
+                                   mk<T>(a21 * rv[0].x + a22 * rv[1].x, a21 * rv[0].y + a22 * rv[1].y), cscale(rv[2], bb)};
+                    double q = 0;
+                    for (int c = 0; c < 3; ++c) { z[base + c * nf + e] = zv[c]; p[base + c * nf + e] = zv[c]; q += (double)rv[c].x * (double)zv[c].x + (double)rv[c].y * (double)zv[c].y; }
+                    s += q * (double)lam[e % Nyh];
+                }
+            } else
             for (size_t e = (size_t)j * NT + tid; e < per_batch; e += (size_t)RED_BLOCKS * NT) {
                 C2<T> rv = b[base + e];
                 if (Ax) rv = rv - Ax[base + e];
@@ -247,6 +344,7 @@ struct SumPartialsBody {
 
 template <class T> void diag_mul(PlanT<T>& P, int basis, const T* diag, int Cd, const void* in, void* out, int C, bool ldiv, cmblStream_t st);
 template <class T> void qu_eb(PlanT<T>& P, int dir, const C2<T>* in, C2<T>* out, int Nb, int stride_planes, int first_plane, cmblStream_t st);
+template <class T> void blockdiag_ieb(PlanT<T>& P, int mode, const T* block, const C2<T>* in, C2<T>* out, int Nb, cmblStream_t st);
 // per-batch dot into device partial sums; returns pointer to partial[Nb][RED_BLOCKS] (plan scratch)
 template <class T> void dot_partials(PlanT<T>& P, int basis, const void* a, const void* b, int Npol, int Nb, double* partial, cmblStream_t st);
 

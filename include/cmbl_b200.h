@@ -72,6 +72,10 @@ int cmbl_diag_mul(cmbl_plan* plan, int basis, const void* diag, int Cd, const vo
 /* QU<->EB rotation in Fourier space (src/proj_lambert.jl:253-271). dir 0: EB->QU, 1: QU->EB.  The two planes of each of
  * the Nb pairs are consecutive; pair_stride_planes = Npol of the array (2 for QU, 3 for IQU with first_plane = 1). */
 int cmbl_qu_eb(cmbl_plan* plan, int dir, const void* in, void* out, int Nb, int pair_stride_planes, int first_plane, void* stream);
+/* BlockDiagIEB on an IEBFourier field of Nb batch items (src/specialops.jl:61-118; 2x2 sqrt/pinv src/field_vectors.jl:62-78).
+ * block: 4 REAL half-planes [SigmaTE[1,1], SigmaTE[2,1], SigmaTE[2,2], SigmaB] (Cl_to_Cov(:IP) builds the 2x2 block symmetric,
+ * src/proj_lambert.jl:368-371).  mode 0: L*f, 1: L\f = pinv(L)*f, 2: sqrt(L)*f (simulate).  in may alias out. */
+int cmbl_blockdiag_ieb(cmbl_plan* plan, int mode, const void* block, const void* in, void* out, int Nb, void* stream);
 /* dot(a,b) per batch item (src/proj_lambert.jl:318-328): Map: Σ a·b; Fourier: Σ Re(conj(a) b) λ_rfft / (Ny Nx).
  * out_host[Nb] (double, HOST); synchronises the stream. */
 int cmbl_dot(cmbl_plan* plan, int basis, const void* a, const void* b, int Npol, int Nb, double* out_host, void* stream);
@@ -103,8 +107,11 @@ int cmbl_lenseflow_get_p(cmbl_flow* flow, int k, void* out_host);
 
 /* ---- CG Wiener filter: argmaxf_logpdf for a BaseDataSet with diagonal Cf, Cn, B, Mfourier and a pixel mask ---------
  * (src/maximization.jl:17-42, src/dataset.jl:76-80,129-132, src/numerical_algorithms.jl:73-134).
- * All diagonals are REAL device arrays of `Npol` half-planes in the harmonic basis of the field (Fourier for Npol=1,
- * EBFourier for Npol=2), shared by every batch item; mask_pix is a REAL Map-basis diagonal of Npol planes or NULL. */
+ * Npol = 1 | 2: all diagonals are REAL device arrays of `Npol` half-planes in the harmonic basis of the field (Fourier |
+ * EBFourier), shared by every batch item.  Npol = 3 (pol = :IP, IEBFourier): every operator is a BlockDiagIEB given as 4 REAL
+ * half-planes [SigmaTE[1,1], SigmaTE[2,1], SigmaTE[2,2], SigmaB] (see cmbl_blockdiag_ieb); the preconditioner is then the
+ * BlockDiagIEB pinv(Cf) + Bhat'Mhat'pinv(Cnhat)Mhat Bhat (src/specialops.jl:99-102) and `M \ r` = pinv(M)*r (:78).
+ * mask_pix is a REAL Map-basis diagonal of Npol planes or NULL. */
 typedef struct cmbl_dataset_desc {
     int Npol, Nb;
     const void* Cf;        /* signal covariance          */

@@ -165,6 +165,61 @@ def diag_ldiv(d: np.ndarray, f: np.ndarray) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# BlockDiagIEB (src/specialops.jl:61-118) with the 2×2 helpers of src/field_vectors.jl:64-84.
+# Stored as 4 real half-planes [ΣTE[1,1], ΣTE[2,1], ΣTE[2,2], ΣB] on axis 1: Cℓ_to_Cov(:IP) builds the
+# 2×2 block symmetric ([ΣTT ΣTE; ΣTE ΣEE], src/proj_lambert.jl:368-371) and sqrt/pinv/det read the
+# off-diagonal from [2,1] twice (`a, c, b, d = A[1,1], A[2,1], A[2,1], A[2,2]`).
+# ----------------------------------------------------------------------------------------------
+def block_from_diag(d3: np.ndarray) -> np.ndarray:
+    """DiagOp{IEBFourier} (3 planes) as a block with zero off-diagonal."""
+    return np.stack([d3[:, 0], np.zeros_like(d3[:, 0]), d3[:, 1], d3[:, 2]], axis=1)
+
+
+def block_mul(A: np.ndarray, F: np.ndarray) -> np.ndarray:
+    """L * f::IEBFourier (:79-82): (i,e) = ΣTE·(I,E), b = ΣB·B."""
+    out = np.empty(np.broadcast_shapes(A[:, :3].shape, F.shape), dtype=F.dtype)
+    out[:, 0] = A[:, 0] * F[:, 0] + A[:, 1] * F[:, 1]
+    out[:, 1] = A[:, 1] * F[:, 0] + A[:, 2] * F[:, 1]
+    out[:, 2] = A[:, 3] * F[:, 2]
+    return out
+
+
+def block_pinv(A: np.ndarray) -> np.ndarray:
+    """pinv(L) (:88) with pinv(::2×2) of src/field_vectors.jl:74-78: idet = pinv(ad − bc); [d·idet −b·idet; −c·idet a·idet]."""
+    a, c, d = A[:, 0], A[:, 1], A[:, 2]
+    idet = pinv_diag(a * d - c * c)
+    return np.stack([d * idet, -(c * idet), a * idet, pinv_diag(A[:, 3])], axis=1).astype(A.dtype)
+
+
+def block_sqrt(A: np.ndarray) -> np.ndarray:
+    """sqrt(L) (:87) with sqrt(::2×2) of src/field_vectors.jl:62-67: s = √(ad−bc), t = pinv(√(a+(d+2s)))."""
+    a, c, d = A[:, 0], A[:, 1], A[:, 2]
+    s = np.sqrt(a * d - c * c)
+    t = pinv_diag(np.sqrt(a + (d + 2 * s)))
+    return np.stack([t * (a + s), t * c, t * (d + s), np.sqrt(A[:, 3])], axis=1).astype(A.dtype)
+
+
+def block_hess_sandwich(X: np.ndarray, M: np.ndarray, Y: np.ndarray) -> np.ndarray:
+    """X'·M'·Y·M·X for BlockDiagIEBs (`*(La, Lb)` = 2×2 matrix product ⊕ product of the B parts, src/specialops.jl:101),
+    evaluated left to right with full (non-symmetric) 2×2 intermediates; the result is symmetric and is returned as the
+    4 planes [1,1], [2,1], [2,2], B."""
+    full = lambda A: (A[:, 0], A[:, 1], A[:, 1], A[:, 2], A[:, 3])                       # [a b; c d] ⊕ e
+    mm = lambda x, y: (x[0] * y[0] + x[1] * y[2], x[0] * y[1] + x[1] * y[3], x[2] * y[0] + x[3] * y[2], x[2] * y[1] + x[3] * y[3], x[4] * y[4])
+    x, m, y = full(X), full(M), full(Y)
+    h = mm(mm(mm(mm(x, m), y), m), x)
+    return np.stack([h[0], h[2], h[3], h[4]], axis=1).astype(X.dtype)
+
+
+def op_mul(pol: str, A: np.ndarray, F: np.ndarray) -> np.ndarray:
+    """Harmonic-basis operator times field: DiagOp for I / P, BlockDiagIEB (4 planes) for IP."""
+    return block_mul(A, F).astype(F.dtype) if pol == "IP" else A * F
+
+
+def op_pinv(pol: str, A: np.ndarray) -> np.ndarray:
+    return block_pinv(A) if pol == "IP" else pinv_diag(A)
+
+
+# ----------------------------------------------------------------------------------------------
 # dot / logdet / tr (src/proj_lambert.jl:318-353)
 # ----------------------------------------------------------------------------------------------
 def dot_map(a: np.ndarray, b: np.ndarray) -> np.ndarray:
@@ -399,7 +454,7 @@ class DataSet:
     (Fourier for I, EBFourier for P; arrays (1|Nb, Npol, Nx, Ny/2+1) real); the pixel part of M is
     a Map-basis diagonal (QUMap for P).  M = Mfourier * Mpix ; M̂ = Mfourier (:283-296)."""
     proj: ProjLambert
-    pol: str                      # "I" or "P"
+    pol: str                      # "I", "P" or "IP" (IP: every harmonic operator is a BlockDiagIEB of 4 planes)
     Cf: np.ndarray
     Cn: np.ndarray
     Cnhat: np.ndarray
@@ -412,14 +467,14 @@ class DataSet:
 
     @property
     def npol(self):
-        return 1 if self.pol == "I" else 2
+        return {"I": 1, "P": 2, "IP": 3}[self.pol]
 
 
 def to_lense_basis(ds_or_pol, proj, F):
     """Ł(f) for a harmonic-basis field: (EB→QU) then irfft2 (src/generic.jl:88-93)."""
     pol = ds_or_pol if isinstance(ds_or_pol, str) else ds_or_pol.pol
-    if pol == "P":
-        F = eb_to_qu(proj, F)
+    if pol != "I":
+        F = eb_to_qu(proj, F, 1 if pol == "IP" else 0)        # IQU: components 2:3 (src/proj_lambert.jl:284)
     return irfft2(F, proj.Ny)
 
 
@@ -427,8 +482,8 @@ def to_harmonic_basis(ds_or_pol, proj, f):
     """EBFourier(f::QUMap) / Fourier(f::Map)."""
     pol = ds_or_pol if isinstance(ds_or_pol, str) else ds_or_pol.pol
     F = rfft2(f)
-    if pol == "P":
-        F = qu_to_eb(proj, F)
+    if pol != "I":
+        F = qu_to_eb(proj, F, 1 if pol == "IP" else 0)        # :292
     return F
 
 
@@ -436,12 +491,12 @@ def apply_M(ds: DataSet, F):
     """M*f = Mfourier * (Mpix * f)."""
     if ds.Mpix is not None:
         F = to_harmonic_basis(ds, ds.proj, ds.Mpix * to_lense_basis(ds, ds.proj, F))
-    return ds.Mf * F
+    return op_mul(ds.pol, ds.Mf, F)
 
 
 def apply_MH(ds: DataSet, F):
     """M'*f = Mpix' * (Mfourier' * f); result left in the Map (QUMap) basis when Mpix is present."""
-    F = ds.Mf * F
+    F = op_mul(ds.pol, ds.Mf, F)
     if ds.Mpix is not None:
         return ds.Mpix * to_lense_basis(ds, ds.proj, F), True
     return F, False
@@ -455,18 +510,19 @@ def gradientf_logpdf(ds: DataSet, f_harm: np.ndarray, d: np.ndarray) -> np.ndarr
     (EB) basis so the caller sees one basis throughout — a unitary change, not a numerical one."""
     proj = ds.proj
     ft = lenseflow_apply(ds.L, OP_L, to_lense_basis(ds, proj, f_harm))             # Lϕ*f   (Map)
-    Bf = ds.B * to_harmonic_basis(ds, proj, ft)                                   # B*f̃
+    pol0 = 1 if ds.pol == "IP" else 0
+    Bf = op_mul(ds.pol, ds.B, to_harmonic_basis(ds, proj, ft))                    # B*f̃
     res = d - apply_M(ds, Bf)
-    x = pinv_diag(ds.Cn) * res
+    x = op_mul(ds.pol, op_pinv(ds.pol, ds.Cn), res)
     x, is_map = apply_MH(ds, x)
     if is_map:
         x = to_harmonic_basis(ds, proj, x)
-    x = ds.B * x                                                                  # B' (real diag)
-    xq = eb_to_qu(proj, x) if ds.pol == "P" else x                                # Ð(·) → QUFourier
+    x = op_mul(ds.pol, ds.B, x)                                                   # B' (real, symmetric)
+    xq = eb_to_qu(proj, x, pol0) if ds.pol != "I" else x                          # Ð(·) → (I)QUFourier
     y = lenseflow_apply(ds.L, OP_LH, xq.astype(proj.cT))                          # Lϕ'*  (QU/Fourier)
-    if ds.pol == "P":
-        y = qu_to_eb(proj, y)
-    return (y - pinv_diag(ds.Cf) * f_harm).astype(proj.cT)
+    if ds.pol != "I":
+        y = qu_to_eb(proj, y, pol0)
+    return (y - op_mul(ds.pol, op_pinv(ds.pol, ds.Cf), f_harm)).astype(proj.cT)
 
 
 def mix(ds: DataSet, proj: ProjLambert, pol: str, f_harm: np.ndarray, phi_four: np.ndarray, D=None, G=None, nsteps: int = 7):
@@ -486,18 +542,25 @@ def unmix(ds: DataSet, proj: ProjLambert, pol: str, f_mixed_map: np.ndarray, phi
 
 def hess_preconditioner(ds: DataSet) -> np.ndarray:
     """Hessian_logpdf_preconditioner(:f) (src/dataset.jl:129-132): pinv(Cf) + B̂'M̂'pinv(Cn̂)M̂B̂."""
+    if ds.pol == "IP":       # BlockDiagIEB sums / products (src/specialops.jl:101-102)
+        return (block_pinv(ds.Cf) + block_hess_sandwich(ds.Bhat, ds.Mf, block_pinv(ds.Cnhat))).astype(ds.proj.T)
     return (pinv_diag(ds.Cf) + ds.Bhat * ds.Mf * pinv_diag(ds.Cnhat) * ds.Mf * ds.Bhat).astype(ds.proj.T)
 
 
-def conjugate_gradient(Mdiag, A, dot, b, x0, nsteps: int, tol: float):
+def conjugate_gradient(Mdiag, A, dot, b, x0, nsteps: int, tol: float, pol: str = "I"):
     """conjugate_gradient (src/numerical_algorithms.jl:73-134), exact update order; `Mdiag` is the
     diagonal preconditioner (M \\ r = nan2zero(r ./ diag)); per-batch scalars broadcast over axis 0
     (BatchedReal, src/batching.jl:9-45).  Returns (bestx, history[(i, res)])."""
     def bc(s, like):
         return np.asarray(s, dtype=like.real.dtype).reshape((-1,) + (1,) * (like.ndim - 1))
+    if pol == "IP":          # M \\ r = pinv(M) * IEBFourier(r) (src/specialops.jl:78)
+        Minv = block_pinv(Mdiag)
+        ldiv = lambda M_, r_: block_mul(Minv, r_).astype(r_.dtype)
+    else:
+        ldiv = diag_ldiv
     x = x0
     r = b - A(x)
-    z = diag_ldiv(Mdiag, r)
+    z = ldiv(Mdiag, r)
     p = z
     res = dot(r, z)
     assert not np.any(np.isnan(res))
@@ -508,7 +571,7 @@ def conjugate_gradient(Mdiag, A, dot, b, x0, nsteps: int, tol: float):
         alpha = res / dot(p, Ap)
         x = (x + bc(alpha, x) * p).astype(x.dtype)
         r = (r - bc(alpha, r) * Ap).astype(r.dtype)
-        z = diag_ldiv(Mdiag, r)
+        z = ldiv(Mdiag, r)
         res2 = dot(r, z)
         p = (z + bc(res2 / res, p) * p).astype(p.dtype)
         res = res2
@@ -531,7 +594,7 @@ def argmaxf_logpdf(ds: DataSet, d=None, fstart=None, nsteps: int = 500, tol: flo
         b = b + a0
     A = lambda f: gradientf_logpdf(ds, f, np.zeros_like(d)) - a0
     dot = lambda u, v: dot_fourier(proj, u, v)
-    return conjugate_gradient(hess_preconditioner(ds), A, dot, b, zero_f if fstart is None else fstart, nsteps, tol)
+    return conjugate_gradient(hess_preconditioner(ds), A, dot, b, zero_f if fstart is None else fstart, nsteps, tol, pol=ds.pol)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -566,28 +629,36 @@ def cosine_border_mask(proj: ProjLambert, border_deg: float = 1.0) -> np.ndarray
 def make_dataset(Ny, Nx, theta_pix, pol="I", T=np.float64, nb=1, seed=0, nsteps=7, mask=True,
                  muK_arcmin_T=3.0, lknee=100.0, aknee=3.0, beam_fwhm=0.0, lowpass=3000, cls=None,
                  mask_border_deg=1.0):
-    """load_sim restricted to pol ∈ {I,P}; returns dict(f, phi, d, ds, proj) with harmonic-basis fields."""
+    """load_sim (src/dataset.jl:186-338) for pol ∈ {I, P, IP}; returns dict(f, phi, d, ds, proj) with harmonic-basis
+    fields.  For IP every harmonic operator is a BlockDiagIEB (4 planes [TT, TE, EE, BB]); the TE entry of the noise, mask
+    and beam blocks is zero (:279,:299, src/cls.jl:298)."""
     cls = cls or load_fiducial_cls()
     proj = ProjLambert(Ny, Nx, theta_pix, T)
     ell = cls["ell"].astype(np.float64)
     rng = np.random.default_rng(seed)
-    keys = ("ut_TT",) if pol == "I" else ("ut_EE", "ut_BB")
-    Cf = np.stack([cl_to_cov(proj, ell, cls[k]) for k in keys])[None]
-    Cphi = cl_to_cov(proj, ell, cls["pp"])[None, None]
-    Cn = np.stack([cl_to_cov(proj, ell, noise_cls(ell, muK_arcmin_T, lknee, aknee, pol=(pol == "P"))) for _ in keys])[None]
+    keys = {"I": ("TT",), "P": ("EE", "BB"), "IP": ("TT", "TE", "EE", "BB")}[pol]
+    npol = {"I": 1, "P": 2, "IP": 3}[pol]
     lb, wl = lowpass_wl(lowpass)
-    Mf = np.stack([cl_to_cov(proj, lb, wl, units=1) for _ in keys])[None]
-    B = np.stack([cl_to_cov(proj, ell, np.sqrt(beam_cls(ell, beam_fwhm)), units=1) for _ in keys])[None]
+    zero = lambda: np.zeros(proj.fourier_shape, dtype=proj.T)
+    Cf = np.stack([cl_to_cov(proj, ell, cls["ut_" + k]) for k in keys])[None]
+    Cphi = cl_to_cov(proj, ell, cls["pp"])[None, None]
+    Cn = np.stack([zero() if k == "TE" else cl_to_cov(proj, ell, noise_cls(ell, muK_arcmin_T, lknee, aknee, pol=(k != "TT"))) for k in keys])[None]
+    Mf = np.stack([zero() if k == "TE" else cl_to_cov(proj, lb, wl, units=1) for k in keys])[None]
+    B = np.stack([zero() if k == "TE" else cl_to_cov(proj, ell, np.sqrt(beam_cls(ell, beam_fwhm)), units=1) for k in keys])[None]
     Mpix = None
     if mask:
         m = cosine_border_mask(proj, mask_border_deg)
-        Mpix = np.broadcast_to(m, (1, len(keys)) + m.shape).copy()
-    f = simulate_diag(proj, Cf, rng, nb)
+        Mpix = np.broadcast_to(m, (1, npol) + m.shape).copy()
+    if pol == "IP":          # simulate(rng, L::BlockDiagIEB) = sqrt(L) * randn (src/specialops.jl:94)
+        sim = lambda C: block_mul(block_sqrt(C), rfft2(rng.standard_normal((nb, 3) + proj.map_shape).astype(proj.T))).astype(proj.cT)
+    else:
+        sim = lambda C: simulate_diag(proj, C, rng, nb)
+    f = sim(Cf)
     phi = simulate_diag(proj, Cphi, rng, nb)
-    n = simulate_diag(proj, Cn, rng, nb)
+    n = sim(Cn)
     L = precompute(proj, phi, nsteps, phi_is_fourier=True)
     ds = DataSet(proj, pol, Cf, Cn, Cn.copy(), B, B.copy(), Mf, Mpix, None, L)
     ft = lenseflow_apply(L, OP_L, to_lense_basis(pol, proj, f))
-    d = (apply_M(ds, B * to_harmonic_basis(pol, proj, ft)) + n).astype(proj.cT)
+    d = (apply_M(ds, op_mul(pol, B, to_harmonic_basis(pol, proj, ft))) + n).astype(proj.cT)
     ds.d = d
     return dict(f=f, phi=phi, d=d, ds=ds, proj=proj, Cphi=Cphi)

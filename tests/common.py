@@ -24,11 +24,14 @@ def make_problem(pkg, Ny, Nx, pol, dtype, nb, nbphi=None, nsteps=7, mask=True, s
     sim["ds"].L = Lo
     if nbphi != nb:       # data must be consistent with the ϕ actually used
         ft = O.lenseflow_apply(Lo, O.OP_L, O.to_lense_basis(pol, sim["proj"], sim["f"]))
-        sim["d"] = sim["ds"].d = (O.apply_M(sim["ds"], sim["ds"].B * O.to_harmonic_basis(pol, sim["proj"], ft))).astype(sim["proj"].cT)
-    harm = "Fourier" if pol == "I" else "EBFourier"
-    lense = "Map" if pol == "I" else "QUMap"
+        sim["d"] = sim["ds"].d = (O.apply_M(sim["ds"], O.op_mul(pol, sim["ds"].B, O.to_harmonic_basis(pol, sim["proj"], ft)))).astype(sim["proj"].cT)
+    harm = {"I": "Fourier", "P": "EBFourier", "IP": "IEBFourier"}[pol]
+    lense = {"I": "Map", "P": "QUMap", "IP": "IQUMap"}[pol]
     F = lambda a, basis: pkg.Field(basis, torch.from_numpy(np.ascontiguousarray(a)), proj)
-    D = lambda a, basis=harm: pkg.DiagOp(F(a, basis))
+    def D(a, basis=harm):
+        if basis == "IEBFourier":            # BlockDiagIEB from its four half-planes [TT, TE, EE, BB]
+            return pkg.BlockDiagIEB(*(a[0, i] for i in range(4)), proj=proj)
+        return pkg.DiagOp(F(a, basis))
     dso = sim["ds"]
     ds = pkg.BaseDataSet(F(sim["d"], harm), D(dso.Cf), D(dso.Cn), D(dso.B), D(dso.Mf),
                          D(dso.Mpix, lense) if dso.Mpix is not None else None, nsteps=nsteps)

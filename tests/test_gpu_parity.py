@@ -38,7 +38,7 @@ def test_rfft2_irfft2(cuda_pkg, Ny, Nx, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(8, 8, "I", 1, 1), (4, 8, "P", 2, 2), (128, 128, "I", 1, 1), (64, 128, "P", 3, 3),
-                                                 (128, 64, "P", 2, 1), (256, 256, "I", 1, 1)])
+                                                 (128, 64, "P", 2, 1), (256, 256, "I", 1, 1), (64, 32, "IP", 2, 2)])
 def test_lenseflow_all_ops(cuda_pkg, Ny, Nx, pol, nb, nbphi, dtype):
     """Config 0 (Nside=256 T Float64 LenseFlow(ϕ)*f) and the reference's test sizes (runtests.jl:53), all four ops."""
     pkg = cuda_pkg
@@ -49,7 +49,7 @@ def test_lenseflow_all_ops(cuda_pkg, Ny, Nx, pol, nb, nbphi, dtype):
     fm = O.to_lense_basis(pol, oproj, pr["sim"]["f"])
     F0 = O.rfft2(fm)
     Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
-    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, "Fourier" if pol == "I" else "QUFourier")
+    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, {"I": "Fourier", "P": "QUFourier", "IP": "IQUFourier"}[pol])
     tol = TOL[dtype]
     assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
     assert relerr(L.ldiv(fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LINV, fm)) < tol
@@ -59,7 +59,7 @@ def test_lenseflow_all_ops(cuda_pkg, Ny, Nx, pol, nb, nbphi, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi,path", [(1024, 512, "P", 2, 2, 3), (512, 1024, "I", 3, 1, 3), (256, 512, "P", 5, 5, 3),
-                                                      (1024, 1024, "I", 1, 1, 3), (64, 1024, "I", 2, 2, 0), (1024, 32, "P", 2, 1, 0), (256, 256, "P", 2, 2, 3)])
+                                                      (1024, 1024, "I", 1, 1, 3), (64, 1024, "I", 2, 2, 0), (1024, 32, "P", 2, 1, 0), (256, 256, "P", 2, 2, 3), (512, 512, "IP", 2, 2, 3)])
 def test_lenseflow_fast_path(cuda_pkg, Ny, Nx, pol, nb, nbphi, path, dtype):
     """The persistent cp.async stage kernels (csrc/flow_fast.cuh) on the device, all four ops, against the oracle."""
     pkg = cuda_pkg
@@ -70,7 +70,7 @@ def test_lenseflow_fast_path(cuda_pkg, Ny, Nx, pol, nb, nbphi, path, dtype):
     fm = O.to_lense_basis(pol, oproj, pr["sim"]["f"])
     F0 = O.rfft2(fm)
     Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
-    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, "Fourier" if pol == "I" else "QUFourier")
+    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, {"I": "Fourier", "P": "QUFourier", "IP": "IQUFourier"}[pol])
     assert pkg.load().cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == path
     tol = TOL[dtype]
     for _ in range(2):                                   # twice: persistent-kernel state (tickets, buffers) must reset cleanly
@@ -143,7 +143,22 @@ def test_golden_fixture(cuda_pkg):
     assert relerr(L.ldiv(f).cpu_numpy(), z["Linv_f"]) < 1e-11
 
 
-@pytest.mark.parametrize("dtype,pol,mask", [("f64", "I", False), ("f64", "P", True), ("f32", "P", True)])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_blockdiag_ieb(cuda_pkg, dtype):
+    """BlockDiagIEB * f, \\ f, sqrt(L) * f (src/specialops.jl:61-118) and IEB<->IQU on the device against the oracle."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, 128, 64, "IP", dtype, nb=3, nsteps=2, mask=False, device=DEV)
+    f, fo, oproj, Cf, Cfo = pr["f"], pr["sim"]["f"], pr["oproj"], pr["ds"].Cf, pr["dso"].Cf
+    tol = TOL[dtype]
+    assert relerr((Cf * f).cpu_numpy(), O.block_mul(Cfo, fo)) < tol
+    assert relerr(Cf.ldiv(f).cpu_numpy(), O.block_mul(O.block_pinv(Cfo), fo)) < tol
+    assert relerr(Cf.sqrt_mul(f).cpu_numpy(), O.block_mul(O.block_sqrt(Cfo), fo)) < tol
+    assert relerr(pkg.IQUFourier(f).cpu_numpy(), O.eb_to_qu(oproj, fo, 1)) < tol
+    assert relerr(pkg.IQUMap(f).cpu_numpy(), O.to_lense_basis("IP", oproj, fo)) < tol
+    assert relerr(pkg.IEBFourier(pkg.IQUMap(f)).cpu_numpy(), fo) < 10 * tol
+
+
+@pytest.mark.parametrize("dtype,pol,mask", [("f64", "I", False), ("f64", "P", True), ("f32", "P", True), ("f64", "IP", True), ("f32", "IP", False)])
 def test_gradientf_and_cg(cuda_pkg, dtype, pol, mask):
     pkg = cuda_pkg
     pr = make_problem(pkg, 64, 64, pol, dtype, nb=2, nsteps=7, mask=mask, seed=7, theta=3.0, device=DEV)

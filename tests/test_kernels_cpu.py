@@ -89,7 +89,7 @@ def test_qu_eb_diag_dot(pkg, emu, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(8, 8, "I", 1, 1), (4, 8, "I", 2, 2), (8, 4, "P", 1, 1), (32, 16, "I", 1, 1),
-                                                 (16, 64, "P", 2, 2), (64, 64, "P", 3, 1), (128, 64, "I", 2, 1)])
+                                                 (16, 64, "P", 2, 2), (64, 64, "P", 3, 1), (128, 64, "I", 2, 1), (16, 32, "IP", 2, 2), (32, 32, "IP", 2, 1)])
 def test_lenseflow_all_ops(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
     pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=4, mask=False, seed=3, lib=emu)
     L = pkg.LenseFlow(pr["phi"], 4)
@@ -98,7 +98,7 @@ def test_lenseflow_all_ops(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
     fm = O.to_lense_basis(pol, oproj, pr["sim"]["f"])
     F0 = O.rfft2(fm)
     Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
-    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, "Fourier" if pol == "I" else "QUFourier")
+    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, {"I": "Fourier", "P": "QUFourier", "IP": "IQUFourier"}[pol])
     tol = 1e-11 if dtype == "f64" else 2e-5                 # SURVEY §8c tolerances
     assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
     assert relerr(L.ldiv(fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LINV, fm)) < tol
@@ -108,7 +108,7 @@ def test_lenseflow_all_ops(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi,path", [(256, 256, "P", 2, 2, 3), (512, 256, "I", 1, 1, 3), (256, 1024, "I", 2, 1, 3),
-                                                      (1024, 512, "I", 1, 1, 3), (64, 256, "I", 1, 1, 0), (256, 32, "P", 1, 1, 0), (512, 64, "I", 1, 1, 0), (128, 64, "P", 1, 1, 0)])
+                                                      (1024, 512, "I", 1, 1, 3), (256, 256, "IP", 2, 2, 3), (64, 256, "I", 1, 1, 0), (256, 32, "P", 1, 1, 0), (512, 64, "I", 1, 1, 0), (128, 64, "P", 1, 1, 0)])
 def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
     """The persistent cp.async kernels of csrc/flow_fast.cuh (lengths 256/512/1024), all four ops, against the oracle;
     `path` = 3 when the pair of fast kernels (row-grouped internal layout) must have been used, 0 for the generic pair."""
@@ -119,7 +119,7 @@ def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
     fm = O.to_lense_basis(pol, oproj, pr["sim"]["f"])
     F0 = O.rfft2(fm)
     Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
-    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, "Fourier" if pol == "I" else "QUFourier")
+    fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, {"I": "Fourier", "P": "QUFourier", "IP": "IQUFourier"}[pol])
     assert emu.cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == path
     tol = 1e-11 if dtype == "f64" else 2e-5
     assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
@@ -168,7 +168,30 @@ def test_lenseflow_pullback(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
     assert relerr(δf.cpu_numpy(), gf) < tol and relerr(δϕ.cpu_numpy(), gphi) < tol
 
 
-@pytest.mark.parametrize("dtype,pol,mask", [("f64", "I", False), ("f64", "P", True), ("f64", "I", True), ("f32", "P", True)])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_blockdiag_ieb(pkg, emu, dtype):
+    """BlockDiagIEB * f, \\ f, sqrt (src/specialops.jl:61-118, src/field_vectors.jl:62-78) and IEB<->IQU (src/proj_lambert.jl:284,292)."""
+    pr = make_problem(pkg, 32, 16, "IP", dtype, nb=2, lib=emu)
+    f, fo, oproj, Cf, Cfo = pr["f"], pr["sim"]["f"], pr["oproj"], pr["ds"].Cf, pr["dso"].Cf
+    tol = TOL[dtype]
+    assert relerr((Cf * f).cpu_numpy(), O.block_mul(Cfo, fo)) < tol
+    assert relerr(Cf.ldiv(f).cpu_numpy(), O.block_mul(O.block_pinv(Cfo), fo)) < tol
+    assert relerr(Cf.sqrt_mul(f).cpu_numpy(), O.block_mul(O.block_sqrt(Cfo), fo)) < tol
+    assert np.all(np.isfinite(Cf.ldiv(f).cpu_numpy()))                            # pinv: the ℓ = 0 mode maps to 0
+    # sqrt(L)·sqrt(L) = L and pinv(L)·L = 1 where L is invertible (runtests.jl "Algebra" identities for BlockDiagIEB)
+    assert relerr(Cf.sqrt_mul(Cf.sqrt_mul(f)).cpu_numpy(), O.block_mul(Cfo, fo)) < 20 * tol
+    ok = (Cfo[0, 0] * Cfo[0, 2] - Cfo[0, 1] ** 2 != 0) & (Cfo[0, 3] != 0)
+    assert relerr(Cf.ldiv(Cf * f).cpu_numpy() * ok, fo * ok) < 1e3 * tol
+    iqu = pkg.IQUFourier(f)
+    assert relerr(iqu.cpu_numpy(), O.eb_to_qu(oproj, fo, 1)) < tol
+    assert np.array_equal(iqu.cpu_numpy()[:, 0], fo[:, 0])                        # I passes through untouched
+    assert relerr(pkg.IEBFourier(iqu).cpu_numpy(), fo) < 10 * tol
+    assert relerr(pkg.IQUMap(f).cpu_numpy(), O.to_lense_basis("IP", oproj, fo)) < tol
+    assert np.allclose(pkg.dot(f, f), O.dot_fourier(oproj, fo, fo), rtol=1e-12 if dtype == "f64" else 1e-5)
+
+
+@pytest.mark.parametrize("dtype,pol,mask", [("f64", "I", False), ("f64", "P", True), ("f64", "I", True), ("f32", "P", True),
+                                            ("f64", "IP", True), ("f64", "IP", False), ("f32", "IP", True)])
 def test_gradientf_and_cg(pkg, emu, dtype, pol, mask):
     pr = make_problem(pkg, 32, 32, pol, dtype, nb=2, nsteps=3, mask=mask, seed=7, theta=3.0, lib=emu)
     ds, dso, f = pr["ds"], pr["dso"], pr["f"]
