@@ -39,37 +39,70 @@ def algorithmic_bytes(s):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML poll every ~2 ms between begin()
+    and end() (a 10-step timed region lasts < 100 ms — too short for `nvidia-smi -lms`, whose first sample arrives after
+    ~1 s); falls back to one `nvidia-smi` query issued while the GPU is kept busy when NVML cannot be loaded."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+        self.index, self.sm, self.bits, self.mx, self.power = index, [], 0, None, []
+        self._run, self._thr, self.nv, self.h = False, None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve by PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    hi = nv.nvmlDeviceGetHandleByIndex(i)
+                    if nv.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        self.h = hi
+                        break
+            self.mx = int(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while self._run:
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v == "Active":
-                    reasons.add(name)
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+    def begin(self):
+        if self.nv is not None:
+            self._run = True
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
+
+    def end(self):
+        if self.nv is not None:
+            self._run = False
+            self._thr.join()
+
+    def smi_fallback(self):
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
+            v = [x.strip() for x in r.stdout.strip().splitlines()[0].split(",")]
+            reasons = [n for n, a in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), v[2:6]) if a == "Active"]
+            return {"sm_mhz": int(v[0]), "sm_max_mhz": int(v[1]), "reasons": reasons, "samples": 1, "source": "nvidia-smi (one query under load)"}
+        except Exception as e:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock query unavailable: {e}"], "samples": 0}
+
+    def summary(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b),
+                "samples": len(sm), "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(self.power) if self.power else None,
+                "source": "NVML poll (2 ms) inside the timed region"}
 
 
 def measured_peak():
@@ -183,17 +216,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = lib.launch_count()
+        if sampler:
+            sampler.begin()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        if sampler:
+            sampler.end()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -201,11 +238,19 @@ def main():
             ms = float(t.item())
         return ms / steps, (lib.launch_count() - n0)
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, launches = timed(step_device, args.steps, max(args.warmup, 3), sampler if (sampler and sampler.nv) else None)
+    clocks = None
     if rank == 0:
-        sampler.start()
-    ms_step, launches = timed(step_device, args.steps, max(args.warmup, 3))
-    clocks = sampler.stop() if rank == 0 else None
+        if sampler.nv is not None and sampler.sm:
+            clocks = sampler.summary()
+        else:                                            # keep the GPU busy with the same step while nvidia-smi answers
+            import concurrent.futures as cf
+            with cf.ThreadPoolExecutor(1) as ex:
+                fut = ex.submit(sampler.smi_fallback)
+                while not fut.done():
+                    step_device(); torch.cuda.synchronize()
+                clocks = fut.result()
 
     # ---- end-to-end: HOST buffers through the C ABI, copies inside the timed region ---------------------------------
     hin = torch.empty(fmap.arr.shape, dtype=tT).pin_memory(); hin.copy_(fmap.arr)

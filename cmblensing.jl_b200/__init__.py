@@ -28,6 +28,7 @@ __all__ = [
     "LenseBasis", "DerivBasis", "HarmonicBasis",
     "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "BlockDiagIEB", "dot", "BaseDataSet", "gradientf_logpdf",
     "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
+    "Cℓ_to_2D", "Cℓ_to_Cov", "Cl_to_Cov", "simulate", "sample_f", "convert",
     "CmblError", "load",
 ]
 
@@ -333,6 +334,38 @@ class BlockDiagIEB:
     def sqrt_mul(self, f): return self._apply(f, 2)
 
 
+# -- covariance operators from power spectra (setup; src/proj_lambert.jl:173-175,361-371, src/numerical_algorithms.jl:148-177) ---
+def Cℓ_to_2D(proj: ProjLambert, ℓ, Cℓ) -> np.ndarray:
+    """nan2zero.(Cℓ.(ℓmag)) with the reference's LinearInterpolation (NaN outside the table, so ℓ = 0 and ℓ > ℓmax map to 0)."""
+    ℓ, Cℓ = np.asarray(ℓ, dtype=np.float64), np.asarray(Cℓ, dtype=np.float64)
+    x = proj.ℓmag.astype(np.float64)
+    i = np.clip(np.searchsorted(ℓ, x, side="left") - 1, 0, len(ℓ) - 2)
+    m = np.diff(Cℓ) / np.diff(ℓ)
+    y = Cℓ[i] + m[i] * (x - ℓ[i])
+    y = np.where((x < ℓ[0]) | (x > ℓ[-1]) | ~np.isfinite(y), 0.0, y)
+    return y.astype(_NP_REAL[proj.dtype_code])
+
+
+def Cℓ_to_Cov(pol: str, proj: ProjLambert, ℓ, *Cℓs, units=None):
+    """Cℓ_to_Cov(:I | :P | :IP, proj, Cℓ...; units=Ωpix): Diagonal(Fourier), Diagonal(EBFourier) from (EE, BB), or
+    BlockDiagIEB from (TT, EE, BB, TE) — argument order as the reference (src/proj_lambert.jl:361-371)."""
+    units = proj.Ωpix if units is None else units
+    npT = _NP_REAL[proj.dtype_code]
+    planes = [(Cℓ_to_2D(proj, ℓ, c) / npT(units)).astype(npT) for c in Cℓs]
+    want = {"I": 1, "P": 2, "IP": 4}.get(pol)
+    if want is None:
+        raise CmblError("`pol` should be one of I, P, or IP")                     # src/dataset.jl:263
+    if len(planes) != want:
+        raise CmblError(f"Cℓ_to_Cov({pol}) takes {want} spectra")
+    if pol == "IP":
+        TT, EE, BB, TE = planes
+        return BlockDiagIEB(TT, TE, EE, BB, proj=proj)
+    return DiagOp(Field("Fourier" if pol == "I" else "EBFourier", torch.from_numpy(np.stack(planes)[None]), proj))
+
+
+Cl_to_Cov = Cℓ_to_Cov
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # LenseFlow (src/lenseflow.jl:19-60, src/flowops.jl:11-14)
 # ------------------------------------------------------------------------------------------------------------------
@@ -535,3 +568,45 @@ def argmaxf_logpdf(ds: BaseDataSet, ϕ: Field, fstart: Field | None = None, offs
 
 
 argmaxf_lnP = argmaxf_logpdf          # the name BASELINE.json uses (pre-0.10 spelling)
+
+
+def _sqrt_mul(op, w: Field) -> Field:
+    """sqrt(C) * w for a DiagOp or BlockDiagIEB covariance (simulate, src/specialops.jl:6,94)."""
+    if isinstance(op, BlockDiagIEB):
+        return op.sqrt_mul(w)
+    return DiagOp(Field(op.diag.basis, torch.sqrt(op._real).to(op.diag.arr.dtype), op.diag.proj)) * w
+
+
+def _apply_MB(ds: BaseDataSet, ft: Field) -> Field:
+    """M * (B * f̃) with M = Mfourier * Mpix (src/dataset.jl:60-67,283-290)."""
+    x = ds.B * HarmonicBasis(ft)
+    if ds.Mpix is not None:
+        x = ds.Mpix * LenseBasis(x)
+    return ds.Mf * HarmonicBasis(x)
+
+
+def simulate(ds: BaseDataSet, ϕ: Field, white_f: Field | None = None, white_n: Field | None = None, generator=None):
+    """simulate(rng, ds; ϕ) of the BaseDataSet forward model (src/dataset.jl:60-67): f ~ N(0, Cf), d ~ N(M B L(ϕ) f, Cn).
+    The unit white-noise maps may be passed in (LenseBasis fields) so that a CPU restatement can be fed the same draws."""
+    d0 = ds.d
+    p = d0.proj
+    lense = ("Map", "QUMap", "IQUMap")[d0.Npol - 1]
+    draw = lambda: Field(lense, torch.randn(p.map_shape(d0.Npol, d0.Nbatch), dtype=p.T, device=p.device, generator=generator), p)
+    wf = white_f if white_f is not None else draw()
+    wn = white_n if white_n is not None else draw()
+    f = _sqrt_mul(ds.Cf, HarmonicBasis(wf))
+    n = _sqrt_mul(ds.Cn, HarmonicBasis(wn))
+    L = ds.L(ϕ, ds.nsteps) if isinstance(ds.L, type) else ds.L
+    f̃ = L * f
+    d = _apply_MB(ds, f̃) + n
+    return dict(f=f, f̃=f̃, ϕ=ϕ, d=d)
+
+
+def sample_f(ds: BaseDataSet, ϕ: Field, white_f: Field | None = None, white_n: Field | None = None, generator=None,
+             conjgrad_kwargs=dict(tol=1e-1, nsteps=500), fstart: Field | None = None):
+    """sample_f(rng, ds, (;ϕ)) (src/maximization.jl:56-62): a posterior sample of f at fixed ϕ,
+    sim.f + argmaxf_logpdf(ds, Ω, d − sim.d; offset=true).  Returns (f, history)."""
+    sim = simulate(ds, ϕ, white_f, white_n, generator)
+    ds2 = BaseDataSet(ds.d - sim["d"], ds.Cf, ds.Cn, ds.B, ds.Mf, ds.Mpix, ds.Cnhat, ds.Bhat, L=ds.L, nsteps=ds.nsteps, D=ds.D, G=ds.G)
+    Δf, hist = argmaxf_logpdf(ds2, ϕ, fstart=fstart, offset=True, conjgrad_kwargs=conjgrad_kwargs)
+    return sim["f"] + Δf, hist

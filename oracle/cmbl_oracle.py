@@ -597,6 +597,28 @@ def argmaxf_logpdf(ds: DataSet, d=None, fstart=None, nsteps: int = 500, tol: flo
     return conjugate_gradient(hess_preconditioner(ds), A, dot, b, zero_f if fstart is None else fstart, nsteps, tol, pol=ds.pol)
 
 
+def op_sqrt_mul(pol: str, C: np.ndarray, F: np.ndarray) -> np.ndarray:
+    """simulate(rng, L) = sqrt(L) * randn (src/specialops.jl:6,94) applied to the transform F of a unit white map."""
+    return (block_mul(block_sqrt(C), F) if pol == "IP" else np.sqrt(C) * F).astype(F.dtype)
+
+
+def simulate_ds(ds: DataSet, white_f: np.ndarray, white_n: np.ndarray):
+    """simulate(rng, ds; ϕ) (src/dataset.jl:60-67) with the unit white-noise maps given explicitly."""
+    proj = ds.proj
+    f = op_sqrt_mul(ds.pol, ds.Cf, to_harmonic_basis(ds, proj, white_f))
+    n = op_sqrt_mul(ds.pol, ds.Cn, to_harmonic_basis(ds, proj, white_n))
+    ft = lenseflow_apply(ds.L, OP_L, to_lense_basis(ds, proj, f))
+    d = (apply_M(ds, op_mul(ds.pol, ds.B, to_harmonic_basis(ds, proj, ft))) + n).astype(proj.cT)
+    return dict(f=f, ft=ft, d=d)
+
+
+def sample_f(ds: DataSet, white_f: np.ndarray, white_n: np.ndarray, nsteps: int = 500, tol: float = 1e-1):
+    """sample_f (src/maximization.jl:56-62): sim.f + argmaxf_logpdf(ds, Ω, d − sim.d; offset=true)."""
+    sim = simulate_ds(ds, white_f, white_n)
+    df, hist = argmaxf_logpdf(ds, d=(ds.d - sim["d"]).astype(ds.proj.cT), nsteps=nsteps, tol=tol, offset=True)
+    return (sim["f"] + df).astype(ds.proj.cT), hist
+
+
 # ----------------------------------------------------------------------------------------------
 # Synthetic flat-sky inputs (harness; mirrors load_sim defaults, src/dataset.jl:186-338)
 # ----------------------------------------------------------------------------------------------

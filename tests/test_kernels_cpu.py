@@ -228,6 +228,24 @@ def test_mix_unmix(pkg, emu, pol):
     assert relerr(pkg.HarmonicBasis(f2).cpu_numpy(), pr["sim"]["f"]) < 0.3           # coarse grid: L\\(L f) only approximately f (Nyquist modes)
 
 
+@pytest.mark.parametrize("pol", ["P", "IP"])
+def test_sample_f_and_cl_to_cov(pkg, emu, pol):
+    """sample_f (src/maximization.jl:56-62) fed the same white-noise draws as the oracle; Cℓ_to_Cov (src/proj_lambert.jl:361-371)."""
+    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=3, mask=True, seed=5, theta=3.0, lib=emu)
+    ds, dso, oproj, proj = pr["ds"], pr["dso"], pr["oproj"], pr["proj"]
+    rng = np.random.default_rng(3)
+    wf = rng.standard_normal((2, dso.npol) + oproj.map_shape); wn = rng.standard_normal((2, dso.npol) + oproj.map_shape)
+    fs, hist = pkg.sample_f(ds, pr["phi"], pr["F"](wf, pr["lense"]), pr["F"](wn, pr["lense"]), conjgrad_kwargs=dict(tol=0.0, nsteps=6))
+    fo, histo = O.sample_f(dso, wf, wn, nsteps=6, tol=0.0)
+    assert len(hist) == len(histo) and relerr(fs.cpu_numpy(), fo) < 1e-9
+    cls = O.load_fiducial_cls(); ell = cls["ell"]
+    keys = ("ut_EE", "ut_BB") if pol == "P" else ("ut_TT", "ut_EE", "ut_BB", "ut_TE")
+    C = pkg.Cℓ_to_Cov(pol, proj, ell, *(cls[k] for k in keys))
+    assert relerr(C._real.numpy(), dso.Cf) < 1e-14                              # TE sits in plane 2 of the block
+    with pytest.raises(pkg.CmblError):
+        pkg.Cℓ_to_Cov("Q", proj, ell, cls["ut_TT"])
+
+
 def test_cg_stops_on_tol_like_reference(pkg, emu):
     pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=emu)
     _, h0 = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=0.0)

