@@ -50,6 +50,32 @@ int cmbl_lenseflow_apply(cmbl_flow* flow, int op, const void* in, void* out, voi
     CMBL_API_END
 }
 
+#ifndef CMBL_EMU
+namespace {
+// copy streams / events of the pipelined host path (per host thread, created on first use)
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_fin = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    void ensure(int n) {
+        if (!s_in) {
+            CMBL_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+            CMBL_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+            CMBL_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+            CMBL_CUDA(cudaEventCreateWithFlags(&ev_fin, cudaEventDisableTiming));
+        }
+        while ((int)ev_in.size() < n) {
+            cudaEvent_t a, b;
+            CMBL_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CMBL_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            ev_in.push_back(a); ev_done.push_back(b);
+        }
+    }
+};
+int host_chunks() { static const int v = [] { const char* e = getenv("CMBL_HOST_CHUNKS"); return e ? atoi(e) : 4; }(); return v; }
+}  // namespace
+#endif
+
 int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream) {
     CMBL_API_BEGIN
     CMBL_REQUIRE(flow && flow->f && in_host && out_host, "NULL argument");
@@ -62,11 +88,50 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
         void* d = io.reserve(bytes);
 #ifdef CMBL_EMU
         memcpy(d, in_host, bytes);
-#else
-        CMBL_CUDA(cudaMemcpyAsync(d, in_host, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
-#endif
         cmbl::flow_apply<T>(F, op, d, d, as_stream(stream));
         cmbl::dev_download(out_host, d, bytes, as_stream(stream));
+#else
+        cudaStream_t st = as_stream(stream);
+        int nch = host_chunks();
+        if (nch > F.Nb) nch = F.Nb;
+        if (four || nch <= 1) {
+            CMBL_CUDA(cudaMemcpyAsync(d, in_host, bytes, cudaMemcpyHostToDevice, st));
+            cmbl::flow_apply<T>(F, op, d, d, st);
+            cmbl::dev_download(out_host, d, bytes, st);
+        } else {
+            // Map-space flows (L*f, L\f): batch items are independent, so the batch moves through a three-stage pipeline —
+            // H2D of items i+1.. on one copy stream, the integration of item group i on the caller's stream, D2H of finished
+            // groups on a second copy stream (PCIe is full duplex) — instead of copy-in, compute, copy-out back to back.
+            static thread_local HostPipe hp;
+            hp.ensure(nch);
+            const int n = F.nsteps, per = (F.Nb + nch - 1) / nch;
+            const size_t plane_b = sizeof(T) * P.map_elems();
+            const char* hin = static_cast<const char*>(in_host); char* hout = static_cast<char*>(out_host); char* dd = static_cast<char*>(d);
+            CMBL_CUDA(cudaEventRecord(hp.ev_start, st));                       // the staging buffer is free once earlier work on `st` is done
+            CMBL_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_start, 0));
+            int nused = 0;
+            for (int b0 = 0; b0 < F.Nb; b0 += per, ++nused) {
+                const int nb = (F.Nb - b0 < per) ? F.Nb - b0 : per;
+                const size_t off = plane_b * (size_t)b0 * F.Npol, cb = plane_b * (size_t)nb * F.Npol;
+                CMBL_CUDA(cudaMemcpyAsync(dd + off, hin + off, cb, cudaMemcpyHostToDevice, hp.s_in));
+                CMBL_CUDA(cudaEventRecord(hp.ev_in[nused], hp.s_in));
+            }
+            int i = 0;
+            for (int b0 = 0; b0 < F.Nb; b0 += per, ++i) {
+                const int nb = (F.Nb - b0 < per) ? F.Nb - b0 : per;
+                const size_t off = plane_b * (size_t)b0 * F.Npol, cb = plane_b * (size_t)nb * F.Npol;
+                CMBL_CUDA(cudaStreamWaitEvent(st, hp.ev_in[i], 0));
+                cmbl::flow_integrate_range<T>(F, false, reinterpret_cast<T*>(d), op == CMBL_OP_L ? 0 : 2 * n, op == CMBL_OP_L ? 2 * n : 0,
+                                              b0 * F.Npol, nb * F.Npol, st);
+                CMBL_CUDA(cudaEventRecord(hp.ev_done[i], st));
+                CMBL_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_done[i], 0));
+                CMBL_CUDA(cudaMemcpyAsync(hout + off, dd + off, cb, cudaMemcpyDeviceToHost, hp.s_out));
+            }
+            CMBL_CUDA(cudaEventRecord(hp.ev_fin, hp.s_out));
+            CMBL_CUDA(cudaStreamWaitEvent(st, hp.ev_fin, 0));
+            CMBL_CUDA(cudaStreamSynchronize(st));                              // out_host is valid on return, as before
+        }
+#endif
     });
     CMBL_API_END
 }

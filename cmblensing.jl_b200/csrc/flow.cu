@@ -153,31 +153,41 @@ static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, c
     }
 }
 
-template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st) {
+// working buffers of the integrator, sized for all F.C planes
+template <class T> static void flow_reserve(FlowT<T>& F, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
+    const size_t nmap = P.map_elems();
+    if (flow_rg_rows(P)) F.yrg.reserve(sizeof(T) * nmap * F.C);
+    F.acc.reserve(sizeof(T) * nmap * F.C);
+    F.ubuf.reserve(sizeof(T) * nmap * F.C);
+    F.tmp.reserve(sizeof(T) * nmap * F.C);
+    F.nline.reserve(sizeof(T) * (size_t)P.Ny * F.C);
+    F.jn.reserve(sizeof(T) * (size_t)P.Ny * F.C);
+    if (F.counter.cap < sizeof(int) * (size_t)F.C) { F.counter.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.counter.p, sizeof(int) * (size_t)F.C, st); }
+}
+
+// RK4 over stages k0 → k1 for the planes [c0, c0 + nC) of the caller's state `ycaller` (reference layout, F.C planes).
+// Planes of different batch items are independent, so a caller may integrate plane ranges one after another (the pipelined
+// host path below overlaps their transfers with the integration of their neighbours).
+template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* ycaller, int k0, int k1, int c0, int nC, cmblStream_t st) {
     CMBL_REQUIRE(F.have_p, "LenseFlow used before cmbl_lenseflow_precompute");
+    CMBL_REQUIRE(c0 >= 0 && nC >= 1 && c0 + nC <= F.C && c0 % F.Npol == 0 && nC % F.Npol == 0, "plane range must cover whole batch items");
     PlanT<T>& P = *F.P;
     const size_t nmap = P.map_elems();
     const int n = F.nsteps;
     const int G = flow_rg_rows(P);
     CMBL_REQUIRE(G == F.pcache_G, "p-cache layout does not match the kernel path");
-    T* ycaller = y;
+    flow_reserve(F, st);
+    T* y = ycaller;
     if (G) {                                        // integrate on a row-grouped copy of the state (flow_fast.cuh)
-        y = reinterpret_cast<T*>(F.yrg.reserve(sizeof(T) * nmap * F.C));
-        convert_layout<T, true>(P, G, ycaller, y, F.C, st);
+        y = reinterpret_cast<T*>(F.yrg.p);
+        convert_layout<T, true>(P, G, ycaller + (size_t)c0 * nmap, y + (size_t)c0 * nmap, nC, st);
     }
-    T* acc = reinterpret_cast<T*>(F.acc.reserve(sizeof(T) * nmap * F.C));
-    T* ub = reinterpret_cast<T*>(F.ubuf.reserve(sizeof(T) * nmap * F.C));
-    F.tmp.reserve(sizeof(T) * nmap * F.C);
-    F.nline.reserve(sizeof(T) * (size_t)P.Ny * F.C);
-    F.jn.reserve(sizeof(T) * (size_t)P.Ny * F.C);
-    if (F.counter.cap < sizeof(int) * (size_t)F.C) { F.counter.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.counter.p, sizeof(int) * (size_t)F.C, st); }
+    T* acc = reinterpret_cast<T*>(F.acc.p);
+    T* ub = reinterpret_cast<T*>(F.ubuf.p);
     const int sgn = k1 > k0 ? 1 : -1;
     const double h = (double)sgn / n;
     const T h2 = (T)(h / 2), h1 = (T)h, h6 = (T)(h / 6), h3 = (T)(h / 3);
-    static const int chunk_env = [] { const char* e = getenv("CMBL_FLOW_CHUNK"); return e ? atoi(e) : 0; }();
-    const int chunk = (chunk_env > 0 && chunk_env < F.C) ? chunk_env : F.C;       // planes integrated together (L2 residency)
-    for (int c0 = 0; c0 < F.C; c0 += chunk) {
-    const int nC = (F.C - c0 < chunk) ? F.C - c0 : chunk;
     int kk = k0;
     for (int step = 0; step < n; ++step) {
         for (int s = 0; s < 4; ++s) {
@@ -193,8 +203,15 @@ template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int 
         }
         kk += 2 * sgn;
     }
-    }
-    if (G) convert_layout<T, false>(P, G, y, ycaller, F.C, st);
+    if (G) convert_layout<T, false>(P, G, y + (size_t)c0 * nmap, ycaller + (size_t)c0 * nmap, nC, st);
+}
+
+template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st) {
+    static const int chunk_env = [] { const char* e = getenv("CMBL_FLOW_CHUNK"); return e ? atoi(e) : 0; }();
+    int chunk = (chunk_env > 0 && chunk_env < F.C) ? chunk_env : F.C;             // planes integrated together (L2 residency)
+    chunk = (chunk + F.Npol - 1) / F.Npol * F.Npol;
+    for (int c0 = 0; c0 < F.C; c0 += chunk)
+        flow_integrate_range<T>(F, adj, y, k0, k1, c0, (F.C - c0 < chunk) ? F.C - c0 : chunk, st);
 }
 
 template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st) {
@@ -241,6 +258,7 @@ template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_rg_rows(*F.P)
 #define INST(T)                                                                                        \
     template void flow_precompute<T>(FlowT<T>&, const void*, int, bool, cmblStream_t);                 \
     template void flow_integrate<T>(FlowT<T>&, bool, T*, int, int, cmblStream_t);                      \
+    template void flow_integrate_range<T>(FlowT<T>&, bool, T*, int, int, int, int, cmblStream_t);      \
     template void flow_apply<T>(FlowT<T>&, int, const void*, void*, cmblStream_t);                     \
     template int flow_kernel_path<T>(FlowT<T>&);
 INST(float)

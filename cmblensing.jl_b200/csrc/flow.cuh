@@ -339,6 +339,7 @@ template <class T> struct FlowT : FlowBase {
 template <class T> void flow_precompute(FlowT<T>& F, const void* phi, int phi_basis, bool with_minv, cmblStream_t st);
 // integrate the map-space flow in place on y from stage index k0 to k1 (0 or 2n)
 template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st);
+template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* y, int k0, int k1, int c0, int nC, cmblStream_t st);
 template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st);
 template <class T> int flow_kernel_path(FlowT<T>& F);
 

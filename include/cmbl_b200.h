@@ -90,7 +90,10 @@ int cmbl_lenseflow_destroy(cmbl_flow* flow);
 int cmbl_lenseflow_precompute(cmbl_flow* flow, const void* phi, int phi_basis, int with_minv, void* stream);
 /* *, \ on FlowOp / Adjoint (src/flowops.jl:11-14). ops 0,2: in/out Map; ops 1,3: in/out Fourier. in may alias out. */
 int cmbl_lenseflow_apply(cmbl_flow* flow, int op, const void* in, void* out, void* stream);
-/* same, HOST buffers, copies included (the end-to-end path bench.py times) */
+/* same, HOST buffers, copies included (the end-to-end path bench.py times).  Returns when out_host is valid.  For the
+ * map-space flows (ops 0, 2) the batch items are pipelined: H2D of the next item group, integration of the current one and
+ * D2H of the finished one overlap on separate streams (pin the host buffers to get the overlap; CMBL_HOST_CHUNKS = number
+ * of groups, default 4, 1 = copy-in / compute / copy-out back to back). */
 int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream);
 /* pullback through Lϕ*f (op 0) or Lϕ\f (op 2): negδvelocityᴴ transpose flow (src/lenseflow.jl:176-214, src/flowops.jl:40-68).
  * f_out_map = the forward result (Map), delta = cotangent (Fourier). Outputs: dfield (Fourier, C planes), dphi (Fourier,
