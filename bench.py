@@ -137,14 +137,14 @@ def reference_arm(args, rank):
     ms = dt * NB * 1e3
     val = 1e3 / ms
     sample = f"1 of {NB} batch items per step (QU pair, Nside={NSIDE}, n={NSTEPS_RK}), time scaled x{NB}; scipy.fft/pocketfft workers={cores}"
-    print(json.dumps({
+    print_line({
         "impl": "reference", "metric": "lenseflow_batched_applies_per_sec", "value": val, "unit": "applies/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"LenseFlow apply Lphi*f, Nside={NSIDE} QU batch={NB} (Cphi={NB}), RK4 n={NSTEPS_RK}, theta_pix={THETA}'"},
         "cpu_baseline": {"value": val, "unit": "applies/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -158,6 +158,14 @@ def main():
     ap.add_argument("--cg-iters", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: library chatter (e.g. "NCCL version ..." printed at communicator creation) is sent
+    # to stderr by pointing fd 1 at fd 2 for the duration of the run; the line itself is written to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_line
+    def print_line(obj):
+        _real_stdout.write(json.dumps(obj) + "\n"); _real_stdout.flush()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return reference_arm(args, rank)
@@ -357,7 +365,7 @@ def main():
                    "gpu_launches": launches_cg, "algorithmic_GBs": AB["cg_iter"] / ms_cg / 1e6, "frac": AB["cg_iter"] / ms_cg / 1e6 / peak,
                    "res_first": res0[0], "res_last": res1[0]},
         }
-        print(json.dumps(line))
+        print_line(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -72,7 +72,7 @@ struct HostPipe {
         }
     }
 };
-int host_chunks() { static const int v = [] { const char* e = getenv("CMBL_HOST_CHUNKS"); return e ? atoi(e) : 4; }(); return v; }
+int host_chunks() { static const int v = [] { const char* e = getenv("CMBL_HOST_CHUNKS"); return e ? atoi(e) : 2; }(); return v; }
 }  // namespace
 #endif
 
