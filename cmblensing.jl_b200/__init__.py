@@ -29,6 +29,7 @@ __all__ = [
     "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "BlockDiagIEB", "dot", "BaseDataSet", "gradientf_logpdf",
     "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
     "Cℓ_to_2D", "Cℓ_to_Cov", "Cl_to_Cov", "simulate", "sample_f", "convert",
+    "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint",
     "CmblError", "load",
 ]
 
@@ -449,10 +450,11 @@ class BaseDataSet:
 
     def __init__(self, d: Field, Cf: DiagOp, Cn: DiagOp, B: DiagOp, Mf: DiagOp, Mpix: DiagOp | None = None,
                  Cnhat: DiagOp | None = None, Bhat: DiagOp | None = None, L=LenseFlow, nsteps: int = 7,
-                 D: DiagOp | None = None, G: DiagOp | None = None):
+                 D: DiagOp | None = None, G: DiagOp | None = None, Cϕ: DiagOp | None = None, Nϕ: DiagOp | None = None):
         self.d, self.Cf, self.Cn, self.B, self.Mf, self.Mpix = HarmonicBasis(d), Cf, Cn, B, Mf, Mpix
         self.Cnhat, self.Bhat, self.L, self.nsteps = Cnhat or Cn, Bhat or B, L, nsteps
         self.D, self.G = D, G                      # mixing matrices of the Mixed parametrisation (src/dataset.jl:96-117); None = identity
+        self.Cϕ, self.Nϕ = Cϕ, Nϕ                  # ϕ prior and ϕ-noise estimate (logpdf, ϕ° Hessian preconditioner, src/dataset.jl:45-57,134-137)
         self._cg = {}
 
     def _solver(self, ϕ: Field):
@@ -497,7 +499,8 @@ def gradientf_logpdf(ds: BaseDataSet, f: Field, ϕ: Field, d: Field | None = Non
     f = HarmonicBasis(f)
     out = torch.empty_like(f.arr)
     p = f.proj
-    dptr = _ptr(HarmonicBasis(d).arr) if d is not None else c_void_p(0)
+    dh = HarmonicBasis(d) if d is not None else None          # keep the converted field alive across the call
+    dptr = _ptr(dh.arr) if dh is not None else c_void_p(0)
     p.lib.call("cmbl_gradientf_logpdf", h, _ptr(f.arr), dptr, 1 if d_zero else 0, _ptr(out), _stream(out))
     return f._like(out)
 
@@ -531,7 +534,8 @@ def conjugate_gradient_wiener(ds: BaseDataSet, ϕ: Field, fstart: Field | None =
     nb = ds.d.Nbatch
     st = _stream(ds.d.arr)
     res = (c_double * nb)()
-    fs = _ptr(HarmonicBasis(fstart).arr) if fstart is not None else c_void_p(0)
+    fsf = HarmonicBasis(fstart) if fstart is not None else None   # keep the converted field alive while the solver reads it
+    fs = _ptr(fsf.arr) if fsf is not None else c_void_p(0)
     out = torch.empty_like(ds.d.arr)
     if group is None:
         hist = (c_double * (nsteps * nb))()
@@ -610,3 +614,174 @@ def sample_f(ds: BaseDataSet, ϕ: Field, white_f: Field | None = None, white_n: 
     ds2 = BaseDataSet(ds.d - sim["d"], ds.Cf, ds.Cn, ds.B, ds.Mf, ds.Mpix, ds.Cnhat, ds.Bhat, L=ds.L, nsteps=ds.nsteps, D=ds.D, G=ds.G)
     Δf, hist = argmaxf_logpdf(ds2, ϕ, fstart=fstart, offset=True, conjgrad_kwargs=conjgrad_kwargs)
     return sim["f"] + Δf, hist
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Joint posterior: logpdf, Mixed(ds), its gradient, MAP_joint (src/dataset.jl:60-67,84-117, src/distributions.jl:11-15,
+# src/maximization.jl:115-222).  Control flow lives here on the host, as it does in the reference; every field operation
+# is a call into the library (flows, δ-flows, transforms, diagonal products, dots).
+# ------------------------------------------------------------------------------------------------------------------
+def logdet(op) -> float:
+    """logdet(Diagonal(::Fourier-basis field)) = Σ nan2zero(log|diag|)·λ_rfft (src/proj_lambert.jl:331-336);
+    logdet(BlockDiagIEB) = logdet(det ΣTE) + logdet ΣB (src/specialops.jl:94).  A setup-time constant of the operator."""
+    p = op.proj if isinstance(op, BlockDiagIEB) else op.diag.proj
+    λ = torch.from_numpy(p.λ_rfft).to(op._real.device, torch.float64)
+    def ld(t):
+        v = torch.log(t.abs().to(torch.float64)) * λ
+        return float(torch.where(torch.isfinite(v), v, torch.zeros_like(v)).sum())
+    r = op._real
+    if isinstance(op, BlockDiagIEB):
+        return ld(r[0, 0] * r[0, 2] - r[0, 1] * r[0, 1]) + ld(r[0, 3])
+    if not op.diag.is_fourier:
+        raise CmblError("logdet on this path is implemented for Fourier-basis diagonals and BlockDiagIEB")
+    return ld(r)
+
+
+def _quad(C, v: Field) -> np.ndarray:
+    """v' pinv(Σ) v + logdet Σ per batch item (src/distributions.jl:11-15)."""
+    return dot(v, C.ldiv(v)) + logdet(C)
+
+
+def logpdf(ds, f: Field | None = None, ϕ: Field | None = None, **kw) -> np.ndarray:
+    """logpdf(ds; f, ϕ) of the BaseDataSet forward model, or logpdf(Mixed(ds); f°=…, ϕ°=…) (src/dataset.jl:60-67,84-87).
+    Returns one value per batch item."""
+    if isinstance(ds, Mixed):
+        f, ϕ = unmix(ds.ds, kw.get("f°", f), kw.get("ϕ°", ϕ))
+        return logpdf(ds.ds, f, ϕ)                       # − logdet(D,θ) − logdet(G,θ), both 0 without θ dependence (src/generic.jl:269)
+    if ds.Cϕ is None:
+        raise CmblError("logpdf needs BaseDataSet(..., Cϕ=...)")
+    L = ds.L(ϕ, ds.nsteps) if isinstance(ds.L, type) else LenseFlow(ϕ, ds.nsteps)
+    f = HarmonicBasis(f)
+    z = _apply_MB(ds, L * f) - ds.d
+    return -(_quad(ds.Cn, z) + _quad(ds.Cf, f) + _quad(ds.Cϕ, Fourier(ϕ))) / 2
+
+
+class Mixed:
+    """Mixed(ds): the same posterior in the mixed variables f° = L(ϕ) D f, ϕ° = G ϕ (src/dataset.jl:28-30,84-117)."""
+    def __init__(self, ds: BaseDataSet): self.ds = ds
+
+
+def gradient_logpdf_mixed(ds: BaseDataSet, f_mixed: Field, ϕ_mixed: Field, bug_compat: bool = True):
+    """gradient((f°, ϕ°) -> logpdf(Mixed(ds); f°, ϕ°)) (src/maximization.jl:151) through the reference's pullbacks: the chain
+    f° → f₁ = L(ϕ)\\f° → f = D\\f₁ → f̃ = L(ϕ) f → r = d − M B f̃ is walked backwards with the transpose δ-flows of `L*f` and `L\\f`
+    (negδvelocityᴴ, src/lenseflow.jl:176-214; rules src/flowops.jl:40-68).  Two flows and two δ-flows on the device.
+    Returns (∇f° in the Ð basis, ∇ϕ° Fourier):  d lnP = ⟨∇f°, δf°⟩ + ⟨∇ϕ°, δϕ°⟩."""
+    if ds.Cϕ is None:
+        raise CmblError("gradient_logpdf_mixed needs BaseDataSet(..., Cϕ=...)")
+    ϕ = ds.G.ldiv(ϕ_mixed) if ds.G is not None else Fourier(ϕ_mixed)
+    f_mixed = LenseBasis(f_mixed)
+    Lc = LenseFlow(ϕ, ds.nsteps).cache(f_mixed, with_minv=True)
+    f1 = Lc.apply(OP_LINV, f_mixed)
+    f = ds.D.ldiv(f1) if ds.D is not None else HarmonicBasis(f1)
+    f̃ = Lc.apply(OP_L, f)
+    r = ds.d - _apply_MB(ds, f̃)
+    x = ds.Mf * ds.Cn.ldiv(r)                                                   # M' = Mpix'·Mf' after pinv(Cn)
+    if ds.Mpix is not None:
+        x = HarmonicBasis(ds.Mpix * LenseBasis(x))
+    g_f̃ = ds.B * x                                                              # ∂lnP/∂f̃ = B'M'pinv(Cn) r
+    δf_a, δϕ_a = Lc.pullback(OP_L, f̃, g_f̃, bug_compat)
+    g_f = HarmonicBasis(δf_a) - ds.Cf.ldiv(f)
+    g_f1 = ds.D.ldiv(g_f) if ds.D is not None else g_f                           # D is real and diagonal: D⁻ᵀ = D⁻¹
+    δf0, δϕ_b = Lc.pullback(OP_LINV, f1, g_f1, bug_compat)
+    g_ϕ = δϕ_a + δϕ_b - ds.Cϕ.ldiv(ϕ)
+    if ds.G is not None:
+        g_ϕ = ds.G.ldiv(g_ϕ)
+    return δf0, g_ϕ
+
+
+def _brent_bounded(fun, a: float, b: float, xatol: float, maxiter: int = 500):
+    """Brent's derivative-free minimiser on [a, b] (golden section + successive parabolic interpolation) — the algorithm
+    behind Optim.Brent() that MAP_joint's line search calls (src/maximization.jl:171-176).  Returns (x, f(x), evaluations)."""
+    golden = 0.5 * (3.0 - 5.0 ** 0.5)
+    sqrt_eps = float(np.sqrt(2.2e-16))
+    x = w = v = a + golden * (b - a)
+    fx = fw = fv = fun(x)
+    d = e = 0.0
+    n = 1
+    while n < maxiter:
+        m = 0.5 * (a + b)
+        tol1 = sqrt_eps * abs(x) + xatol / 3.0
+        tol2 = 2.0 * tol1
+        if abs(x - m) <= tol2 - 0.5 * (b - a):
+            break
+        use_golden = True
+        if abs(e) > tol1:                                   # parabolic fit through (v, w, x)
+            r_ = (x - w) * (fx - fv)
+            q = (x - v) * (fx - fw)
+            p_ = (x - v) * q - (x - w) * r_
+            q = 2.0 * (q - r_)
+            if q > 0:
+                p_ = -p_
+            q = abs(q)
+            r_, e = e, d
+            if abs(p_) < abs(0.5 * q * r_) and p_ > q * (a - x) and p_ < q * (b - x):
+                d = p_ / q
+                u = x + d
+                if (u - a) < tol2 or (b - u) < tol2:
+                    d = tol1 if m >= x else -tol1
+                use_golden = False
+        if use_golden:
+            e = (b - x) if x < m else (a - x)
+            d = golden * e
+        u = x + (d if abs(d) >= tol1 else (tol1 if d > 0 else -tol1))
+        fu = fun(u); n += 1
+        if fu <= fx:
+            if u >= x: a = x
+            else: b = x
+            v, fv, w, fw, x, fx = w, fw, x, fx, u, fu
+        else:
+            if u < x: a = u
+            else: b = u
+            if fu <= fw or w == x:
+                v, fv, w, fw = w, fw, u, fu
+            elif fu <= fv or v == x or v == w:
+                v, fv = u, fu
+    return x, fx, n
+
+
+def MAP_joint(ds: BaseDataSet, ϕstart: Field | None = None, nsteps: int = 20, fstart: Field | None = None, αtol: float = 1e-4,
+              αmax: float | None = None, conjgrad_kwargs=dict(tol=1e-1, nsteps=500), bug_compat: bool = True, group=None):
+    """MAP_joint(ds; nsteps, αtol, conjgrad_kwargs) (src/maximization.jl:115-222) for Ω = (ϕ,): coordinate descent that alternates
+    the CG Wiener filter at fixed ϕ (`argmaxf_logpdf`) with one step along pinv(H)·∇ϕ° logpdf(Mixed(ds)), H = pinv(Cϕ) + pinv(Nϕ)
+    (src/dataset.jl:134-137), whose length comes from a Brent line search on [0, 2α] of the batch-summed −logpdf(Mixed(ds)).
+    G = 1 during the maximisation, as in the reference (:137).  With a torch.distributed `group` the batch is sharded over ranks:
+    the line-search objective is all-reduced (one scalar per evaluation), so every rank takes the same α.
+    Returns (f, ϕ, history)."""
+    if ds.Cϕ is None or ds.Nϕ is None:
+        raise CmblError("MAP_joint needs BaseDataSet(..., Cϕ=..., Nϕ=...)")
+    d = ds.d
+    p = d.proj
+    G_save, ds.G = ds.G, None
+    ϕ = Fourier(ϕstart) if ϕstart is not None else Field("Fourier", torch.zeros(p.fourier_shape(1, d.Nbatch), dtype=p.cT, device=p.device), p)
+    H = DiagOp(Field("Fourier", (ds.Cϕ.pinv()._real + ds.Nϕ.pinv()._real).to(p.cT), p))
+    f, α, history = fstart, 1.0, []
+
+    def total(v: np.ndarray) -> float:
+        s = float(np.sum(v))
+        if group is not None:
+            import torch.distributed as dist
+            t = torch.tensor([s], dtype=torch.float64, device=d.arr.device if dist.get_backend(group) == "nccl" else "cpu")
+            dist.all_reduce(t, group=group)
+            s = float(t.item())
+        return s
+
+    try:
+        for step in range(1, nsteps + 1):
+            f, cg_hist = argmaxf_logpdf(ds, ϕ, fstart=f, conjgrad_kwargs=conjgrad_kwargs, group=group)      # f step
+            f_m, ϕ_m = mix(ds, f, ϕ)                                                                          # ϕ step
+            _, g = gradient_logpdf_mixed(ds, f_m, ϕ_m, bug_compat)
+            Δ = H.ldiv(g)
+            amax = αmax if αmax is not None else 2 * α
+            mds = Mixed(ds)
+
+            def obj(a):
+                v = -total(logpdf(mds, f_m, ϕ_m + Δ * float(a)))
+                return v if np.isfinite(v) else (a / amax) * np.finfo(np.float64).max                           # :174
+            α, _, nev = _brent_bounded(obj, 0.0, float(amax), αtol)
+            ϕ_m = ϕ_m + Δ * float(α)
+            lp = logpdf(mds, f_m, ϕ_m)
+            f, ϕ = unmix(ds, f_m, ϕ_m)
+            history.append(dict(step=step, logpdf=lp, α=α, cg_iters=len(cg_hist), linesearch_evals=nev))
+    finally:
+        ds.G = G_save
+    return f, ϕ, history

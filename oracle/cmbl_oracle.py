@@ -464,6 +464,10 @@ class DataSet:
     Mpix: np.ndarray | None       # pixel mask (Map basis), or None for I
     d: np.ndarray | None = None   # data, harmonic basis
     L: CachedLenseFlow | None = None
+    Cphi: np.ndarray | None = None    # ϕ prior covariance (Fourier diagonal, (1,1,Nx,Ny/2+1))
+    Nphi: np.ndarray | None = None    # ϕ noise estimate used by the ϕ° Hessian preconditioner (src/dataset.jl:134-137)
+    D: np.ndarray | None = None       # mixing matrices of the Mixed parametrisation (None = identity)
+    G: np.ndarray | None = None
 
     @property
     def npol(self):
@@ -620,6 +624,95 @@ def sample_f(ds: DataSet, white_f: np.ndarray, white_n: np.ndarray, nsteps: int 
 
 
 # ----------------------------------------------------------------------------------------------
+# Joint posterior: logpdf, its gradient in the mixed parametrisation, MAP_joint
+# (src/dataset.jl:60-67,84-117,134-137, src/distributions.jl:11-15, src/maximization.jl:115-222)
+# ----------------------------------------------------------------------------------------------
+def op_logdet(pol: str, proj: ProjLambert, A: np.ndarray) -> np.ndarray:
+    """logdet(Diagonal) (src/proj_lambert.jl:331-336); logdet(BlockDiagIEB) = logdet(det ΣTE) + logdet ΣB (src/specialops.jl:94)."""
+    if pol == "IP":
+        det = A[:, 0] * A[:, 2] - A[:, 1] * A[:, 1]
+        return logdet_fourier(proj, det[:, None]) + logdet_fourier(proj, A[:, 3:4])
+    return logdet_fourier(proj, A)
+
+
+def logpdf(ds: DataSet, f_harm: np.ndarray, phi_four: np.ndarray, d=None) -> np.ndarray:
+    """logpdf(ds; f, ϕ) of the BaseDataSet forward model (src/dataset.jl:60-67) with the MvNormal terms of
+    src/distributions.jl:11-15: −(z'pinv(Σ)z + logdet Σ)/2 for f ~ N(0,Cf), ϕ ~ N(0,Cϕ), d ~ N(M B L(ϕ) f, Cn).  Per batch item."""
+    proj, pol = ds.proj, ds.pol
+    d = ds.d if d is None else d
+    L = precompute(proj, phi_four, ds.L.nsteps, phi_is_fourier=True)
+    ft = lenseflow_apply(L, OP_L, to_lense_basis(ds, proj, f_harm))
+    z = apply_M(ds, op_mul(pol, ds.B, to_harmonic_basis(ds, proj, ft))) - d
+    quad = lambda C, v, pl: dot_fourier(proj, v, op_mul(pl, op_pinv(pl, C), v)) + op_logdet(pl, proj, C)
+    return -(quad(ds.Cn, z, pol) + quad(ds.Cf, f_harm, pol) + quad(ds.Cphi, phi_four, "I")) / 2
+
+
+def logpdf_mixed(ds: DataSet, f_mixed_map: np.ndarray, phi_mixed: np.ndarray) -> np.ndarray:
+    """logpdf(Mixed(ds); f°, ϕ°) (src/dataset.jl:84-87); logdet(D,θ) = logdet(G,θ) = 0 without θ dependence (src/generic.jl:269)."""
+    f, phi = unmix(ds, ds.proj, ds.pol, f_mixed_map, phi_mixed, D=ds.D, G=ds.G, nsteps=ds.L.nsteps)
+    return logpdf(ds, f, phi)
+
+
+def gradient_logpdf_mixed(ds: DataSet, f_mixed_map: np.ndarray, phi_mixed: np.ndarray, bug_compat: bool = True):
+    """gradient(Ω° -> logpdf(Mixed(ds); f°, Ω°...)) (src/maximization.jl:151) by the reference's pullbacks: the chain
+    f° → f₁ = L(ϕ)\f° → f = D\f₁ → f̃ = L(ϕ)f → r = d − M B f̃ is differentiated backwards with the δ-flows of `L*f` and
+    `L\f` (src/flowops.jl:40-68).  Returns (∇f° in the Ð basis, ∇ϕ° Fourier); d lnP = ⟨∇f°, δf°⟩ + ⟨∇ϕ°, δϕ°⟩."""
+    proj, pol = ds.proj, ds.pol
+    pol0 = 1 if pol == "IP" else 0
+    phi = phi_mixed if ds.G is None else diag_ldiv(ds.G, phi_mixed)
+    L = precompute(proj, phi, ds.L.nsteps, phi_is_fourier=True)
+    f1 = lenseflow_apply(L, OP_LINV, f_mixed_map)                                   # Map
+    f1h = to_harmonic_basis(ds, proj, f1)
+    f = f1h if ds.D is None else diag_ldiv(ds.D, f1h)
+    ft = lenseflow_apply(L, OP_L, to_lense_basis(ds, proj, f))
+    r = ds.d - apply_M(ds, op_mul(pol, ds.B, to_harmonic_basis(ds, proj, ft)))
+    x, is_map = apply_MH(ds, op_mul(pol, op_pinv(pol, ds.Cn), r))
+    if is_map:
+        x = to_harmonic_basis(ds, proj, x)
+    g_ft = op_mul(pol, ds.B, x)                                                    # ∂lnP/∂f̃ = B'M'pinv(Cn) r
+    deriv = lambda h: (eb_to_qu(proj, h, pol0) if pol != "I" else h).astype(proj.cT)
+    df_a, dphi_a = lenseflow_grad(L, OP_L, ft, deriv(g_ft), bug_compat)
+    df_a = qu_to_eb(proj, df_a, pol0) if pol != "I" else df_a
+    g_f = df_a - op_mul(pol, op_pinv(pol, ds.Cf), f)
+    g_f1 = g_f if ds.D is None else diag_ldiv(ds.D, g_f)                            # D real, diagonal: D⁻ᵀ = D⁻¹
+    df0, dphi_b = lenseflow_grad(L, OP_LINV, f1, deriv(g_f1), bug_compat)
+    g_phi = dphi_a + dphi_b - pinv_diag(ds.Cphi) * phi
+    if ds.G is not None:
+        g_phi = diag_ldiv(ds.G, g_phi)
+    return df0.astype(proj.cT), g_phi.astype(proj.cT)
+
+
+def MAP_joint(ds: DataSet, nsteps: int = 5, conjgrad_kwargs=dict(tol=1e-1, nsteps=500), alpha_tol: float = 1e-4, bug_compat: bool = True):
+    """MAP_joint (src/maximization.jl:115-222) for (f, ϕ): coordinate descent alternating the CG Wiener filter at fixed ϕ with
+    one preconditioned gradient step in ϕ° whose length is found by Brent's bounded line search on [0, 2α] (the reference
+    calls Optim.Brent; here scipy's bounded Brent).  G = 1 as in the reference (:137).  Returns (f, ϕ, history)."""
+    from scipy.optimize import minimize_scalar
+    proj, pol = ds.proj, ds.pol
+    G_save, ds.G = ds.G, None
+    phi = np.zeros((ds.d.shape[0], 1) + proj.fourier_shape, dtype=proj.cT)
+    f, alpha, hist = None, 1.0, []
+    H = pinv_diag(ds.Cphi) + pinv_diag(ds.Nphi)                                     # Hessian_logpdf_preconditioner((:ϕ°,)) :134-137
+    try:
+        for step in range(nsteps):
+            ds.L = precompute(proj, phi, ds.L.nsteps, phi_is_fourier=True)
+            f, cg_hist = argmaxf_logpdf(ds, fstart=f, **conjgrad_kwargs)
+            f_mixed, phi_mixed = mix(ds, proj, pol, f, phi, D=ds.D, G=None, nsteps=ds.L.nsteps)
+            _, g = gradient_logpdf_mixed(ds, f_mixed, phi_mixed, bug_compat)
+            step_dir = diag_ldiv(H, g)
+            amax = 2 * alpha
+            obj = lambda a: -float(logpdf_mixed(ds, f_mixed, (phi_mixed + proj.T(a) * step_dir).astype(proj.cT)).sum())
+            sol = minimize_scalar(obj, bounds=(0.0, amax), method="bounded", options=dict(xatol=alpha_tol))
+            alpha = float(sol.x)
+            phi_mixed = (phi_mixed + proj.T(alpha) * step_dir).astype(proj.cT)
+            lp = logpdf_mixed(ds, f_mixed, phi_mixed)
+            f, phi = unmix(ds, proj, pol, f_mixed, phi_mixed, D=ds.D, G=None, nsteps=ds.L.nsteps)
+            hist.append(dict(step=step + 1, logpdf=lp, alpha=alpha, cg_iters=len(cg_hist), linesearch_evals=int(sol.nfev)))
+    finally:
+        ds.G = G_save
+    return f, phi, hist
+
+
+# ----------------------------------------------------------------------------------------------
 # Synthetic flat-sky inputs (harness; mirrors load_sim defaults, src/dataset.jl:186-338)
 # ----------------------------------------------------------------------------------------------
 def load_fiducial_cls(path=None):
@@ -680,6 +773,8 @@ def make_dataset(Ny, Nx, theta_pix, pol="I", T=np.float64, nb=1, seed=0, nsteps=
     n = sim(Cn)
     L = precompute(proj, phi, nsteps, phi_is_fourier=True)
     ds = DataSet(proj, pol, Cf, Cn, Cn.copy(), B, B.copy(), Mf, Mpix, None, L)
+    ds.Cphi = Cphi
+    ds.Nphi = (Cphi * 0 + np.median(Cphi[Cphi > 0]) if np.any(Cphi > 0) else Cphi + 1).astype(proj.T)   # harness stand-in for quadratic_estimate(ds).Nϕ
     ft = lenseflow_apply(L, OP_L, to_lense_basis(pol, proj, f))
     d = (apply_M(ds, op_mul(pol, B, to_harmonic_basis(pol, proj, ft))) + n).astype(proj.cT)
     ds.d = d

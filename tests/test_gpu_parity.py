@@ -175,6 +175,32 @@ def test_gradientf_and_cg(cuda_pkg, dtype, pol, mask):
     assert relerr(x.cpu_numpy(), xo) < (1e-9 if dtype == "f64" else 2e-3)
 
 
+@pytest.mark.parametrize("pol", ["P", "IP"])
+def test_logpdf_mixed_gradient_and_map_joint(cuda_pkg, pol):
+    """logpdf(Mixed(ds)), its gradient through the device δ-flows and two MAP_joint steps (src/maximization.jl:115-222) vs the oracle."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, 64, 64, pol, "f64", nb=2, nsteps=5, mask=True, seed=12, theta=3.0, device=DEV)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    rng = np.random.default_rng(2)
+    Dn = (1.0 + 0.5 * rng.random((1, dso.npol) + oproj.fourier_shape)); Gn = 1.0 + 0.5 * rng.random((1, 1) + oproj.fourier_shape)
+    dso.D, dso.G = Dn, Gn
+    ds.D = pkg.DiagOp(pr["F"](Dn, pr["harm"])); ds.G = pkg.DiagOp(pr["F"](Gn, "Fourier"))
+    fo, po = pr["sim"]["f"], pr["sim"]["phi"]
+    assert np.allclose(pkg.logpdf(ds, pr["f"], pr["phi"]), O.logpdf(dso, fo, po), rtol=1e-10)
+    fm, pm = pkg.mix(ds, pr["f"], pr["phi"])
+    fmo, pmo = O.mix(dso, oproj, pol, fo, po, D=Dn, G=Gn, nsteps=5)
+    assert np.allclose(pkg.logpdf(pkg.Mixed(ds), fm, pm), O.logpdf_mixed(dso, fmo, pmo), rtol=1e-10)
+    gf, gp = pkg.gradient_logpdf_mixed(ds, fm, pm)
+    gfo, gpo = O.gradient_logpdf_mixed(dso, fmo, pmo)
+    assert relerr(gf.cpu_numpy(), gfo) < 1e-9 and relerr(gp.cpu_numpy(), gpo) < 1e-9
+    f, ϕ, hist = pkg.MAP_joint(ds, nsteps=2, conjgrad_kwargs=dict(tol=1e-1, nsteps=100))
+    f_o, ϕ_o, histo = O.MAP_joint(dso, nsteps=2, conjgrad_kwargs=dict(tol=1e-1, nsteps=100))
+    for h, ho in zip(hist, histo):
+        assert h["cg_iters"] == ho["cg_iters"] and abs(h["α"] - ho["alpha"]) < 1e-6 and np.allclose(h["logpdf"], ho["logpdf"], rtol=1e-8)
+    assert relerr(ϕ.cpu_numpy(), ϕ_o) < 1e-6 and relerr(f.cpu_numpy(), f_o) < 1e-6
+    assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum()
+
+
 def test_cg_converges_and_stops_like_reference(cuda_pkg):
     pkg = cuda_pkg
     pr = make_problem(pkg, 64, 64, "P", "f64", nb=2, nsteps=7, mask=True, seed=9, theta=3.0, device=DEV)

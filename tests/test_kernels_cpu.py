@@ -246,6 +246,34 @@ def test_sample_f_and_cl_to_cov(pkg, emu, pol):
         pkg.Cℓ_to_Cov("Q", proj, ell, cls["ut_TT"])
 
 
+@pytest.mark.parametrize("pol", ["P", "IP"])
+def test_logpdf_mixed_gradient_and_map_joint(pkg, emu, pol):
+    """logpdf, logpdf(Mixed(ds)), its gradient through the two pullbacks, and two MAP_joint steps (src/dataset.jl:60-117,
+    src/maximization.jl:115-222) against the oracle on the same inputs."""
+    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=4, mask=True, seed=12, theta=3.0, lib=emu)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    rng = np.random.default_rng(2)
+    Dn = (1.0 + 0.5 * rng.random((1, dso.npol) + oproj.fourier_shape)); Gn = 1.0 + 0.5 * rng.random((1, 1) + oproj.fourier_shape)
+    dso.D, dso.G = Dn, Gn
+    ds.D = pkg.DiagOp(pr["F"](Dn, pr["harm"])); ds.G = pkg.DiagOp(pr["F"](Gn, "Fourier"))
+    fo, po = pr["sim"]["f"], pr["sim"]["phi"]
+    assert np.allclose(pkg.logdet(ds.Cf), O.op_logdet(pol, oproj, dso.Cf), rtol=1e-12)
+    assert np.allclose(pkg.logpdf(ds, pr["f"], pr["phi"]), O.logpdf(dso, fo, po), rtol=1e-10)
+    fm, pm = pkg.mix(ds, pr["f"], pr["phi"])
+    fmo, pmo = O.mix(dso, oproj, pol, fo, po, D=Dn, G=Gn, nsteps=4)
+    assert np.allclose(pkg.logpdf(pkg.Mixed(ds), fm, pm), O.logpdf_mixed(dso, fmo, pmo), rtol=1e-10)
+    for bug in (True, False):
+        gf, gp = pkg.gradient_logpdf_mixed(ds, fm, pm, bug_compat=bug)
+        gfo, gpo = O.gradient_logpdf_mixed(dso, fmo, pmo, bug_compat=bug)
+        assert relerr(gf.cpu_numpy(), gfo) < 1e-9 and relerr(gp.cpu_numpy(), gpo) < 1e-9
+    f, ϕ, hist = pkg.MAP_joint(ds, nsteps=2, conjgrad_kwargs=dict(tol=1e-1, nsteps=100))
+    f_o, ϕ_o, histo = O.MAP_joint(dso, nsteps=2, conjgrad_kwargs=dict(tol=1e-1, nsteps=100))
+    for h, ho in zip(hist, histo):
+        assert h["cg_iters"] == ho["cg_iters"] and abs(h["α"] - ho["alpha"]) < 1e-6 and np.allclose(h["logpdf"], ho["logpdf"], rtol=1e-8)
+    assert relerr(ϕ.cpu_numpy(), ϕ_o) < 1e-6 and relerr(f.cpu_numpy(), f_o) < 1e-6
+    assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum()
+
+
 def test_cg_stops_on_tol_like_reference(pkg, emu):
     pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=emu)
     _, h0 = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=0.0)

@@ -206,3 +206,35 @@ def test_blockdiag_ieb_algebra():
     # a diagonal block reduces to DiagOp behaviour
     D = O.block_from_diag(np.stack([Cf[:, 0], Cf[:, 2], Cf[:, 3]], axis=1))
     assert np.allclose(O.block_mul(D, f), np.stack([Cf[:, 0], Cf[:, 2], Cf[:, 3]], axis=1) * f)
+
+
+# ---- joint posterior in the mixed parametrisation (runtests.jl:593-616) ---------------------------------------------
+@pytest.mark.parametrize("pol", ["I", "P", "IP"])
+def test_logpdf_mixed_and_gradient_fd(pol):
+    """`logpdf(ds; f, ϕ) ≈ logpdf(Mixed(ds); f°, ϕ°)` (runtests.jl:609) and the finite-difference test of the gradient of
+    logpdf(Mixed(ds)) along a random (δf°, δϕ°) (runtests.jl:615-616), with non-trivial mixing matrices D, G."""
+    sim = O.make_dataset(32, 32, 3.0, pol=pol, T=np.float64, nb=1, seed=4, nsteps=5, beam_fwhm=3.0)
+    ds, proj = sim["ds"], sim["proj"]
+    rng = np.random.default_rng(1)
+    ds.D = (1.0 + 0.5 * rng.random(ds.Cf[:, :ds.npol].shape)) if pol != "IP" else (1.0 + 0.5 * rng.random((1, 3) + proj.fourier_shape))
+    ds.G = 1.0 + 0.5 * rng.random((1, 1) + proj.fourier_shape)
+    f, phi = sim["f"], sim["phi"]
+    fm, pm = O.mix(ds, proj, pol, f, phi, D=ds.D, G=ds.G, nsteps=5)
+    assert np.allclose(O.logpdf(ds, f, phi), O.logpdf_mixed(ds, fm, pm), rtol=3e-4)
+    dfm = O.to_lense_basis(ds, proj, O.op_sqrt_mul(pol, ds.Cf, O.to_harmonic_basis(ds, proj, rng.standard_normal((1, ds.npol) + proj.map_shape))))
+    dpm = O.simulate_diag(proj, ds.Cphi, rng, 1)
+    for bug, tol in ((False, 5e-4), (True, 2e-2)):           # RK4 pullback = continuous adjoint, O(h⁴) from the exact discrete one; the aliased 2×2 product of the reference perturbs ∇ϕ (SURVEY Q3)
+        gf, gp = O.gradient_logpdf_mixed(ds, fm, pm, bug_compat=bug)
+        an = float(O.dot_fourier(proj, gf, O.rfft2(dfm)).sum() + O.dot_fourier(proj, gp, dpm).sum())
+        eps = 1e-3
+        fd = float((O.logpdf_mixed(ds, fm + eps * dfm, pm + eps * dpm) - O.logpdf_mixed(ds, fm - eps * dfm, pm - eps * dpm)).sum()) / (2 * eps)
+        assert abs(an - fd) <= tol * abs(fd) + 1e-6, (bug, an, fd)
+
+
+def test_map_joint_increases_posterior():
+    sim = O.make_dataset(32, 32, 3.0, pol="P", T=np.float64, nb=1, seed=6, nsteps=5, mask_border_deg=0.3)
+    ds = sim["ds"]
+    f, phi, hist = O.MAP_joint(ds, nsteps=3, conjgrad_kwargs=dict(tol=1e-1, nsteps=200))
+    lp = [float(h["logpdf"].sum()) for h in hist]
+    assert lp[1] > lp[0] and lp[2] > lp[1] and all(h["alpha"] > 0 for h in hist)
+    assert np.abs(phi).max() > 0 and np.all(np.isfinite(phi)) and np.all(np.isfinite(f))
