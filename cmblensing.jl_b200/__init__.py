@@ -371,16 +371,29 @@ Cl_to_Cov = Cℓ_to_Cov
 # LenseFlow (src/lenseflow.jl:19-60, src/flowops.jl:11-14)
 # ------------------------------------------------------------------------------------------------------------------
 class CachedLenseFlow:
+    """CachedLenseFlow (src/lenseflow.jl:33-60): the library handle that owns the p (and M⁻¹) cache and the RK scratch.
+    `precompute(ϕ)` refills the SAME device memory for a new ϕ — the reference's `precompute!!`, which re-caches only when
+    `ϕ !== old` (src/lenseflow.jl:80-129) — so a line search or a sampler that moves ϕ never reallocates the multi-GB cache."""
+
     def __init__(self, ϕ: Field, n: int, Npol: int, Nb_f: int, with_minv=False):
         if ϕ.Npol != 1:
             raise CmblError("ϕ must be a spin-0 field")
         p = ϕ.proj
-        self.proj, self.n, self.Npol, self.Nb_f, self.Nb_ϕ, self.ϕ = p, n, Npol, Nb_f, ϕ.Nbatch, ϕ
+        self.proj, self.n, self.Npol, self.Nb_f, self.Nb_ϕ, self.ϕ = p, n, Npol, Nb_f, ϕ.Nbatch, None
         self.handle = c_void_p()
-        p.lib.call("cmbl_lenseflow_create", byref(self.handle), p.handle, n, Npol, Nb_f, ϕ.Nbatch)
-        p.lib.call("cmbl_lenseflow_precompute", self.handle, _ptr(ϕ.arr), FOURIER if ϕ.is_fourier else MAP,
-                   1 if with_minv else 0, _stream(ϕ.arr))
         self.with_minv = with_minv
+        p.lib.call("cmbl_lenseflow_create", byref(self.handle), p.handle, n, Npol, Nb_f, ϕ.Nbatch)
+        self.precompute(ϕ)
+
+    def precompute(self, ϕ: Field):
+        if ϕ is self.ϕ:
+            return self
+        if ϕ.Nbatch != self.Nb_ϕ or ϕ.proj is not self.proj:
+            raise CmblError("precompute!!: ϕ does not match the cached LenseFlow (batch size / metadata)")
+        self.proj.lib.call("cmbl_lenseflow_precompute", self.handle, _ptr(ϕ.arr), FOURIER if ϕ.is_fourier else MAP,
+                           1 if self.with_minv else 0, _stream(ϕ.arr))
+        self.ϕ = ϕ
+        return self
 
     def __del__(self):
         try:
@@ -412,20 +425,29 @@ class CachedLenseFlow:
         return Δ._like(δf), Field("Fourier", δϕ, p)
 
 
+_FLOW_POOL_MAX = 6
+_FLOW_POOL: dict = {}        # (proj, n, Npol, Nb_f, Nb_ϕ, with_minv) -> CachedLenseFlow: one device cache per shape, refilled per ϕ
+
+
 class LenseFlow:
-    """LenseFlow(ϕ, n=7): lazy wrapper; the cache is (re)built when first applied to a field of a new shape
-    (precompute!!, src/lenseflow.jl:80-129)."""
+    """LenseFlow(ϕ, n=7): lazy wrapper.  Applying it fetches the cached handle for the field's shape and (re)fills it for this
+    ϕ when it currently holds another one (precompute!!, src/lenseflow.jl:80-129): handles are pooled per shape, so distinct
+    LenseFlow(ϕ) objects of the same shape share one p-cache allocation."""
 
     def __init__(self, ϕ: Field, n: int = 7):
-        self.ϕ, self.n, self._cache = ϕ, n, {}
+        self.ϕ, self.n = ϕ, n
 
     def cache(self, f: Field, with_minv=False) -> CachedLenseFlow:
-        key = (f.Npol, f.Nbatch, with_minv)
-        if key not in self._cache:
-            if self.ϕ.Nbatch not in (1, f.Nbatch):
-                raise CmblError("batch sizes must be equal or 1")
-            self._cache[key] = CachedLenseFlow(self.ϕ, self.n, f.Npol, f.Nbatch, with_minv)
-        return self._cache[key]
+        if self.ϕ.Nbatch not in (1, f.Nbatch):
+            raise CmblError("batch sizes must be equal or 1")
+        key = (id(self.ϕ.proj), self.n, f.Npol, f.Nbatch, self.ϕ.Nbatch, bool(with_minv))
+        c = _FLOW_POOL.pop(key, None)
+        if c is None:
+            c = CachedLenseFlow(self.ϕ, self.n, f.Npol, f.Nbatch, with_minv)
+        _FLOW_POOL[key] = c                                                   # most recently used last
+        while len(_FLOW_POOL) > _FLOW_POOL_MAX:
+            _FLOW_POOL.pop(next(iter(_FLOW_POOL)))                            # handles still referenced elsewhere stay alive
+        return c.precompute(self.ϕ)
 
     def __mul__(self, f): return self.cache(f).apply(OP_L, f)                    # Lϕ * f
     def ldiv(self, f): return self.cache(f).apply(OP_LINV, f)                    # Lϕ \ f
@@ -458,24 +480,37 @@ class BaseDataSet:
         self._cg = {}
 
     def _solver(self, ϕ: Field):
-        key = id(ϕ)
-        if key in self._cg:
-            return self._cg[key]
+        """(CG handle, CachedLenseFlow, LenseFlow, ϕ).  The CG handle (diagonals, CG vectors) is built once per dataset and
+        reused for every ϕ: it references the pooled CachedLenseFlow, which is refilled in place for the ϕ at hand."""
         d = self.d
         p = d.proj
         L = self.L(ϕ, self.nsteps) if isinstance(self.L, type) else self.L
-        cache = L.cache(d)                                                    # keyed on (Npol, Nbatch)
+        cache = L.cache(d)                                                    # pooled per shape; precompute!! for L.ϕ
+        cur = self._cg.get("solver")
+        if cur is not None and cur[1] is cache:
+            self._cg["solver"] = (cur[0], cache, L, ϕ)
+            return self._cg["solver"]
         want = BlockDiagIEB if d.Npol == 3 else DiagOp
         for nm in ("Cf", "Cn", "Cnhat", "B", "Bhat", "Mf"):
             if not isinstance(getattr(self, nm), want):
                 raise CmblError(f"BaseDataSet.{nm} must be a {want.__name__} for {d.basis} data")
         desc = DatasetDesc(d.Npol, d.Nbatch, *(c_void_p(D._real.data_ptr()) for D in (self.Cf, self.Cn, self.Cnhat, self.B, self.Bhat, self.Mf)),
                            c_void_p(self.Mpix._real.data_ptr()) if self.Mpix is not None else c_void_p(0), _ptr(d.arr))
-        h = c_void_p()
-        p.lib.call("cmbl_cg_create", byref(h), cache.handle, byref(desc), _stream(d.arr))
-        self._cg.clear()
-        self._cg[key] = (h, cache, L, ϕ)
-        return self._cg[key]
+        h = _CgHandle(p.lib)
+        p.lib.call("cmbl_cg_create", byref(h.h), cache.handle, byref(desc), _stream(d.arr))
+        self._cg["owner"] = h                                                  # previous owner (if any) is released here
+        self._cg["solver"] = (h.h, cache, L, ϕ)
+        return self._cg["solver"]
+
+
+class _CgHandle:
+    """Owns a cmbl_cg* (≈10 field-sized device buffers): destroyed with the dataset that created it."""
+    def __init__(self, lib): self.lib, self.h = lib, c_void_p()
+    def __del__(self):
+        try:
+            if self.h: self.lib.call("cmbl_cg_destroy", self.h)
+        except Exception:
+            pass
 
 
 def mix(ds: BaseDataSet, f: Field, ϕ: Field):
