@@ -39,7 +39,7 @@ def algorithmic_bytes(s):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML poll every ~2 ms between begin()
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML poll every ~5 ms between begin()
     and end() (a 10-step timed region lasts < 100 ms — too short for `nvidia-smi -lms`, whose first sample arrives after
     ~1 s); falls back to one `nvidia-smi` query issued while the GPU is kept busy when NVML cannot be loaded."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
@@ -72,10 +72,9 @@ class ClockSampler:
                 self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def begin(self):
         if self.nv is not None:
@@ -87,6 +86,10 @@ class ClockSampler:
         if self.nv is not None:
             self._run = False
             self._thr.join()
+            try:
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            except Exception:
+                pass
 
     def smi_fallback(self):
         try:
@@ -102,7 +105,7 @@ class ClockSampler:
         sm = sorted(self.sm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b),
                 "samples": len(sm), "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(self.power) if self.power else None,
-                "source": "NVML poll (2 ms) inside the timed region"}
+                "source": "NVML poll (5 ms) inside the timed region"}
 
 
 def measured_peak():
@@ -151,7 +154,7 @@ def reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

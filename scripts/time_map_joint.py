@@ -31,7 +31,8 @@ else:
     Mf = pkg.Cℓ_to_Cov("P", proj, lb, wl, wl, units=1)
     B = pkg.Cℓ_to_Cov("P", proj, ell, one, one, units=1)
 Cϕ = pkg.Cℓ_to_Cov("I", proj, ell, cls["pp"])
-Nϕ = pkg.DiagOp(pkg.Field("Fourier", Cϕ._real * 0 + float(Cϕ._real[Cϕ._real > 0].median()), proj))     # stand-in for quadratic_estimate(ds).Nϕ
+L_ = np.arange(2, 16000, dtype=float)      # stand-in for quadratic_estimate(ds).Nϕ: a flat [L(L+1)]²N_L/2π = 1e-8 plateau rising beyond L ~ 1500
+Nϕ = pkg.Cℓ_to_Cov("I", proj, L_, 2 * np.pi * 1e-8 / (L_ * (L_ + 1)) ** 2 * (1 + (L_ / 1500) ** 4))
 mask = torch.from_numpy(O.cosine_border_mask(O.ProjLambert(N, N, 2.0, np.float32 if dtype == "f32" else np.float64), 1.0))
 Mpix = pkg.DiagOp(pkg.Field(lense, mask[None, None].expand(1, npol, N, N).contiguous(), proj))
 ϕ_true = pkg.DiagOp(pkg.Field("Fourier", torch.sqrt(Cϕ._real), proj)) * w(1)
