@@ -29,7 +29,7 @@ __all__ = [
     "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "BlockDiagIEB", "dot", "BaseDataSet", "gradientf_logpdf",
     "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
     "Cℓ_to_2D", "Cℓ_to_Cov", "Cl_to_Cov", "simulate", "sample_f", "convert",
-    "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint",
+    "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint", "symplectic_integrate", "hmc_step", "mass_matrix_ϕ", "gibbs_sample_ϕ",
     "CmblError", "load",
 ]
 
@@ -820,3 +820,58 @@ def MAP_joint(ds: BaseDataSet, ϕstart: Field | None = None, nsteps: int = 20, f
     finally:
         ds.G = G_save
     return f, ϕ, history
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# HMC step in ϕ° of the Gibbs sampler `sample_joint` (src/sampling.jl:14-55,397-425).  Host control flow; every leap-frog step
+# costs one gradient of logpdf(Mixed(ds)) = two flows + two δ-flows on the device.
+# ------------------------------------------------------------------------------------------------------------------
+def symplectic_integrate(x0: Field, p0: Field, Λ: DiagOp, U, δUδx, N: int = 50, ϵ: float = 0.1):
+    """symplectic_integrate(x₀, p₀, Λ, U, δUδx; N, ϵ) (src/sampling.jl:14-55): leap-frog on the log-density U with mass matrix Λ,
+    H = U − p·(Λ\\p)/2.  Returns (ΔH per batch item, x, p)."""
+    H = lambda x, p: U(x) - dot(p, Λ.ldiv(p)) / 2
+    x, p = x0, p0
+    g = δUδx(x)
+    for _ in range(N):
+        x1 = x - Λ.ldiv(p - g * (ϵ / 2)) * ϵ
+        g1 = δUδx(x1)
+        p = p - (g1 + g) * (ϵ / 2)
+        x, g = x1, g1
+    return H(x, p) - H(x0, p0), x, p
+
+
+def mass_matrix_ϕ(ds: BaseDataSet) -> DiagOp:
+    """mass_matrix_ϕ(θ, ds) = pinv(G)² (pinv(Cϕ) + pinv(Nϕ)) (src/sampling.jl:422-425)."""
+    if ds.Cϕ is None or ds.Nϕ is None:
+        raise CmblError("mass_matrix_ϕ needs BaseDataSet(..., Cϕ=..., Nϕ=...)")
+    m = ds.Cϕ.pinv()._real + ds.Nϕ.pinv()._real
+    if ds.G is not None:
+        m = ds.G.pinv()._real ** 2 * m
+    p = ds.d.proj
+    return DiagOp(Field("Fourier", m.to(p.cT), p))
+
+
+def hmc_step(U, x: Field, Λ: DiagOp, δUδx, symp_kwargs=(dict(N=25, ϵ=0.01),), always_accept=False, white: Field | None = None,
+             uniforms=None, generator=None):
+    """hmc_step (src/sampling.jl:405-418): draw p ~ N(0, Λ), integrate, accept per batch item with probability min(1, e^ΔH).
+    `white` (unit white Map field) and `uniforms` (one U(0,1) per batch item) may be passed in for reproducibility."""
+    pr = x.proj
+    ΔH = accept = None
+    for kw in symp_kwargs:
+        w = white if white is not None else Field("Map", torch.randn(pr.map_shape(1, x.Nbatch), dtype=pr.T, device=pr.device, generator=generator), pr)
+        p0 = DiagOp(Field("Fourier", torch.sqrt(Λ._real).to(pr.cT), pr)) * Fourier(w)          # simulate(rng, Λ)
+        ΔH, xtest, _ = symplectic_integrate(x, p0, Λ, U, δUδx, **kw)
+        u = np.asarray(uniforms, dtype=np.float64) if uniforms is not None else torch.rand(x.Nbatch, generator=None).double().numpy()
+        accept = np.logical_or(always_accept, np.log(u) < ΔH)
+        a = accept.astype(np.float64)
+        x = xtest * a + x * (1 - a)
+    return x, ΔH, accept
+
+
+def gibbs_sample_ϕ(ds: BaseDataSet, f_mixed: Field, ϕ_mixed: Field, symp_kwargs=(dict(N=25, ϵ=0.01),), always_accept=False,
+                   white: Field | None = None, uniforms=None, bug_compat: bool = True):
+    """gibbs_sample_ϕ! (src/sampling.jl:397-403): one HMC update of ϕ° at fixed f° under logpdf(Mixed(ds))."""
+    mds = Mixed(ds)
+    U = lambda x: logpdf(mds, f_mixed, x)
+    δU = lambda x: gradient_logpdf_mixed(ds, f_mixed, x, bug_compat)[1]
+    return hmc_step(U, Fourier(ϕ_mixed), mass_matrix_ϕ(ds), δU, symp_kwargs, always_accept, white, uniforms)

@@ -713,6 +713,46 @@ def MAP_joint(ds: DataSet, nsteps: int = 5, conjgrad_kwargs=dict(tol=1e-1, nstep
 
 
 # ----------------------------------------------------------------------------------------------
+# HMC step in ϕ° of the Gibbs sampler (src/sampling.jl:14-55 symplectic_integrate, :397-425 gibbs_sample_ϕ!, hmc_step, mass_matrix_ϕ)
+# ----------------------------------------------------------------------------------------------
+def symplectic_integrate(x0, p0, Lam, U, dUdx, dot, N: int = 50, eps: float = 0.1):
+    """src/sampling.jl:14-55: leap-frog with mass matrix Λ on the *log-density* U (H = U − p·Λ⁻¹p/2).  Returns (ΔH, x, p)."""
+    bc = lambda v: np.asarray(v).reshape((-1,) + (1,) * (x0.ndim - 1))
+    T = x0.real.dtype.type
+    H = lambda x, p: U(x) - dot(p, diag_ldiv(Lam, p)) / 2
+    x, p = x0, p0
+    g = dUdx(x)
+    for _ in range(N):
+        x1 = (x - T(eps) * diag_ldiv(Lam, p - T(eps) / 2 * g)).astype(x0.dtype)
+        g1 = dUdx(x1)
+        p = (p - T(eps) / 2 * (g1 + g)).astype(x0.dtype)
+        x, g = x1, g1
+    return H(x, p) - H(x0, p0), x, p
+
+
+def mass_matrix_phi(ds: DataSet) -> np.ndarray:
+    """mass_matrix_ϕ (src/sampling.jl:422-425): pinv(G)² (pinv(Cϕ) + pinv(Nϕ))."""
+    m = pinv_diag(ds.Cphi) + pinv_diag(ds.Nphi)
+    return m if ds.G is None else (pinv_diag(ds.G) ** 2 * m).astype(m.dtype)
+
+
+def hmc_step_phi(ds: DataSet, f_mixed_map, phi_mixed, white_map, uniforms, N: int = 25, eps: float = 0.01, always_accept: bool = False,
+                 bug_compat: bool = True):
+    """gibbs_sample_ϕ! / hmc_step (src/sampling.jl:397-417) with the momentum draw p = √Λ·rfft(white) and the accept draws given
+    explicitly.  Returns (ϕ°, ΔH per batch item, accept)."""
+    proj = ds.proj
+    Lam = mass_matrix_phi(ds)
+    dot = lambda a, b: dot_fourier(proj, a, b)
+    U = lambda x: logpdf_mixed(ds, f_mixed_map, x)
+    dU = lambda x: gradient_logpdf_mixed(ds, f_mixed_map, x, bug_compat)[1]
+    p0 = (np.sqrt(Lam) * rfft2(white_map)).astype(proj.cT)
+    dH, xt, _ = symplectic_integrate(phi_mixed, p0, Lam, U, dU, dot, N, eps)
+    accept = np.logical_or(always_accept, np.log(uniforms) < dH)
+    a = accept.astype(proj.T).reshape(-1, 1, 1, 1)
+    return (a * xt + (1 - a) * phi_mixed).astype(proj.cT), dH, accept
+
+
+# ----------------------------------------------------------------------------------------------
 # Synthetic flat-sky inputs (harness; mirrors load_sim defaults, src/dataset.jl:186-338)
 # ----------------------------------------------------------------------------------------------
 def load_fiducial_cls(path=None):

@@ -55,3 +55,9 @@ f_m, ϕ_m = pkg.mix(ds, f, ϕ)
 torch.cuda.synchronize(); t0 = time.perf_counter(); gf, gp = pkg.gradient_logpdf_mixed(ds, f_m, ϕ_m); torch.cuda.synchronize(); tg = time.perf_counter() - t0
 t0 = time.perf_counter(); lp = pkg.logpdf(pkg.Mixed(ds), f_m, ϕ_m); torch.cuda.synchronize(); tl = time.perf_counter() - t0
 print(f"   gradient of logpdf(Mixed) (2 flows + 2 δ-flows): {tg*1e3:.1f} ms;  one logpdf(Mixed) evaluation (precompute + 2 flows): {tl*1e3:.1f} ms")
+# one HMC update of ϕ° (src/sampling.jl:397-417): N leap-frog steps, each one gradient of logpdf(Mixed(ds))
+NL = 5
+torch.cuda.synchronize(); t0 = time.perf_counter()
+x, ΔH, acc = pkg.gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs=(dict(N=NL, ϵ=0.002),), always_accept=False)
+torch.cuda.synchronize(); th = time.perf_counter() - t0
+print(f"   HMC ϕ° update, {NL} leap-frog steps: {th*1e3:.0f} ms = {NL/th:.1f} leap-frog steps/s for the batch of {NB} ({NB*NL/th:.1f} chain-steps/s); ΔH = {np.round(ΔH, 3)}, accept = {acc}")

@@ -201,6 +201,23 @@ def test_logpdf_mixed_gradient_and_map_joint(cuda_pkg, pol):
     assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum()
 
 
+def test_hmc_step_phi(cuda_pkg):
+    """gibbs_sample_ϕ! / hmc_step / symplectic_integrate (src/sampling.jl:14-55,397-425) on the device vs the oracle, same draws."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, 64, 64, "P", "f64", nb=2, nsteps=5, mask=True, seed=14, theta=3.0, device=DEV)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    rng = np.random.default_rng(5)
+    Gn = 1.0 + 0.5 * rng.random((1, 1) + oproj.fourier_shape)
+    dso.G = Gn; ds.G = pkg.DiagOp(pr["F"](Gn, "Fourier"))
+    fm, pm = pkg.mix(ds, pr["f"], pr["phi"])
+    fmo, pmo = O.mix(dso, oproj, "P", pr["sim"]["f"], pr["sim"]["phi"], D=None, G=Gn, nsteps=5)
+    w = rng.standard_normal((2, 1) + oproj.map_shape); u = np.array([0.3, 0.999999])
+    x, dH, acc = pkg.gibbs_sample_ϕ(ds, fm, pm, symp_kwargs=(dict(N=3, ϵ=0.002),), white=pr["F"](w, "Map"), uniforms=u)
+    xo, dHo, acco = O.hmc_step_phi(dso, fmo, pmo, w, u, N=3, eps=0.002)
+    assert np.allclose(dH, dHo, rtol=1e-6, atol=1e-7 * np.abs(O.logpdf_mixed(dso, fmo, pmo)).max()) and np.array_equal(acc, acco)
+    assert relerr(x.cpu_numpy(), xo) < 1e-8
+
+
 def test_cg_converges_and_stops_like_reference(cuda_pkg):
     pkg = cuda_pkg
     pr = make_problem(pkg, 64, 64, "P", "f64", nb=2, nsteps=7, mask=True, seed=9, theta=3.0, device=DEV)

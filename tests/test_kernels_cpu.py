@@ -274,6 +274,24 @@ def test_logpdf_mixed_gradient_and_map_joint(pkg, emu, pol):
     assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum()
 
 
+def test_hmc_step_phi(pkg, emu):
+    """gibbs_sample_ϕ! / hmc_step / symplectic_integrate (src/sampling.jl:14-55,397-425) with the same momentum and accept draws
+    as the oracle; the leap-frog nearly conserves H for a small step."""
+    pr = make_problem(pkg, 32, 32, "P", "f64", nb=2, nsteps=4, mask=True, seed=14, theta=3.0, lib=emu)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    rng = np.random.default_rng(5)
+    Gn = 1.0 + 0.5 * rng.random((1, 1) + oproj.fourier_shape)
+    dso.G = Gn; ds.G = pkg.DiagOp(pr["F"](Gn, "Fourier"))
+    fm, pm = pkg.mix(ds, pr["f"], pr["phi"])
+    fmo, pmo = O.mix(dso, oproj, "P", pr["sim"]["f"], pr["sim"]["phi"], D=None, G=Gn, nsteps=4)
+    w = rng.standard_normal((2, 1) + oproj.map_shape); u = np.array([0.3, 0.999999])
+    x, dH, acc = pkg.gibbs_sample_ϕ(ds, fm, pm, symp_kwargs=(dict(N=3, ϵ=0.005),), white=pr["F"](w, "Map"), uniforms=u)
+    xo, dHo, acco = O.hmc_step_phi(dso, fmo, pmo, w, u, N=3, eps=0.005)
+    assert np.allclose(dH, dHo, rtol=1e-6, atol=1e-7 * np.abs(O.logpdf_mixed(dso, fmo, pmo)).max()) and np.array_equal(acc, acco)
+    assert relerr(x.cpu_numpy(), xo) < 1e-8
+    assert np.all(np.abs(dH) < 5.0)                                # |ΔH| ≪ |H| ~ 1e5: the integrator is symplectic
+
+
 def test_cg_stops_on_tol_like_reference(pkg, emu):
     pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=emu)
     _, h0 = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=0.0)
