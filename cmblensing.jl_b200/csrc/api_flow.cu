@@ -72,7 +72,7 @@ struct HostPipe {
         }
     }
 };
-int host_chunks() { static const int v = [] { const char* e = getenv("CMBL_HOST_CHUNKS"); return e ? atoi(e) : 2; }(); return v; }
+int host_chunks() { static const int v = [] { const char* e = getenv("CMBL_HOST_CHUNKS"); return e ? atoi(e) : 3; }(); return v; }
 }  // namespace
 #endif
 
@@ -94,7 +94,7 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
         cudaStream_t st = as_stream(stream);
         int nch = host_chunks();
         if (nch > F.Nb) nch = F.Nb;
-        if (four || nch <= 1) {
+        if (four || nch <= 1 || !F.integrated_once) {          // (first use of a handle: the serial path also allocates the work buffers)
             CMBL_CUDA(cudaMemcpyAsync(d, in_host, bytes, cudaMemcpyHostToDevice, st));
             cmbl::flow_apply<T>(F, op, d, d, st);
             cmbl::dev_download(out_host, d, bytes, st);
@@ -103,27 +103,39 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
             // H2D of items i+1.. on one copy stream, the integration of item group i on the caller's stream, D2H of finished
             // groups on a second copy stream (PCIe is full duplex) — instead of copy-in, compute, copy-out back to back.
             static thread_local HostPipe hp;
-            hp.ensure(nch);
-            const int n = F.nsteps, per = (F.Nb + nch - 1) / nch;
+            // group sizes: the first and the last group are the exposed transfers, so they are small (a quarter of the batch);
+            // the middle of the batch moves in larger groups that keep the persistent stage kernels filled
+            std::vector<int> sizes;
+            if (nch == 2 || F.Nb < 4) { const int per = (F.Nb + nch - 1) / nch; for (int b0 = 0; b0 < F.Nb; b0 += per) sizes.push_back(F.Nb - b0 < per ? F.Nb - b0 : per); }
+            else {
+                const int q = F.Nb / 4 > 0 ? F.Nb / 4 : 1, mid = F.Nb - 2 * q, nm = nch - 2, per = (mid + nm - 1) / nm;
+                sizes.push_back(q);
+                for (int b0 = 0; b0 < mid; b0 += per) sizes.push_back(mid - b0 < per ? mid - b0 : per);
+                sizes.push_back(q);
+            }
+            const int ng = (int)sizes.size();
+            hp.ensure(ng);
+            const int n = F.nsteps;
             const size_t plane_b = sizeof(T) * P.map_elems();
             const char* hin = static_cast<const char*>(in_host); char* hout = static_cast<char*>(out_host); char* dd = static_cast<char*>(d);
             CMBL_CUDA(cudaEventRecord(hp.ev_start, st));                       // the staging buffer is free once earlier work on `st` is done
             CMBL_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_start, 0));
-            int nused = 0;
-            for (int b0 = 0; b0 < F.Nb; b0 += per, ++nused) {
-                const int nb = (F.Nb - b0 < per) ? F.Nb - b0 : per;
-                const size_t off = plane_b * (size_t)b0 * F.Npol, cb = plane_b * (size_t)nb * F.Npol;
+            // All groups integrate on the caller's stream, one after another.  (Integrating consecutive groups on two streams was
+            // measured and rejected: the persistent column kernel's blocks wait on flags published by other blocks of the same
+            // launch, which is only safe while every block of a launch is resident — two concurrent launches break that and
+            // were seen to stall for seconds.)
+            for (int i = 0, b0 = 0; i < ng; b0 += sizes[i], ++i) {
+                const size_t off = plane_b * (size_t)b0 * F.Npol, cb = plane_b * (size_t)sizes[i] * F.Npol;
                 CMBL_CUDA(cudaMemcpyAsync(dd + off, hin + off, cb, cudaMemcpyHostToDevice, hp.s_in));
-                CMBL_CUDA(cudaEventRecord(hp.ev_in[nused], hp.s_in));
+                CMBL_CUDA(cudaEventRecord(hp.ev_in[i], hp.s_in));
             }
-            int i = 0;
-            for (int b0 = 0; b0 < F.Nb; b0 += per, ++i) {
-                const int nb = (F.Nb - b0 < per) ? F.Nb - b0 : per;
-                const size_t off = plane_b * (size_t)b0 * F.Npol, cb = plane_b * (size_t)nb * F.Npol;
-                CMBL_CUDA(cudaStreamWaitEvent(st, hp.ev_in[i], 0));
+            for (int i = 0, b0 = 0; i < ng; b0 += sizes[i], ++i) {
+                const size_t off = plane_b * (size_t)b0 * F.Npol, cb = plane_b * (size_t)sizes[i] * F.Npol;
+                cudaStream_t sc = st;
+                CMBL_CUDA(cudaStreamWaitEvent(sc, hp.ev_in[i], 0));
                 cmbl::flow_integrate_range<T>(F, false, reinterpret_cast<T*>(d), op == CMBL_OP_L ? 0 : 2 * n, op == CMBL_OP_L ? 2 * n : 0,
-                                              b0 * F.Npol, nb * F.Npol, st);
-                CMBL_CUDA(cudaEventRecord(hp.ev_done[i], st));
+                                              b0 * F.Npol, sizes[i] * F.Npol, sc);
+                CMBL_CUDA(cudaEventRecord(hp.ev_done[i], sc));
                 CMBL_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_done[i], 0));
                 CMBL_CUDA(cudaMemcpyAsync(hout + off, dd + off, cb, cudaMemcpyDeviceToHost, hp.s_out));
             }

@@ -204,6 +204,7 @@ template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* ycaller, 
         kk += 2 * sgn;
     }
     if (G) convert_layout<T, false>(P, G, y + (size_t)c0 * nmap, ycaller + (size_t)c0 * nmap, nC, st);
+    F.integrated_once = true;
 }
 
 template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st) {

@@ -327,6 +327,7 @@ template <class T> struct FlowT : FlowBase {
     PlanT<T>* P = nullptr;
     int nsteps = 7, Npol = 1, Nb = 1, Nbphi = 1, C = 1;
     bool have_p = false, have_minv = false;
+    bool integrated_once = false;       // every lazily allocated work buffer of the stage kernels exists (set by flow_integrate_range)
     int pcache_G = 0;                    // layout of pcache / minv: 0 = reference layout, else rows per row group
     DevBuf yrg;                          // row-grouped copy of the ODE state
     DevBuf g_yf, g_yd, g_yp, g_uf, g_ud, g_up, g_af, g_ad, g_ap, g_kf, g_kd, g_kp, g_ldf, g_gxy, g_a12, g_six, g_spec, g_spec2;   // δ-flow scratch (flow_grad.cu)

@@ -93,7 +93,8 @@ int cmbl_lenseflow_apply(cmbl_flow* flow, int op, const void* in, void* out, voi
 /* same, HOST buffers, copies included (the end-to-end path bench.py times).  Returns when out_host is valid.  For the
  * map-space flows (ops 0, 2) the batch items are pipelined: H2D of the next item group, integration of the current one and
  * D2H of the finished one overlap on separate streams (pin the host buffers to get the overlap; CMBL_HOST_CHUNKS = number
- * of groups, default 2 — measured best at Nside=1024 batch 8: smaller groups under-fill the persistent stage kernels —, 1 = copy-in / compute / copy-out back to back). */
+ * of groups, default 3 = a quarter / half / quarter of the batch: the first and last group are the exposed transfers, the
+ * middle one keeps the persistent stage kernels filled; 1 = copy-in / compute / copy-out back to back). */
 int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream);
 /* pullback through Lϕ*f (op 0) or Lϕ\f (op 2): negδvelocityᴴ transpose flow (src/lenseflow.jl:176-214, src/flowops.jl:40-68).
  * f_out_map = the forward result (Map), delta = cotangent (Fourier). Outputs: dfield (Fourier, C planes), dphi (Fourier,
