@@ -2,41 +2,65 @@
 
 namespace cmbl {
 
+// Planes per pass pair.  The two 1-D passes of a 2-D transform exchange a half-plane spectrum per plane; transforming a few
+// planes at a time keeps that intermediate (and, for irfft2, a scratch buffer reused by every group) inside the 126 MB L2.
+// Measured on B200 at Nside=1024, 16 planes (profiles/r01_fft_chunk.log): it does NOT pay — these kernels are bound by their
+// load → transform → store structure, not by DRAM (16 planes at once 160 µs per pass; 2-plane groups 8 × 33 µs) — so the
+// default is all planes in one pass pair.  CMBL_FFT_CHUNK_MB = spectrum bytes per group (0 = all planes).
+template <class T> static int fft_chunk_planes(const PlanT<T>& P, int C) {
+    static const int mb = [] { const char* e = getenv("CMBL_FFT_CHUNK_MB"); return e ? atoi(e) : 0; }();
+    if (mb <= 0) return C;
+    const size_t per = sizeof(C2<T>) * P.four_elems();
+    int n = (int)(((size_t)mb << 20) / per);
+    if (n < 1) n = 1;
+    return n < C ? n : C;
+}
+
 template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmblStream_t st) {
     if (C <= 0) return;
-    {
-        R2CColBody<T> b;
-        b.fy = P.ay.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh;
-        b.L = col_lines<T>(P.ay.fft, P.Nx); b.tiles_per_plane = P.Nx / (2 * b.L);
-        b.in = map; b.out = four;
-        launch(b, C * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
-    }
-    {
-        C2CRowBody<T, false> b;
-        b.fx = P.ax.fft; b.Nx = P.Nx; b.Nyh = P.Nyh;
-        b.L = row_lines<T>(P.Nx, P.Nyh); b.tiles_per_plane = (P.Nyh + b.L - 1) / b.L;
-        b.in = four; b.out = four;
-        launch(b, C * b.tiles_per_plane, Tile<T, true>::bytes(P.Nx, b.L, 0), st);
+    const int chunk = fft_chunk_planes(P, C);
+    for (int c0 = 0; c0 < C; c0 += chunk) {
+        const int nC = (C - c0 < chunk) ? C - c0 : chunk;
+        const T* in = map + (size_t)c0 * P.map_elems();
+        C2<T>* out = four + (size_t)c0 * P.four_elems();
+        {
+            R2CColBody<T> b;
+            b.fy = P.ay.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh;
+            b.L = col_lines<T>(P.ay.fft, P.Nx); b.tiles_per_plane = P.Nx / (2 * b.L);
+            b.in = in; b.out = out;
+            launch(b, nC * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
+        }
+        {
+            C2CRowBody<T, false> b;
+            b.fx = P.ax.fft; b.Nx = P.Nx; b.Nyh = P.Nyh;
+            b.L = row_lines<T>(P.Nx, P.Nyh); b.tiles_per_plane = (P.Nyh + b.L - 1) / b.L;
+            b.in = out; b.out = out;
+            launch(b, nC * b.tiles_per_plane, Tile<T, true>::bytes(P.Nx, b.L, 0), st);
+        }
     }
 }
 
 template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st) {
     if (C <= 0) return;
-    C2<T>* scratch = reinterpret_cast<C2<T>*>(P.scratch_four.reserve(sizeof(C2<T>) * P.four_elems() * (size_t)C));
-    {
-        C2CRowBody<T, true> b;
-        b.fx = P.ax.fft; b.Nx = P.Nx; b.Nyh = P.Nyh;
-        b.L = row_lines<T>(P.Nx, P.Nyh); b.tiles_per_plane = (P.Nyh + b.L - 1) / b.L;
-        b.in = four; b.out = scratch;
-        launch(b, C * b.tiles_per_plane, Tile<T, true>::bytes(P.Nx, b.L, 0), st);
-    }
-    {
-        C2RColBody<T> b;
-        b.fy = P.ay.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh;
-        b.L = col_lines<T>(P.ay.fft, P.Nx); b.tiles_per_plane = P.Nx / (2 * b.L);
-        b.scale = (T)1 / ((T)P.Ny * (T)P.Nx);
-        b.in = scratch; b.out = map;
-        launch(b, C * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
+    const int chunk = fft_chunk_planes(P, C);
+    C2<T>* scratch = reinterpret_cast<C2<T>*>(P.scratch_four.reserve(sizeof(C2<T>) * P.four_elems() * (size_t)chunk));   // reused by every group
+    for (int c0 = 0; c0 < C; c0 += chunk) {
+        const int nC = (C - c0 < chunk) ? C - c0 : chunk;
+        {
+            C2CRowBody<T, true> b;
+            b.fx = P.ax.fft; b.Nx = P.Nx; b.Nyh = P.Nyh;
+            b.L = row_lines<T>(P.Nx, P.Nyh); b.tiles_per_plane = (P.Nyh + b.L - 1) / b.L;
+            b.in = four + (size_t)c0 * P.four_elems(); b.out = scratch;
+            launch(b, nC * b.tiles_per_plane, Tile<T, true>::bytes(P.Nx, b.L, 0), st);
+        }
+        {
+            C2RColBody<T> b;
+            b.fy = P.ay.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh;
+            b.L = col_lines<T>(P.ay.fft, P.Nx); b.tiles_per_plane = P.Nx / (2 * b.L);
+            b.scale = (T)1 / ((T)P.Ny * (T)P.Nx);
+            b.in = scratch; b.out = map + (size_t)c0 * P.map_elems();
+            launch(b, nC * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
+        }
     }
 }
 
