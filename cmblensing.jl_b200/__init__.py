@@ -29,7 +29,7 @@ __all__ = [
     "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "BlockDiagIEB", "dot", "BaseDataSet", "gradientf_logpdf",
     "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
     "Cℓ_to_2D", "Cℓ_to_Cov", "Cl_to_Cov", "simulate", "sample_f", "convert",
-    "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint", "symplectic_integrate", "hmc_step", "mass_matrix_ϕ", "gibbs_sample_ϕ",
+    "quadratic_estimate", "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint", "symplectic_integrate", "hmc_step", "mass_matrix_ϕ", "gibbs_sample_ϕ",
     "CmblError", "load",
 ]
 
@@ -472,10 +472,12 @@ class BaseDataSet:
 
     def __init__(self, d: Field, Cf: DiagOp, Cn: DiagOp, B: DiagOp, Mf: DiagOp, Mpix: DiagOp | None = None,
                  Cnhat: DiagOp | None = None, Bhat: DiagOp | None = None, L=LenseFlow, nsteps: int = 7,
-                 D: DiagOp | None = None, G: DiagOp | None = None, Cϕ: DiagOp | None = None, Nϕ: DiagOp | None = None):
+                 D: DiagOp | None = None, G: DiagOp | None = None, Cϕ: DiagOp | None = None, Nϕ: DiagOp | None = None,
+                 Cf̃: DiagOp | None = None):
         self.d, self.Cf, self.Cn, self.B, self.Mf, self.Mpix = HarmonicBasis(d), Cf, Cn, B, Mf, Mpix
         self.Cnhat, self.Bhat, self.L, self.nsteps = Cnhat or Cn, Bhat or B, L, nsteps
         self.D, self.G = D, G                      # mixing matrices of the Mixed parametrisation (src/dataset.jl:96-117); None = identity
+        self.Cf̃ = Cf̃                              # lensed ("total") field covariance, used by quadratic_estimate (src/dataset.jl:270)
         self.Cϕ, self.Nϕ = Cϕ, Nϕ                  # ϕ prior and ϕ-noise estimate (logpdf, ϕ° Hessian preconditioner, src/dataset.jl:45-57,134-137)
         self._cg = {}
 
@@ -638,7 +640,7 @@ def simulate(ds: BaseDataSet, ϕ: Field, white_f: Field | None = None, white_n: 
     L = ds.L(ϕ, ds.nsteps) if isinstance(ds.L, type) else ds.L
     f̃ = L * f
     d = _apply_MB(ds, f̃) + n
-    return dict(f=f, f̃=f̃, ϕ=ϕ, d=d)
+    return {"f": f, "f̃": f̃, "ϕ": ϕ, "d": d}
 
 
 def sample_f(ds: BaseDataSet, ϕ: Field, white_f: Field | None = None, white_n: Field | None = None, generator=None,
@@ -875,3 +877,101 @@ def gibbs_sample_ϕ(ds: BaseDataSet, f_mixed: Field, ϕ_mixed: Field, symp_kwarg
     U = lambda x: logpdf(mds, f_mixed, x)
     δU = lambda x: gradient_logpdf_mixed(ds, f_mixed, x, bug_compat)[1]
     return hmc_step(U, Fourier(ϕ_mixed), mass_matrix_ϕ(ds), δU, symp_kwargs, always_accept, white, uniforms)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Quadratic estimate of ϕ and its analytic N⁰ (src/quadratic_estimate.jl:30-199): products of inverse-variance-filtered "legs"
+# in map space; every leg is one cmbl_irfft2, every product goes back through cmbl_rfft2.  A setup-time computation
+# (load_sim uses it once for Nϕ, src/dataset.jl:316), written with the host mirror's broadcast arithmetic like the reference's.
+# ------------------------------------------------------------------------------------------------------------------
+def quadratic_estimate(ds: BaseDataSet, which: str | None = None, wiener_filtered: bool = True, weights: str = "unlensed", AL: DiagOp | None = None,
+                       abs_each_term: bool = True):
+    """quadratic_estimate(ds, which; wiener_filtered, weights, AL) for which ∈ {TT, EE, EB}: returns dict(ϕqe, AL, Nϕ), Nϕ = AL.
+    `abs_each_term=True` is the reference's normalisation pinv(Σ_ij abs.(∇ᵢ∇ⱼ·Fourier(A(i,j)))) (:117,151,190), which under-normalises
+    EB by ≈40 % because the cross terms are not sign-definite; `False` takes |Σ_ij …| (unit response)."""
+    from itertools import product
+    if weights not in ("lensed", "unlensed"):
+        raise CmblError("weights should be lensed or unlensed")
+    d = ds.d
+    p = d.proj
+    which = which or ("TT" if d.Npol == 1 else "EB")
+    if which not in ("TT", "EE", "EB") or d.Npol != (1 if which == "TT" else 2):
+        raise CmblError(f"which='{which}' not implemented for {d.basis} data")
+    if ds.Cf̃ is None or ds.Cϕ is None:
+        raise CmblError("quadratic_estimate needs BaseDataSet(..., Cf̃=..., Cϕ=...)")
+    dev, cT = p.device, p.cT
+    lx = torch.from_numpy(p.ℓx).to(dev)[:, None]; ly = torch.from_numpy(p.ℓy).to(dev)[None, :]
+    grad = {1: (1j * lx).to(cT).expand(p.Nx, p.Nyh), 2: (1j * ly).to(cT).expand(p.Nx, p.Nyh)}
+    lmag = torch.from_numpy(p.ℓmag).to(dev)
+    nz = lambda t: torch.where(torch.isfinite(t.real) & (torch.isfinite(t.imag) if t.is_complex() else True), t, torch.zeros_like(t))
+    irf = lambda F: Map(Field("Fourier", F.to(cT), p)).arr                    # cmbl_irfft2
+    fou = lambda m: Fourier(Field("Map", m, p)).arr                           # cmbl_rfft2
+    memo = {}
+
+    def leg(C, *inds):                                                        # QE_leg (:84-93), memoised on (C, n, p₁, p₂)
+        n = sum(1 for x in inds if isinstance(x, int))
+        first = [x if isinstance(x, int) else x[0] for x in inds]
+        key = (id(C), n, first.count(1), first.count(2))
+        if key not in memo:
+            memo[key] = (irf(nz(C * grad[1] ** key[2] * grad[2] ** key[3] / lmag ** n)), C)
+        return memo[key][0]
+
+    eps = lambda a, b: 0 if a == b else (1 if (a, b) == (1, 2) else -1)      # levicivita([a, b, 3])
+    inds = lambda D: list(product((1, 2), repeat=D))
+    pinv = lambda t: torch.where(t == 0, torch.zeros_like(t), 1 / t)
+    ldiv = lambda S, x: nz(x / S)
+    sl = lambda A, c: A[:, c:c + 1]
+    TF = ds.Mf._real * ds.Bhat._real
+    Cf, Cft, Cn = ds.Cf._real, ds.Cf̃._real, ds.Cnhat._real
+    Cw = Cf if weights == "unlensed" else Cft
+
+    def norm(A):
+        terms = [grad[i] * grad[j] * fou(A(i, j)) for i, j in inds(2)]
+        tot = sum(t.abs() for t in terms) if abs_each_term else sum(terms).abs()
+        return pinv(tot.to(p.T))
+
+    if which == "TT":
+        S = TF ** 2 * Cft + Cn
+        a, b = ldiv(S, TF * d.arr), Cw * ldiv(S, TF * d.arr)
+        unnorm = -sum(grad[i] * fou(leg(a) * leg(b, [i])) for i in (1, 2))
+        if AL is None:
+            X2, X1, X0 = TF ** 2 * Cw ** 2 / S, TF ** 2 * Cw / S, TF ** 2 / S
+            ALr = norm(lambda i, j: leg(X2, [i], [j]) * leg(X0) + leg(X1, [i]) * leg(X1, [j]))
+    else:
+        TF2E, TF2B = sl(TF, 0) ** 2, sl(TF, 1) ** 2
+        SE, SB = TF2E * sl(Cft, 0) + sl(Cn, 0), TF2B * sl(Cft, 1) + sl(Cn, 1)
+        CE, CB = sl(Cw, 0), sl(Cw, 1)
+        tE, tB = sl(TF * d.arr, 0), sl(TF * d.arr, 1)
+        if which == "EE":
+            a1, b2 = CE * ldiv(SE, tE), ldiv(SE, tE)
+            I = lambda i: -(2 * sum(leg(a1, [i], j, k) * leg(b2, j, k) for j, k in inds(2)) - leg(a1, [i]) * leg(b2))
+            unnorm = sum(grad[i] * fou(I(i)) for i in (1, 2))
+            if AL is None:
+                X2, X1, X0 = TF2E * CE ** 2 / SE, TF2E * CE / SE, TF2E / SE
+                A1 = lambda i, j: -4 * sum(eps(m, q_) * eps(n, r_) * (leg(X2, [i], [j], k, l, m, n) * leg(X0, k, l, q_, r_)
+                                                                        + leg(X1, [i], k, l, m, n) * leg(X1, [j], k, l, q_, r_))
+                                           for k, l, m, n, q_, r_ in inds(6) if eps(m, q_) and eps(n, r_))
+                A2 = lambda i, j: leg(X2, [i], [j]) * leg(X0) + leg(X1, [i]) * leg(X1, [j])
+                ALr = norm(lambda i, j: A1(i, j) + A2(i, j))
+        else:
+            aE, aE0 = CE * ldiv(SE, tE), ldiv(SE, tE)
+            bB, bB0 = CB * ldiv(SB, tB), ldiv(SB, tB)
+            I = lambda i: 2 * sum(eps(k, l) * (leg(aE, [i], j, k) * leg(bB0, j, l) - leg(aE0, j, k) * leg(bB, [i], j, l))
+                                  for j, k, l in inds(3) if eps(k, l))
+            unnorm = sum(grad[i] * fou(I(i)) for i in (1, 2))
+            if AL is None:
+                XE2, XE1, XE0 = TF2E * CE ** 2 / SE, TF2E * CE / SE, TF2E / SE
+                XB2, XB1, XB0 = TF2B * CB ** 2 / SB, TF2B * CB / SB, TF2B / SB
+                A = lambda i, j: 4 * sum(eps(m, q_) * eps(n, r_) * (leg(XE2, [i], [j], k, l, m, n) * leg(XB0, k, l, q_, r_)
+                                                                    - 2 * leg(XE1, [i], k, l, m, n) * leg(XB1, [j], k, l, q_, r_)
+                                                                    + leg(XE0, k, l, m, n) * leg(XB2, [i], [j], k, l, q_, r_))
+                                         for k, l, m, n, q_, r_ in inds(6) if eps(m, q_) and eps(n, r_))
+                ALr = norm(A)
+    if AL is not None:
+        ALr = AL._real
+    ϕ = ALr * unnorm
+    if wiener_filtered:
+        Cp = ds.Cϕ._real
+        ϕ = Cp * pinv(Cp + ALr) * ϕ
+    ALop = DiagOp(Field("Fourier", ALr.to(cT), p))
+    return {"ϕqe": Field("Fourier", ϕ.to(cT), p), "AL": ALop, "Nϕ": ALop}      # string keys: identifiers would be NFKC-normalised (ϕ → φ)

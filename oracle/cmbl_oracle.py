@@ -468,6 +468,7 @@ class DataSet:
     Nphi: np.ndarray | None = None    # ϕ noise estimate used by the ϕ° Hessian preconditioner (src/dataset.jl:134-137)
     D: np.ndarray | None = None       # mixing matrices of the Mixed parametrisation (None = identity)
     G: np.ndarray | None = None
+    Cftilde: np.ndarray | None = None # lensed ("total") field covariance Cf̃ used by the quadratic estimate (src/dataset.jl:270)
 
     @property
     def npol(self):
@@ -713,6 +714,108 @@ def MAP_joint(ds: DataSet, nsteps: int = 5, conjgrad_kwargs=dict(tol=1e-1, nstep
 
 
 # ----------------------------------------------------------------------------------------------
+# Quadratic estimate of ϕ and its analytic N⁰ (src/quadratic_estimate.jl:30-199)
+# ----------------------------------------------------------------------------------------------
+class _QELegs:
+    """QE_leg (src/quadratic_estimate.jl:84-93): Map(nan2zero(C · ∇[1].diag^p₁ · ∇[2].diag^p₂ / sqrt(∇².diag)^n)) for an index list
+    in which a bracketed index [i] contributes the wave-vector factor iℓ_i and a plain index j the factor iℓ_j/|ℓ|; memoised on
+    (C, n, p₁, p₂) like the reference (all terms are symmetric in their indices)."""
+    def __init__(self, proj):
+        self.proj, self.memo = proj, {}
+        self.d1, self.d2 = grad_diag(proj, 1), grad_diag(proj, 2)
+        self.lmag = proj.lmag.astype(proj.T)
+
+    def __call__(self, C, *inds):
+        n = sum(1 for x in inds if isinstance(x, int))
+        first = [x if isinstance(x, int) else x[0] for x in inds]
+        p1, p2 = first.count(1), first.count(2)
+        key = (id(C), n, p1, p2)
+        if key not in self.memo:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                F = nan2zero(C * self.d1 ** p1 * self.d2 ** p2 / self.lmag ** n).astype(self.proj.cT)
+            self.memo[key] = (irfft2(F, self.proj.Ny), C)          # keep C alive so that id(C) stays unique
+        return self.memo[key][0]
+
+
+def _eps(a, b):          # levicivita([a, b, 3])
+    return 0 if a == b else (1 if (a, b) == (1, 2) else -1)
+
+
+def quadratic_estimate(ds: DataSet, which: str | None = None, wiener_filtered: bool = True, weights: str = "unlensed", AL=None, d2=None,
+                       abs_each_term: bool = True):
+    """quadratic_estimate(ds, which; wiener_filtered, weights, AL) (src/quadratic_estimate.jl:30-199) for which ∈ {TT, EE, EB}:
+    returns dict(phi_qe, AL, Nphi) with Nϕ = AL.  Only the Fourier-diagonal B̂, M̂, Cn̂ enter (TF = M̂·B̂), as in the reference.
+    `abs_each_term=True` reproduces the reference's normalisation `pinv(Σ_ij abs.(∇ᵢ∇ⱼ·Fourier(A(i,j))))` (:117,151,190), which takes
+    the absolute value of every (i,j) term before summing; the cross terms are not sign-definite, so for EB this under-normalises
+    the estimate by ≈40 % (measured response 0.53–0.62; tests/test_oracle.py).  `False` uses |Σ_ij …|, whose response is 1."""
+    from itertools import product
+    proj, pol = ds.proj, ds.pol
+    assert weights in ("lensed", "unlensed")
+    which = which or ("TT" if pol == "I" else "EB")
+    assert which in ("TT", "EE", "EB") and pol in (("I",) if which == "TT" else ("P",))
+    leg = _QELegs(proj)
+    grad = {1: leg.d1, 2: leg.d2}
+    TF = ds.Mf * ds.Bhat
+    d1 = ds.d
+    d2 = d1 if d2 is None else d2
+    inds = lambda D: list(product((1, 2), repeat=D))
+    div = lambda a, b: (np.divide(a, b, out=np.full(np.broadcast_shapes(a.shape, b.shape), np.nan, dtype=np.result_type(a, b)), where=(b != 0)))
+    sl = lambda A, c: A[:, c:c + 1]
+    fou = lambda m: rfft2(m.astype(proj.T))
+    def norm(A):
+        terms = [grad[i] * grad[j] * fou(A(i, j)) for i, j in inds(2)]
+        tot = sum(np.abs(t) for t in terms) if abs_each_term else np.abs(sum(terms))
+        return pinv_diag(tot.astype(proj.T))
+    if which == "TT":
+        S = TF ** 2 * ds.Cftilde + ds.Cnhat
+        CT = ds.Cf if weights == "unlensed" else ds.Cftilde
+        a, b = diag_ldiv(S, TF * d1), CT * diag_ldiv(S, TF * d2)
+        unnorm = -sum(grad[i] * fou(leg(a) * leg(b, [i])) for i in (1, 2))
+        if AL is None:
+            X2, X1, X0 = div(TF ** 2 * CT ** 2, S), div(TF ** 2 * CT, S), div(TF ** 2, S)
+            A = lambda i, j: leg(X2, [i], [j]) * leg(X0) + leg(X1, [i]) * leg(X1, [j])
+            AL = norm(A)
+    else:
+        E, B = 0, 1
+        TF2E, TF2B = sl(TF, E) ** 2, sl(TF, B) ** 2
+        SE, SB = TF2E * sl(ds.Cftilde, E) + sl(ds.Cnhat, E), TF2B * sl(ds.Cftilde, B) + sl(ds.Cnhat, B)
+        Cw = ds.Cf if weights == "unlensed" else ds.Cftilde
+        CE, CB = sl(Cw, E), sl(Cw, B)
+        tE1, tE2, tB2 = sl(TF * d1, E), sl(TF * d2, E), sl(TF * d2, B)
+        if which == "EE":
+            a1, a2, b2 = CE * diag_ldiv(SE, tE1), diag_ldiv(SE, tE1), diag_ldiv(SE, tE2)
+            a1 = CE * diag_ldiv(SE, tE1)
+            I = lambda i: -(2 * sum(leg(a1, [i], j, k) * leg(b2, j, k) for j, k in inds(2)) - leg(a1, [i]) * leg(b2))
+            unnorm = sum(grad[i] * fou(I(i)) for i in (1, 2))
+            if AL is None:
+                X2, X1, X0 = div(TF2E * CE ** 2, SE), div(TF2E * CE, SE), div(TF2E, SE)
+                A1 = lambda i, j: -4 * sum(_eps(m, p) * _eps(n, q) * (leg(X2, [i], [j], k, l, m, n) * leg(X0, k, l, p, q)
+                                                                        + leg(X1, [i], k, l, m, n) * leg(X1, [j], k, l, p, q))
+                                           for k, l, m, n, p, q in inds(6) if _eps(m, p) and _eps(n, q))
+                A2 = lambda i, j: leg(X2, [i], [j]) * leg(X0) + leg(X1, [i]) * leg(X1, [j])
+                AL = norm(lambda i, j: A1(i, j) + A2(i, j))
+        else:
+            aE, aE0 = CE * diag_ldiv(SE, tE1), diag_ldiv(SE, tE1)
+            bB, bB0 = CB * diag_ldiv(SB, tB2), diag_ldiv(SB, tB2)
+            I = lambda i: 2 * sum(_eps(k, l) * (leg(aE, [i], j, k) * leg(bB0, j, l) - leg(aE0, j, k) * leg(bB, [i], j, l))
+                                  for j, k, l in inds(3) if _eps(k, l))
+            unnorm = sum(grad[i] * fou(I(i)) for i in (1, 2))
+            if AL is None:
+                XE2, XE1, XE0 = div(TF2E * CE ** 2, SE), div(TF2E * CE, SE), div(TF2E, SE)
+                XB2, XB1, XB0 = div(TF2B * CB ** 2, SB), div(TF2B * CB, SB), div(TF2B, SB)
+                A = lambda i, j: 4 * sum(_eps(m, p) * _eps(n, q) * (leg(XE2, [i], [j], k, l, m, n) * leg(XB0, k, l, p, q)
+                                                                    - 2 * leg(XE1, [i], k, l, m, n) * leg(XB1, [j], k, l, p, q)
+                                                                    + leg(XE0, k, l, m, n) * leg(XB2, [i], [j], k, l, p, q))
+                                         for k, l, m, n, p, q in inds(6) if _eps(m, p) and _eps(n, q))
+                AL = norm(A)
+    Nphi = AL
+    phi = (AL * unnorm).astype(proj.cT)
+    if wiener_filtered:
+        phi = (ds.Cphi * pinv_diag(ds.Cphi + Nphi) * phi).astype(proj.cT)
+    return dict(phi_qe=phi, AL=AL, Nphi=Nphi)
+
+
+# ----------------------------------------------------------------------------------------------
 # HMC step in ϕ° of the Gibbs sampler (src/sampling.jl:14-55 symplectic_integrate, :397-425 gibbs_sample_ϕ!, hmc_step, mass_matrix_ϕ)
 # ----------------------------------------------------------------------------------------------
 def symplectic_integrate(x0, p0, Lam, U, dUdx, dot, N: int = 50, eps: float = 0.1):
@@ -814,7 +917,9 @@ def make_dataset(Ny, Nx, theta_pix, pol="I", T=np.float64, nb=1, seed=0, nsteps=
     L = precompute(proj, phi, nsteps, phi_is_fourier=True)
     ds = DataSet(proj, pol, Cf, Cn, Cn.copy(), B, B.copy(), Mf, Mpix, None, L)
     ds.Cphi = Cphi
-    ds.Nphi = (Cphi * 0 + np.median(Cphi[Cphi > 0]) if np.any(Cphi > 0) else Cphi + 1).astype(proj.T)   # harness stand-in for quadratic_estimate(ds).Nϕ
+    ds.Nphi = (Cphi * 0 + np.median(Cphi[Cphi > 0]) if np.any(Cphi > 0) else Cphi + 1).astype(proj.T)   # stand-in; load_sim's value is quadratic_estimate(ds).Nϕ / 2 (:316), see `nphi_from_qe`
+    if pol != "IP" and "tot_TT" in cls:
+        ds.Cftilde = np.stack([cl_to_cov(proj, ell, cls["tot_" + k]) for k in keys])[None]
     ft = lenseflow_apply(L, OP_L, to_lense_basis(pol, proj, f))
     d = (apply_M(ds, op_mul(pol, B, to_harmonic_basis(pol, proj, ft))) + n).astype(proj.cT)
     ds.d = d

@@ -31,6 +31,7 @@ else:
     Mf = pkg.Cℓ_to_Cov("P", proj, lb, wl, wl, units=1)
     B = pkg.Cℓ_to_Cov("P", proj, ell, one, one, units=1)
 Cϕ = pkg.Cℓ_to_Cov("I", proj, ell, cls["pp"])
+Cft = (pkg.Cℓ_to_Cov("P", proj, ell, cls["tot_EE"], cls["tot_BB"]) if pol == "P" else None)          # Cf̃ for the quadratic estimate
 L_ = np.arange(2, 16000, dtype=float)      # stand-in for quadratic_estimate(ds).Nϕ: a flat [L(L+1)]²N_L/2π = 1e-8 plateau rising beyond L ~ 1500
 Nϕ = pkg.Cℓ_to_Cov("I", proj, L_, 2 * np.pi * 1e-8 / (L_ * (L_ + 1)) ** 2 * (1 + (L_ / 1500) ** 4))
 mask = torch.from_numpy(O.cosine_border_mask(O.ProjLambert(N, N, 2.0, np.float32 if dtype == "f32" else np.float64), 1.0))
@@ -38,7 +39,16 @@ Mpix = pkg.DiagOp(pkg.Field(lense, mask[None, None].expand(1, npol, N, N).contig
 ϕ_true = pkg.DiagOp(pkg.Field("Fourier", torch.sqrt(Cϕ._real), proj)) * w(1)
 ds0 = pkg.BaseDataSet(pkg.HarmonicBasis(w(npol)), Cf, Cn, B, Mf, Mpix, nsteps=7, Cϕ=Cϕ, Nϕ=Nϕ)
 sim = pkg.simulate(ds0, ϕ_true, generator=gen)
-ds = pkg.BaseDataSet(sim["d"], Cf, Cn, B, Mf, Mpix, nsteps=7, Cϕ=Cϕ, Nϕ=Nϕ)
+ds = pkg.BaseDataSet(sim["d"], Cf, Cn, B, Mf, Mpix, nsteps=7, Cϕ=Cϕ, Nϕ=Nϕ, Cf̃=Cft)
+if pol == "P":                                 # load_sim: Nϕ = quadratic_estimate(ds).Nϕ / Nϕ_fac, Nϕ_fac = 2 (src/dataset.jl:222,316)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    qe = pkg.quadratic_estimate(ds)
+    torch.cuda.synchronize(); tq = time.perf_counter() - t0
+    ds.Nϕ = pkg.DiagOp(pkg.Field("Fourier", (qe["Nϕ"]._real / 2).to(proj.cT), proj))
+    a, b = pkg.Map(qe["ϕqe"]).arr, pkg.Map(ϕ_true).arr
+    q = slice(N // 4, 3 * N // 4)
+    cc = [float(torch.corrcoef(torch.stack([a[i, 0, q, q].flatten(), b[i, 0, q, q].flatten()]))[0, 1]) for i in range(NB)]
+    print(f"quadratic_estimate (EB, Wiener-filtered): {tq*1e3:.0f} ms; corr(ϕqe, ϕ_true) = {np.round(cc, 3)}")
 lib = pkg.load()
 torch.cuda.synchronize(); n0 = lib.launch_count(); t0 = time.perf_counter()
 f, ϕ, hist = pkg.MAP_joint(ds, nsteps=steps, conjgrad_kwargs=dict(tol=1e-1, nsteps=500))
@@ -58,6 +68,6 @@ print(f"   gradient of logpdf(Mixed) (2 flows + 2 δ-flows): {tg*1e3:.1f} ms;  o
 # one HMC update of ϕ° (src/sampling.jl:397-417): N leap-frog steps, each one gradient of logpdf(Mixed(ds))
 NL = 5
 torch.cuda.synchronize(); t0 = time.perf_counter()
-x, ΔH, acc = pkg.gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs=(dict(N=NL, ϵ=0.002),), always_accept=False)
+x, ΔH, acc = pkg.gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs=(dict(N=NL, ϵ=0.01),), always_accept=False)
 torch.cuda.synchronize(); th = time.perf_counter() - t0
 print(f"   HMC ϕ° update, {NL} leap-frog steps: {th*1e3:.0f} ms = {NL/th:.1f} leap-frog steps/s for the batch of {NB} ({NB*NL/th:.1f} chain-steps/s); ΔH = {np.round(ΔH, 3)}, accept = {acc}")

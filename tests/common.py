@@ -35,6 +35,7 @@ def make_problem(pkg, Ny, Nx, pol, dtype, nb, nbphi=None, nsteps=7, mask=True, s
     dso = sim["ds"]
     ds = pkg.BaseDataSet(F(sim["d"], harm), D(dso.Cf), D(dso.Cn), D(dso.B), D(dso.Mf),
                          D(dso.Mpix, lense) if dso.Mpix is not None else None, nsteps=nsteps,
-                         Cϕ=pkg.DiagOp(F(dso.Cphi, "Fourier")), Nϕ=pkg.DiagOp(F(dso.Nphi, "Fourier")))
+                         Cϕ=pkg.DiagOp(F(dso.Cphi, "Fourier")), Nϕ=pkg.DiagOp(F(dso.Nphi, "Fourier")),
+                         Cf̃=D(dso.Cftilde) if dso.Cftilde is not None else None)
     return dict(sim=sim, proj=proj, oproj=sim["proj"], phi=F(phi_np, "Fourier"), f=F(sim["f"], harm), ds=ds, dso=dso, Lo=Lo,
                 harm=harm, lense=lense, F=F)

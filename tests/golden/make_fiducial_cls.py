@@ -4,7 +4,8 @@ Run HERE (container with /root/reference mounted); the GPU box never reads /root
 Source: /root/reference/dat/default_camb_Cls.jld2 (written by dat/compute_default_camb_Cls.jl,
 `camb(ℓmax=16000)`, src/cls.jl:181-196).  The JLD2/HDF5 container stores 21 zlib-deflated
 Float64[15998] chunks (ℓ = 2..15999); we scan for zlib headers and inflate.
-Output: tests/golden/fiducial_cls.npz  (ℓ, unlensed_total TT/EE/BB/TE = unlensed_scalar + tensor(r=0.2), ϕϕ)
+Output: tests/golden/fiducial_cls.npz  (ℓ, unlensed_total TT/EE/BB/TE = unlensed_scalar + tensor(r=0.2), ϕϕ, and the lensed
+`total` TT/EE/BB/TE that load_sim uses for Cf̃, src/dataset.jl:270)
 stored as float64 for ℓ = 2..LMAX_KEEP.
 """
 import zlib, sys, os
@@ -40,7 +41,7 @@ def main():
     keep = ell <= LMAX_KEEP
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fiducial_cls.npz")
     np.savez_compressed(out, ell=ell[keep].astype(np.int32),
-                        **{k: C[k][keep] for k in ("ut_TT", "ut_EE", "ut_BB", "ut_TE", "pp")})
+                        **{k: C[k][keep] for k in ("ut_TT", "ut_EE", "ut_BB", "ut_TE", "pp", "tot_TT", "tot_EE", "tot_BB", "tot_TE")})
     print("wrote", out, os.path.getsize(out), "bytes")
 
 if __name__ == "__main__":

@@ -201,6 +201,17 @@ def test_logpdf_mixed_gradient_and_map_joint(cuda_pkg, pol):
     assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum()
 
 
+@pytest.mark.parametrize("pol,which", [("I", "TT"), ("P", "EB")])
+def test_quadratic_estimate(cuda_pkg, pol, which):
+    """quadratic_estimate (src/quadratic_estimate.jl:30-199) on the device against the oracle."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, 128, 128, pol, "f64", nb=2, nsteps=5, mask=False, seed=8, theta=2.0, device=DEV)
+    r = pkg.quadratic_estimate(pr["ds"], which)
+    ro = O.quadratic_estimate(pr["dso"], which)
+    assert relerr(O.pinv_diag(r["AL"]._real.cpu().numpy()), O.pinv_diag(ro["AL"])) < 1e-9
+    assert relerr(r["ϕqe"].cpu_numpy(), ro["phi_qe"]) < 1e-8
+
+
 def test_hmc_step_phi(cuda_pkg):
     """gibbs_sample_ϕ! / hmc_step / symplectic_integrate (src/sampling.jl:14-55,397-425) on the device vs the oracle, same draws."""
     pkg = cuda_pkg

@@ -274,6 +274,24 @@ def test_logpdf_mixed_gradient_and_map_joint(pkg, emu, pol):
     assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum()
 
 
+@pytest.mark.parametrize("pol,which", [("I", "TT"), ("P", "EE"), ("P", "EB")])
+def test_quadratic_estimate(pkg, emu, pol, which):
+    """quadratic_estimate (src/quadratic_estimate.jl:30-199): AL = Nϕ and the (Wiener-filtered) estimate against the oracle, with the
+    reference's per-term abs.() normalisation and with the exact one."""
+    pr = make_problem(pkg, 32, 64, pol, "f64", nb=2, nsteps=4, mask=False, seed=8, theta=2.0, lib=emu)
+    for each in (True, False):
+        r = pkg.quadratic_estimate(pr["ds"], which, abs_each_term=each)
+        ro = O.quadratic_estimate(pr["dso"], which, abs_each_term=each)
+        # compare 1/AL (the normalisation sum): beyond twice the band limit of the filters it is pure rounding noise, whose
+        # reciprocal is arbitrary in the reference as well
+        assert relerr(O.pinv_diag(r["AL"]._real.numpy()), O.pinv_diag(ro["AL"])) < 1e-9 and relerr(r["ϕqe"].cpu_numpy(), ro["phi_qe"]) < 1e-8
+    r2 = pkg.quadratic_estimate(pr["ds"], which, wiener_filtered=False, weights="lensed", AL=r["AL"])
+    ro2 = O.quadratic_estimate(pr["dso"], which, wiener_filtered=False, weights="lensed", AL=ro["AL"])
+    assert relerr(r2["ϕqe"].cpu_numpy() * (pr["oproj"].lmag < 5000), ro2["phi_qe"] * (pr["oproj"].lmag < 5000)) < 1e-8
+    with pytest.raises(pkg.CmblError):
+        pkg.quadratic_estimate(pr["ds"], "TE")
+
+
 def test_hmc_step_phi(pkg, emu):
     """gibbs_sample_ϕ! / hmc_step / symplectic_integrate (src/sampling.jl:14-55,397-425) with the same momentum and accept draws
     as the oracle; the leap-frog nearly conserves H for a small step."""
