@@ -29,7 +29,7 @@ __all__ = [
     "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "BlockDiagIEB", "dot", "BaseDataSet", "gradientf_logpdf",
     "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
     "Cℓ_to_2D", "Cℓ_to_Cov", "Cl_to_Cov", "simulate", "sample_f", "convert",
-    "quadratic_estimate", "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint", "symplectic_integrate", "hmc_step", "mass_matrix_ϕ", "gibbs_sample_ϕ",
+    "quadratic_estimate", "mixing_D", "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint", "symplectic_integrate", "hmc_step", "mass_matrix_ϕ", "gibbs_sample_ϕ",
     "CmblError", "load",
 ]
 
@@ -691,6 +691,18 @@ def logpdf(ds, f: Field | None = None, ϕ: Field | None = None, **kw) -> np.ndar
     f = HarmonicBasis(f)
     z = _apply_MB(ds, L * f) - ds.d
     return -(_quad(ds.Cn, z) + _quad(ds.Cf, f) + _quad(ds.Cϕ, Fourier(ϕ))) / 2
+
+
+def mixing_D(ds: BaseDataSet, σ_len_arcmin: float = 5.0) -> DiagOp:
+    """The mixing matrix load_sim attaches to a dataset: D = sqrt((Cf + (σ²len + 2Cn̂)) · pinv(Cf)), σ²len = deg2rad(5/60)²
+    (src/dataset.jl:325-332).  It decorrelates f° from ϕ°, which is what makes pinv(Cϕ)+pinv(Nϕ) a usable ϕ° Hessian in MAP_joint
+    (with D = 1 the line search collapses to α ~ 1e-4)."""
+    if not isinstance(ds.Cf, DiagOp):
+        raise CmblError("mixing_D is implemented for diagonal Cf (pol = I, P)")
+    σ2 = float(np.deg2rad(σ_len_arcmin / 60.0) ** 2)
+    cf, cn = ds.Cf._real, ds.Cnhat._real
+    r = torch.sqrt((cf + (σ2 + 2 * cn)) * torch.where(cf == 0, torch.zeros_like(cf), 1 / cf))
+    return DiagOp(Field(ds.Cf.diag.basis, r.to(ds.Cf.diag.arr.dtype), ds.Cf.diag.proj))
 
 
 class Mixed:

@@ -648,6 +648,12 @@ def logpdf(ds: DataSet, f_harm: np.ndarray, phi_four: np.ndarray, d=None) -> np.
     return -(quad(ds.Cn, z, pol) + quad(ds.Cf, f_harm, pol) + quad(ds.Cphi, phi_four, "I")) / 2
 
 
+def mixing_D(ds: DataSet, sigma_len_arcmin: float = 5.0) -> np.ndarray:
+    """load_sim's D = sqrt((Cf + (σ²len + 2Cn̂)) pinv(Cf)), σ²len = deg2rad(5/60)² (src/dataset.jl:325-332)."""
+    s2 = ds.proj.T(np.deg2rad(sigma_len_arcmin / 60.0) ** 2)
+    return np.sqrt((ds.Cf + (s2 + 2 * ds.Cnhat)) * pinv_diag(ds.Cf)).astype(ds.proj.T)
+
+
 def logpdf_mixed(ds: DataSet, f_mixed_map: np.ndarray, phi_mixed: np.ndarray) -> np.ndarray:
     """logpdf(Mixed(ds); f°, ϕ°) (src/dataset.jl:84-87); logdet(D,θ) = logdet(G,θ) = 0 without θ dependence (src/generic.jl:269)."""
     f, phi = unmix(ds, ds.proj, ds.pol, f_mixed_map, phi_mixed, D=ds.D, G=ds.G, nsteps=ds.L.nsteps)

@@ -45,6 +45,7 @@ if pol == "P":                                 # load_sim: Nϕ = quadratic_estim
     qe = pkg.quadratic_estimate(ds)
     torch.cuda.synchronize(); tq = time.perf_counter() - t0
     ds.Nϕ = pkg.DiagOp(pkg.Field("Fourier", (qe["Nϕ"]._real / 2).to(proj.cT), proj))
+    ds.D = pkg.mixing_D(ds)                      # load_sim's mixing matrix (src/dataset.jl:325-332)
     a, b = pkg.Map(qe["ϕqe"]).arr, pkg.Map(ϕ_true).arr
     q = slice(N // 4, 3 * N // 4)
     cc = [float(torch.corrcoef(torch.stack([a[i, 0, q, q].flatten(), b[i, 0, q, q].flatten()]))[0, 1]) for i in range(NB)]

@@ -290,6 +290,7 @@ def test_quadratic_estimate(pkg, emu, pol, which):
     assert relerr(r2["ϕqe"].cpu_numpy() * (pr["oproj"].lmag < 5000), ro2["phi_qe"] * (pr["oproj"].lmag < 5000)) < 1e-8
     with pytest.raises(pkg.CmblError):
         pkg.quadratic_estimate(pr["ds"], "TE")
+    assert relerr(pkg.mixing_D(pr["ds"])._real.numpy(), O.mixing_D(pr["dso"])) < 1e-13
 
 
 def test_hmc_step_phi(pkg, emu):
