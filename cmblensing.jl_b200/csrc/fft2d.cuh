@@ -8,6 +8,17 @@
 #pragma once
 #include "plan.cuh"
 
+// launch shape of the three general-transform kernels (threads per block, minimum resident blocks per SM → register cap).
+// Uncapped, the fp64 kernels take 196-255 registers and run ONE 256-thread block per SM, so a block's load → passes → store
+// phases overlap with nothing; capping at 128 registers (a few hundred bytes of spills) doubles the residency and is 26 %
+// faster at Nside=1024 (profiles/r01_fft_launch_shape.log; 128 threads × 3-4 blocks and 256 × 3 measured, not better).
+#ifndef CMBL_FFT_NT
+#define CMBL_FFT_NT 256
+#endif
+#ifndef CMBL_FFT_MINB
+#define CMBL_FFT_MINB 2
+#endif
+
 namespace cmbl {
 
 inline int tile_budget_bytes() {
@@ -41,7 +52,7 @@ template <class T> int row_lines(int N, int maxL) {
 // column pass of rfft2
 // ---------------------------------------------------------------------------------------------------------------
 template <class T> struct R2CColBody {
-    static constexpr int NT = 256;
+    static constexpr int NT = CMBL_FFT_NT, MINB = CMBL_FFT_MINB;
     static const char* name() { return "rfft2_cols"; }
     Fft1D<T> fy; int Ny, Nx, Nyh, L, tiles_per_plane;
     const T* in; C2<T>* out;
@@ -75,7 +86,7 @@ template <class T> struct R2CColBody {
 // row pass (C2C along x) on a chunk of L consecutive ky, forward (in place allowed) or inverse (in -> out)
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool INV> struct C2CRowBody {
-    static constexpr int NT = 256;
+    static constexpr int NT = CMBL_FFT_NT, MINB = CMBL_FFT_MINB;
     static const char* name() { return "fft2_rows"; }
     Fft1D<T> fx; int Nx, Nyh, L, tiles_per_plane;
     const C2<T>* in; C2<T>* out;
@@ -107,7 +118,7 @@ template <class T, bool INV> struct C2CRowBody {
 // column pass of irfft2 (C2R along y)
 // ---------------------------------------------------------------------------------------------------------------
 template <class T> struct C2RColBody {
-    static constexpr int NT = 256;
+    static constexpr int NT = CMBL_FFT_NT, MINB = CMBL_FFT_MINB;
     static const char* name() { return "irfft2_cols"; }
     Fft1D<T> fy; int Ny, Nx, Nyh, L, tiles_per_plane; T scale;
     const C2<T>* in; T* out;
