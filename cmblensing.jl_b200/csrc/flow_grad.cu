@@ -10,6 +10,7 @@
 //     m = M⁻¹w   — reference: m₁ = M₁₁w₁+M₁₂w₂ ; m₂ = M₂₁·m₁+M₂₂w₂ (aliased in-place product, src/lenseflow.jl:198-200 with
 //                  src/field_vectors.jl:48-49).  bug_compat = false uses the exact m₂ = M₂₁w₁+M₂₂w₂.
 //     dδϕ/dt = iℓₓ·rfft2(m₁) + iℓᵧ·rfft2(m₂) + Σ_ij (−iℓ_i)(−iℓ_j)·rfft2(t·p_j·m_i)
+//              (the (1,2) and (2,1) terms share their multiplier and are summed before the transform: 5 transforms, not 6)
 // M⁻¹₁₂ ≡ M⁻¹₂₁ (the reference reads [2,1] twice, src/field_vectors.jl:87), so the cache holds 3 maps per time.
 // This path is not on the headline roofline: it is built from the library's general transforms plus
 // three fused pointwise kernels; the caches may be in the row-grouped layout of the fast stage kernels (index remap).
@@ -45,7 +46,7 @@ template <class T> struct DeltaPointBody {
     const T* ldf; const T* gx; const T* gy;          // [Nb][Npol] maps (reference layout)
     const T* pk; const T* mk3;                        // p[k]: [Nbphi][2] maps, M⁻¹[k]: [Nbphi][3] maps (layout G)
     T* dfdt; T* a1; T* a2;                            // [Nb][Npol] maps
-    T* six;                                           // [Nb][6] maps: m1, m2, t p1 m1, t p2 m1, t p1 m2, t p2 m2
+    T* six;                                           // [Nb][5] maps: m1, m2, t p1 m1, t (p2 m1 + p1 m2), t p2 m2  (the two mixed terms share (−iℓx)(−iℓy))
     DEV void operator()(int blk, unsigned char*) const {
         const size_t nmap = (size_t)Nx * Ny;
         CMBL_FOR_THREADS(tid, NT) {
@@ -67,9 +68,9 @@ template <class T> struct DeltaPointBody {
                 }
                 const T m1 = m11 * w1 + m21 * w2;                                      // M₁₂ ≡ M₂₁
                 const T m2 = bug_compat ? (m21 * m1 + m22 * w2) : (m21 * w1 + m22 * w2);
-                T* s = six + b * 6 * nmap + r;
+                T* s = six + b * 5 * nmap + r;
                 s[0] = m1; s[nmap] = m2;
-                s[2 * nmap] = t * p1 * m1; s[3 * nmap] = t * p2 * m1; s[4 * nmap] = t * p1 * m2; s[5 * nmap] = t * p2 * m2;
+                s[2 * nmap] = t * p1 * m1; s[3 * nmap] = t * p2 * m1 + t * p1 * m2; s[4 * nmap] = t * p2 * m2;
             }
         }
     }
@@ -92,13 +93,12 @@ template <class T> struct DeltaSpecBody {
                 if (pl < (size_t)C) ddf[e] = cmul(d1, A1[e]) + cmul(d2, A2[e]);
                 else {
                     const size_t b = pl - C;
-                    const C2<T>* s = S6 + b * 6 * nf + r;
+                    const C2<T>* s = S6 + b * 5 * nf + r;
                     const C2<T> n1 = mk<T>((T)0, -lx[kx]), n2 = mk<T>((T)0, -ly[ky]);
                     C2<T> v = cmul(d1, s[0]) + cmul(d2, s[nf]);
                     v = v + cmul(n1, cmul(n1, s[2 * nf]));       // i=1 (m1), j=1 (p1)
-                    v = v + cmul(n1, cmul(n2, s[3 * nf]));       // i=1, j=2
-                    v = v + cmul(n2, cmul(n1, s[4 * nf]));       // i=2 (m2), j=1
-                    v = v + cmul(n2, cmul(n2, s[5 * nf]));       // i=2, j=2
+                    v = v + cmul(n1, cmul(n2, s[3 * nf]));       // (i,j) = (1,2) and (2,1): rfft2 is linear, one transform for both
+                    v = v + cmul(n2, cmul(n2, s[4 * nf]));       // i=2, j=2
                     ddphi[b * nf + r] = v;
                 }
             }
@@ -123,6 +123,29 @@ template <class T> static void axpy(size_t n, const T* x, const T* k, T s, T* ou
     launch(b, (int)((n + b.NT - 1) / b.NT), 0, st);
 }
 
+// One RK4 stage update of the joint state (three components stored as real arrays):
+//   acc = (acc_in ? acc_in : y) + cb·k ;  u = y + ca·k  (u == nullptr: not needed — last stage, or the δϕ component, which
+//   never feeds the velocity).  k is read once for both results.
+template <class T> struct RkUpdateBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "rk_update"; }
+    struct Seg { size_t n; const T* y; const T* acc_in; const T* k; T* acc; T* u; };
+    Seg seg[3]; size_t off1, off2, total; T ca, cb;
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < total) {
+                const int si = e < off1 ? 0 : (e < off2 ? 1 : 2);
+                const Seg& g = seg[si];
+                const size_t i = e - (si == 0 ? 0 : (si == 1 ? off1 : off2));
+                const T kk = g.k[i], yy = g.y[i];
+                g.acc[i] = (g.acc_in ? g.acc_in[i] : yy) + cb * kk;
+                if (g.u) g.u[i] = yy + ca * kk;
+            }
+        }
+    }
+};
+
 template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,
                                   bool bug_compat, cmblStream_t st) {
     CMBL_REQUIRE(F.have_p && F.have_minv, "cmbl_lenseflow_grad needs cmbl_lenseflow_precompute(..., with_minv = 1)");
@@ -133,12 +156,12 @@ template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T
     // scratch: state copies (y: f, δf, δϕ), stage inputs u, accumulators acc, velocities k, and the work arrays of one evaluation
     auto R = [&](DevBuf& b, size_t bytes) { return b.reserve(bytes); };
     T* yf = (T*)R(F.g_yf, sizeof(T) * mC);           C2<T>* yd = (C2<T>*)R(F.g_yd, sizeof(C2<T>) * fC);   C2<T>* yp = (C2<T>*)R(F.g_yp, sizeof(C2<T>) * fB);
-    T* uf = (T*)R(F.g_uf, sizeof(T) * mC);           C2<T>* ud = (C2<T>*)R(F.g_ud, sizeof(C2<T>) * fC);   C2<T>* up = (C2<T>*)R(F.g_up, sizeof(C2<T>) * fB);
+    T* uf = (T*)R(F.g_uf, sizeof(T) * mC);           C2<T>* ud = (C2<T>*)R(F.g_ud, sizeof(C2<T>) * fC);
     T* af = (T*)R(F.g_af, sizeof(T) * mC);           C2<T>* ad = (C2<T>*)R(F.g_ad, sizeof(C2<T>) * fC);   C2<T>* ap = (C2<T>*)R(F.g_ap, sizeof(C2<T>) * fB);
     T* kf = (T*)R(F.g_kf, sizeof(T) * mC);           C2<T>* kd = (C2<T>*)R(F.g_kd, sizeof(C2<T>) * fC);   C2<T>* kp = (C2<T>*)R(F.g_kp, sizeof(C2<T>) * fB);
     T* ldf = (T*)R(F.g_ldf, sizeof(T) * mC);         T* gxy = (T*)R(F.g_gxy, sizeof(T) * 2 * mC);         T* a12 = (T*)R(F.g_a12, sizeof(T) * 2 * mC);
-    T* six = (T*)R(F.g_six, sizeof(T) * 6 * nmap * Nb);
-    C2<T>* spec = (C2<T>*)R(F.g_spec, sizeof(C2<T>) * (2 * fC > 6 * fB ? 2 * fC : 6 * fB));
+    T* six = (T*)R(F.g_six, sizeof(T) * 5 * nmap * Nb);
+    C2<T>* spec = (C2<T>*)R(F.g_spec, sizeof(C2<T>) * (2 * fC > 5 * fB ? 2 * fC : 5 * fB));
     C2<T>* spec2 = (C2<T>*)R(F.g_spec2, sizeof(C2<T>) * 2 * fC);
 
     auto velocity = [&](int k, const T* f, const C2<T>* df, T* of, C2<T>* od, C2<T>* ophi) {
@@ -159,7 +182,7 @@ template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T
             launch(b, (int)((nmap * Nb + b.NT - 1) / b.NT), 0, st);
         }
         rfft2<T>(P, a12, spec2, 2 * C, st);
-        rfft2<T>(P, six, spec, 6 * Nb, st);
+        rfft2<T>(P, six, spec, 5 * Nb, st);
         {
             DeltaSpecBody<T> b{P.Nx, P.Nyh, C, Nb, P.lx, P.ly, spec2, spec2 + fC, spec, od, ophi};
             launch(b, (int)((nf * (size_t)(C + Nb) + b.NT - 1) / b.NT), 0, st);
@@ -181,18 +204,15 @@ template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T
             const T* f_in = (s == 0) ? yf : uf; const C2<T>* d_in = (s == 0) ? yd : ud;
             velocity(kq, f_in, d_in, kf, kd, kp);
             const T cb = (s == 0 || s == 3) ? h6 : h3, ca = (s < 2) ? h2 : h1;
-            if (s < 3) {
-                // acc = (s == 0 ? y : acc) + cb k ;  u = y + ca k
-                axpy<T>(mC, s == 0 ? yf : af, kf, cb, af, st);
-                axpy<T>(2 * fC, s == 0 ? rr(yd) : rr(ad), rr(kd), cb, rr(ad), st);
-                axpy<T>(2 * fB, s == 0 ? rr(yp) : rr(ap), rr(kp), cb, rr(ap), st);
-                axpy<T>(mC, yf, kf, ca, uf, st);
-                axpy<T>(2 * fC, rr(yd), rr(kd), ca, rr(ud), st);
-                axpy<T>(2 * fB, rr(yp), rr(kp), ca, rr(up), st);       // δϕ does not feed the velocity, kept for symmetry of the state
-            } else {
-                axpy<T>(mC, af, kf, cb, yf, st);
-                axpy<T>(2 * fC, rr(ad), rr(kd), cb, rr(yd), st);
-                axpy<T>(2 * fB, rr(ap), rr(kp), cb, rr(yp), st);
+            {
+                // stages 1-3: acc = (s == 0 ? y : acc) + cb k, u = y + ca k;  stage 4: y = acc + cb k  (written as acc := y_out)
+                RkUpdateBody<T> b;
+                const bool last = (s == 3);
+                b.seg[0] = {mC, last ? af : yf, (s == 0 || last) ? nullptr : af, kf, last ? yf : af, last ? nullptr : uf};
+                b.seg[1] = {2 * fC, last ? rr(ad) : rr(yd), (s == 0 || last) ? nullptr : rr(ad), rr(kd), last ? rr(yd) : rr(ad), last ? nullptr : rr(ud)};
+                b.seg[2] = {2 * fB, last ? rr(ap) : rr(yp), (s == 0 || last) ? nullptr : rr(ap), rr(kp), last ? rr(yp) : rr(ap), nullptr};
+                b.off1 = mC; b.off2 = mC + 2 * fC; b.total = mC + 2 * fC + 2 * fB; b.ca = ca; b.cb = cb;
+                launch(b, (int)((b.total + b.NT - 1) / b.NT), 0, st);
             }
         }
         kk += 2 * sgn;

@@ -72,3 +72,11 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 x, ΔH, acc = pkg.gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs=(dict(N=NL, ϵ=0.01),), always_accept=False)
 torch.cuda.synchronize(); th = time.perf_counter() - t0
 print(f"   HMC ϕ° update, {NL} leap-frog steps: {th*1e3:.0f} ms = {NL/th:.1f} leap-frog steps/s for the batch of {NB} ({NB*NL/th:.1f} chain-steps/s); ΔH = {np.round(ΔH, 3)}, accept = {acc}")
+# per-kernel device time of one gradient (CUDA events around every launch)
+lib.cdll.cmbl_profile_begin()
+pkg.gradient_logpdf_mixed(ds, f_m, ϕ_m)
+rows = []
+for line in lib.cdll.cmbl_profile_end().decode().strip().splitlines():
+    nm, cnt, t = line.split(); rows.append((float(t), nm, int(cnt)))
+tot = sum(r[0] for r in rows)
+print("   gradient kernel profile (ms, launches): " + ", ".join(f"{nm} {t:.1f} ({cnt})" for t, nm, cnt in sorted(rows, reverse=True)[:12]) + f"; sum {tot:.1f} ms")
