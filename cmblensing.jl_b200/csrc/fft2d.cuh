@@ -61,8 +61,8 @@ template <class T> struct R2CColBody {
         Tile<T, false> tv = line_tile<T>(smem, L, fy);
         const T* src = in + ((size_t)c * Nx + x0) * Ny;
         CMBL_FOR_THREADS(tid, NT) {
-            for (int e = tid; e < L * Ny; e += NT) {
-                int l = e / Ny, y = e - l * Ny;
+            for (int e = tid; e < L * Ny; e += NT) {                     // Ny is a power of two: shifts, no division
+                const int l = e >> fy.logN, y = e & (Ny - 1);
                 tv.at(l, y) = mk<T>(src[(size_t)(2 * l) * Ny + y], src[(size_t)(2 * l + 1) * Ny + y]);
             }
         }
@@ -70,13 +70,14 @@ template <class T> struct R2CColBody {
         fft_forward_passes<T, false, NT>(tv, fy, 0, fy.npass);
         C2<T>* dst = out + ((size_t)c * Nx + x0) * Nyh;
         CMBL_FOR_THREADS(tid, NT) {
-            for (int e = tid; e < L * Nyh; e += NT) {
-                int l = e / Nyh, k = e - l * Nyh;
-                C2<T> zk = tv.at(l, CMBL_LDG(&fy.pos[k]));
-                C2<T> zm = tv.at(l, CMBL_LDG(&fy.pos[(Ny - k) & (Ny - 1)]));
+            for (int k = tid; k < Nyh; k += NT) {                        // Nyh = Ny/2+1 is odd: loop per line instead of dividing
+                const int pk = CMBL_LDG(&fy.pos[k]), pm = CMBL_LDG(&fy.pos[(Ny - k) & (Ny - 1)]);
                 const T h = (T)0.5;
-                dst[(size_t)(2 * l) * Nyh + k] = mk<T>((zk.x + zm.x) * h, (zk.y - zm.y) * h);
-                dst[(size_t)(2 * l + 1) * Nyh + k] = mk<T>((zk.y + zm.y) * h, (zm.x - zk.x) * h);
+                for (int l = 0; l < L; ++l) {
+                    const C2<T> zk = tv.at(l, pk), zm = tv.at(l, pm);
+                    dst[(size_t)(2 * l) * Nyh + k] = mk<T>((zk.x + zm.x) * h, (zk.y - zm.y) * h);
+                    dst[(size_t)(2 * l + 1) * Nyh + k] = mk<T>((zk.y + zm.y) * h, (zm.x - zk.x) * h);
+                }
             }
         }
     }
@@ -95,9 +96,10 @@ template <class T, bool INV> struct C2CRowBody {
         Tile<T, true> tv{reinterpret_cast<C2<T>*>(smem), L, 0, 0};
         const C2<T>* src = in + (size_t)c * Nx * Nyh;
         C2<T>* dst = out + (size_t)c * Nx * Nyh;
+        const int logL = ilog2(L);                                              // L is a power of two
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < L * Nx; e += NT) {
-                int x = e / L, l = e - x * L;
+                const int x = e >> logL, l = e & (L - 1);
                 C2<T> v = (k0 + l < Nyh) ? src[(size_t)x * Nyh + k0 + l] : mk<T>(0, 0);
                 tv.at(l, INV ? CMBL_LDG(&fx.pos[x]) : x) = v;
             }
@@ -107,7 +109,7 @@ template <class T, bool INV> struct C2CRowBody {
         else fft_forward_passes<T, true, NT>(tv, fx, 0, fx.npass);
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < L * Nx; e += NT) {
-                int x = e / L, l = e - x * L;
+                const int x = e >> logL, l = e & (L - 1);
                 if (k0 + l < Nyh) dst[(size_t)x * Nyh + k0 + l] = tv.at(l, INV ? x : CMBL_LDG(&fx.pos[x]));
             }
         }
@@ -127,12 +129,15 @@ template <class T> struct C2RColBody {
         Tile<T, false> tv = line_tile<T>(smem, L, fy);
         const C2<T>* src = in + ((size_t)c * Nx + x0) * Nyh;
         CMBL_FOR_THREADS(tid, NT) {
-            for (int e = tid; e < L * Nyh; e += NT) {
-                int l = e / Nyh, k = e - l * Nyh;
-                C2<T> a = src[(size_t)(2 * l) * Nyh + k], b = src[(size_t)(2 * l + 1) * Nyh + k];
-                if (k == 0 || 2 * k == Ny) { a.y = 0; b.y = 0; }            // c2r ignores Im of DC / Nyquist rows
-                tv.at(l, CMBL_LDG(&fy.pos[k])) = mk<T>(a.x - b.y, a.y + b.x);
-                if (k != 0 && 2 * k != Ny) tv.at(l, CMBL_LDG(&fy.pos[Ny - k])) = mk<T>(a.x + b.y, b.x - a.y);
+            for (int k = tid; k < Nyh; k += NT) {
+                const bool edge = (k == 0 || 2 * k == Ny);
+                const int pk = CMBL_LDG(&fy.pos[k]), pm = edge ? 0 : CMBL_LDG(&fy.pos[Ny - k]);
+                for (int l = 0; l < L; ++l) {
+                    C2<T> a = src[(size_t)(2 * l) * Nyh + k], b = src[(size_t)(2 * l + 1) * Nyh + k];
+                    if (edge) { a.y = 0; b.y = 0; }                            // c2r ignores Im of DC / Nyquist rows
+                    tv.at(l, pk) = mk<T>(a.x - b.y, a.y + b.x);
+                    if (!edge) tv.at(l, pm) = mk<T>(a.x + b.y, b.x - a.y);
+                }
             }
         }
         CMBL_SYNC();
@@ -140,7 +145,7 @@ template <class T> struct C2RColBody {
         T* dst = out + ((size_t)c * Nx + x0) * Ny;
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < L * Ny; e += NT) {
-                int l = e / Ny, y = e - l * Ny;
+                const int l = e >> fy.logN, y = e & (Ny - 1);
                 C2<T> z = tv.at(l, y);
                 dst[(size_t)(2 * l) * Ny + y] = z.x * scale;
                 dst[(size_t)(2 * l + 1) * Ny + y] = z.y * scale;
