@@ -79,9 +79,9 @@ template <class T> void cg_setup(CgT<T>& G, const cmbl_dataset_desc& ds, cmblStr
 
 template <class T>
 static void chain(CgT<T>& G, const C2<T>* in, const T* din, const C2<T>* d, bool neg, const T* pre, int rot, const T* post,
-                  const T* sdiag, const C2<T>* sub, C2<T>* out, cmblStream_t st, const T* pre2 = nullptr) {
+                  const T* sdiag, const C2<T>* sub, C2<T>* out, cmblStream_t st, const T* pre2 = nullptr, int rot2 = 0) {
     FourierChainBody<T> b;
-    b.Npol = G.Npol; b.Nb = G.Nb; b.nf = G.nf(); b.rot = (G.Npol >= 2) ? rot : 0; b.neg = neg;
+    b.Npol = G.Npol; b.Nb = G.Nb; b.nf = G.nf(); b.rot = (G.Npol >= 2) ? rot : 0; b.rot2 = (G.Npol >= 2) ? rot2 : 0; b.neg = neg;
     b.sin2phi = G.P->sin2phi; b.cos2phi = G.P->cos2phi;
     b.in = in; b.din = din; b.d = d; b.pre = pre; b.pre2 = pre2; b.post = post; b.sdiag = sdiag; b.sub = sub; b.out = out;
     size_t threads = (G.Npol >= 2) ? b.nf * G.Nb : b.nf * G.Nb * G.Npol;
@@ -104,20 +104,16 @@ template <class T> void cg_gradientf(CgT<T>& G, const C2<T>* f, const C2<T>* d, 
     flow_integrate<T>(F, false, m1, 0, 2 * n, st);
     rfft2<T>(P, m1, w1, C, st);
     if (G.mask) {
-        // B then M = Mf∘Mpix:   QU→EB, ×B, EB→QU | irfft2 | ×Mpix | rfft2 | QU→EB ×Mf
-        chain<T>(G, w1, none, cnone, false, none, 2, G.B, none, cnone, w2, st);
-        chain<T>(G, w2, none, cnone, false, none, 1, none, none, cnone, w1, st);
-        irfft2<T>(P, w1, m1, C, st);
-        diag_mul<T>(P, CMBL_MAP, G.mask, G.Npol, m1, m1, C, false, st);
+        // B then M = Mf∘Mpix:   QU→EB, ×B, EB→QU (one pass) | irfft2 with ×Mpix on its store | rfft2 | QU→EB ×Mf
+        chain<T>(G, w1, none, cnone, false, none, 2, G.B, none, cnone, w2, st, none, 1);
+        irfft2<T>(P, w2, m1, C, st, G.mask, G.Npol);
         rfft2<T>(P, m1, w1, C, st);
         chain<T>(G, w1, none, cnone, false, none, 2, G.Mf, none, cnone, w2, st);
         // pinv(Cn)(d − ·), then M' = Mpix'∘Mf': ×(Mf·pinv(Cn)), EB→QU | irfft2 | ×Mpix | rfft2 | QU→EB, ×B', EB→QU
         chain<T>(G, w2, none, d, d == nullptr, icn1, 1, none, none, cnone, w1, st, icn2);
-        irfft2<T>(P, w1, m1, C, st);
-        diag_mul<T>(P, CMBL_MAP, G.mask, G.Npol, m1, m1, C, false, st);
+        irfft2<T>(P, w1, m1, C, st, G.mask, G.Npol);
         rfft2<T>(P, m1, w1, C, st);
-        chain<T>(G, w1, none, cnone, false, none, 2, G.B, none, cnone, w2, st);
-        chain<T>(G, w2, none, cnone, false, none, 1, none, none, cnone, w1, st);
+        chain<T>(G, w1, none, cnone, false, none, 2, G.B, none, cnone, w1, st, none, 1);
     } else {
         // everything between Lϕ and Lϕ' is diagonal in the harmonic basis: B'·Mf·pinv(Cn)·(d − Mf·B·f̃)
         chain<T>(G, w1, none, cnone, false, none, 2, G.B, none, cnone, w2, st);

@@ -40,7 +40,7 @@ template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmb
     }
 }
 
-template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st) {
+template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st, const T* post_diag, int post_planes) {
     if (C <= 0) return;
     const int chunk = fft_chunk_planes(P, C);
     C2<T>* scratch = reinterpret_cast<C2<T>*>(P.scratch_four.reserve(sizeof(C2<T>) * P.four_elems() * (size_t)chunk));   // reused by every group
@@ -59,6 +59,8 @@ template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cm
             b.L = col_lines<T>(P.ay.fft, P.Nx); b.tiles_per_plane = P.Nx / (2 * b.L);
             b.scale = (T)1 / ((T)P.Ny * (T)P.Nx);
             b.in = scratch; b.out = map + (size_t)c0 * P.map_elems();
+            CMBL_REQUIRE(!post_diag || (c0 % post_planes == 0), "plane groups must start on a diagonal period");
+            b.post_diag = post_diag; b.post_planes = post_planes;
             launch(b, nC * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
         }
     }
@@ -66,7 +68,7 @@ template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cm
 
 template void rfft2<float>(PlanT<float>&, const float*, C2<float>*, int, cmblStream_t);
 template void rfft2<double>(PlanT<double>&, const double*, C2<double>*, int, cmblStream_t);
-template void irfft2<float>(PlanT<float>&, const C2<float>*, float*, int, cmblStream_t);
-template void irfft2<double>(PlanT<double>&, const C2<double>*, double*, int, cmblStream_t);
+template void irfft2<float>(PlanT<float>&, const C2<float>*, float*, int, cmblStream_t, const float*, int);
+template void irfft2<double>(PlanT<double>&, const C2<double>*, double*, int, cmblStream_t, const double*, int);
 
 }  // namespace cmbl

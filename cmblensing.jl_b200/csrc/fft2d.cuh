@@ -124,6 +124,7 @@ template <class T> struct C2RColBody {
     static const char* name() { return "irfft2_cols"; }
     Fft1D<T> fy; int Ny, Nx, Nyh, L, tiles_per_plane; T scale;
     const C2<T>* in; T* out;
+    const T* post_diag = nullptr; int post_planes = 1;          // optional Map-basis diagonal applied to the result (plane c uses plane c % post_planes)
     DEV void operator()(int blk, unsigned char* smem) const {
         const int c = blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
         Tile<T, false> tv = line_tile<T>(smem, L, fy);
@@ -143,18 +144,23 @@ template <class T> struct C2RColBody {
         CMBL_SYNC();
         fft_inverse_passes<T, false, NT>(tv, fy, 0, fy.npass);
         T* dst = out + ((size_t)c * Nx + x0) * Ny;
+        const T* pd = post_diag ? post_diag + ((size_t)(c % post_planes) * Nx + x0) * Ny : nullptr;
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < L * Ny; e += NT) {
                 const int l = e >> fy.logN, y = e & (Ny - 1);
                 C2<T> z = tv.at(l, y);
-                dst[(size_t)(2 * l) * Ny + y] = z.x * scale;
-                dst[(size_t)(2 * l + 1) * Ny + y] = z.y * scale;
+                const size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
+                T a = z.x * scale, b = z.y * scale;
+                if (pd) { a = pd[ia] * a; b = pd[ib] * b; }                    // same product order as DiagMulBody on the stored map
+                dst[ia] = a; dst[ib] = b;
             }
         }
     }
 };
 
 template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmblStream_t st);
-template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st);
+// post_diag: optional REAL Map-basis diagonal (post_planes planes, broadcast over the batch) multiplied into the result — the
+// pixel mask of M = Mfourier·Mpix rides on the transform's store instead of a separate pass over the maps
+template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st, const T* post_diag = nullptr, int post_planes = 1);
 
 }  // namespace cmbl

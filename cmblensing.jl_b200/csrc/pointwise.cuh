@@ -44,7 +44,7 @@ template <class T, bool CPLX> struct DiagMulBody {
 // ---------------------------------------------------------------------------------------------------------------
 // fused Fourier-space chain on harmonic-basis fields (Npol = 1: no rotation; Npol = 2: planes (E,B) / (Q,U);
 // Npol = 3: planes (I,E,B) / (I,Q,U), the rotation acts on planes 2:3, src/proj_lambert.jl:284,292):
-//   v = in;  v *= din;  v = d − v (or −v when neg);  v *= pre;  v *= pre2;  v = Rot(v);  v *= post;  v −= sdiag·sub;  out = v
+//   v = in;  v *= din;  v = d − v (or −v when neg);  v *= pre;  v *= pre2;  v = Rot(v);  v *= post;  v −= sdiag·sub;  v = Rot2(v);  out = v
 // Npol ≤ 2: every diagonal is REAL with Npol planes shared across the batch (NULL = skip).
 // Npol = 3: every operator is a BlockDiagIEB (src/specialops.jl:61-82) of 4 REAL planes [ΣTE[1,1], ΣTE[2,1], ΣTE[2,2], ΣB]
 //           applied to (I,E,B):  i′ = A11 i + A21 e,  e′ = A21 i + A22 e,  b′ = ΣB b   (the 2×2 block is symmetric).
@@ -57,6 +57,7 @@ template <class T> struct FourierChainBody {
     const T *sin2phi, *cos2phi;
     const C2<T>* in; const T* din; const C2<T>* d; const T* pre; const T* post; const T* sdiag; const C2<T>* sub; C2<T>* out;
     const T* pre2 = nullptr;                          // second pre-rotation operator (Npol = 3 only; diagonals are fused instead)
+    int rot2 = 0;                                     // second rotation applied after `post` (QU→EB, ×B, EB→QU in one pass)
     HD void block(const T* A, size_t r, C2<T>& i, C2<T>& e, C2<T>& b) const {
         const T a11 = A[r], a21 = A[nf + r], a22 = A[2 * nf + r], bb = A[3 * nf + r];
         const C2<T> ni = mk<T>(a11 * i.x + a21 * e.x, a11 * i.y + a21 * e.y);
@@ -95,7 +96,9 @@ template <class T> struct FourierChainBody {
                     size_t e0 = (b * 2) * nf + r, e1 = e0 + nf;
                     C2<T> a = head(in[e0], r, 0, e0), c = head(in[e1], r, 1, e1);
                     if (rot) rotate(rot, r, a, c);
-                    out[e0] = tail(a, r, 0, e0); out[e1] = tail(c, r, 1, e1);
+                    a = tail(a, r, 0, e0); c = tail(c, r, 1, e1);
+                    if (rot2) rotate(rot2, r, a, c);
+                    out[e0] = a; out[e1] = c;
                 }
             } else if (Npol == 3) {
                 if (t < nf * Nb) {
@@ -114,6 +117,7 @@ template <class T> struct FourierChainBody {
                         block(sdiag, r, si, sa, sc);
                         i = i - si; a = a - sa; c = c - sc;
                     }
+                    if (rot2) rotate(rot2, r, a, c);
                     out[e0] = i; out[e1] = a; out[e2] = c;
                 }
             } else {
