@@ -104,20 +104,10 @@ template <class T> static bool fast_cols_ok(const PlanT<T>& P) {
     return P.Nx % cols == 0;
 }
 
-// the pair of fast persistent stage kernels (flow_fast.cuh) serves this plan
-template <class T> static bool flow_fast_ok(const PlanT<T>& P) {
-    return fast_rows_ok(P) && fast_cols_ok(P) && P.Ny % 64 == 0 && P.Nx % 32 == 0;
-}
-static bool generic_rg_enabled() { static const bool v = [] { const char* e = getenv("CMBL_FLOW_GENERIC_RG"); return !e || atoi(e) != 0; }(); return v; }
-// rows per group of the row-grouped internal layout, 0 = the generic kernels on the reference layout.  The fast kernels always
-// work row-grouped; the generic kernels do so for transform lengths above the fast path's (2048, 4096): in the reference layout
-// their row tile is Nx pieces of 2L·sizeof(T) = 32 bytes at a 16 KB stride, row-grouped with G = 2L it is one contiguous run.
+// rows per group of the row-grouped internal layout (flow_fast.cuh), 0 = the generic kernels on the reference layout
 template <class T> int flow_rg_rows(const PlanT<T>& P) {
-    if (flow_fast_ok(P)) return (FAST_TILE_BYTES / (P.Nx * 16)) * (16 / (int)sizeof(T));
-    if (!generic_rg_enabled() || (P.Nx <= 1024 && P.Ny <= 1024)) return 0;
-    const int G = 2 * col_lines<T>(P.ax.fft, P.Ny), V = 16 / (int)sizeof(T);
-    if (G % V != 0 || 64 % G != 0 || P.Ny % 64 != 0 || P.Nx % 32 != 0 || P.Ny % G != 0) return 0;
-    return G;
+    if (!fast_rows_ok(P) || !fast_cols_ok(P) || P.Ny % 64 != 0 || P.Nx % 32 != 0) return 0;
+    return (FAST_TILE_BYTES / (P.Nx * 16)) * (16 / (int)sizeof(T));
 }
 template <class T, bool TO_RG> static void convert_layout(PlanT<T>& P, int G, const T* in, T* out, int C, cmblStream_t st) {
     typedef LayoutBody<T, TO_RG> B;
@@ -130,8 +120,7 @@ static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, c
                        T ca, T cb, cmblStream_t st) {
     PlanT<T>& P = *F.P;
     T* tmp = reinterpret_cast<T*>(F.tmp.p); T* nline = reinterpret_cast<T*>(F.nline.p); T* jn = reinterpret_cast<T*>(F.jn.p);
-    const bool fast = flow_fast_ok(P);
-    const int Grg = fast ? 0 : flow_rg_rows(P);                 // generic kernels on the row-grouped layout
+    const bool fast = flow_rg_rows(P) > 0;
     if (fast) {
         switch (P.Nx) {
             case 256: fast_rows<T, 8, ADJ>(F, c0, nC, u, kq, wgt, st); break;
@@ -142,7 +131,7 @@ static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, c
         FlowRowBody<T, ADJ> b;
         b.fx = P.ax.fft; b.fy = P.ay.fft; b.mult = P.ax.mult_deriv; b.mult_sign_y = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
         b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.ax.fft, P.Ny); b.logL = ilog2(b.L); b.tiles_per_plane = P.Ny / (2 * b.L);
-        b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.G = Grg;
+        b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
         b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.nline = nline; b.jn = jn; b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
         b.counter = reinterpret_cast<int*>(F.counter.p);
         launch(b, nC * b.tiles_per_plane, FlowRowBody<T, ADJ>::smem_bytes(b.fx, b.fy, b.L), st);
@@ -157,7 +146,7 @@ static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, c
         FlowColBody<T, ADJ> b;
         b.fy = P.ay.fft; b.mult_d = P.ay.mult_deriv;
         b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.ay.fft, P.Nx); b.logNyv = ilog2(P.Ny / Vec<T>::N); b.tiles_per_plane = P.Nx / (2 * b.L);
-        b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.G = Grg;
+        b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
         b.u = u; b.pk = F.pk(kq); b.tmp = tmp; b.jn = jn; b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
         b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
         launch(b, nC * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
@@ -265,8 +254,7 @@ template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* ou
     (void)nf;
 }
 
-// 3: fast persistent stage kernels, 1: generic kernels on the row-grouped layout, 0: generic kernels on the reference layout
-template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_fast_ok(*F.P) ? 3 : (flow_rg_rows(*F.P) > 0 ? 1 : 0); }
+template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_rg_rows(*F.P) > 0 ? 3 : 0; }
 
 #define INST(T)                                                                                        \
     template void flow_precompute<T>(FlowT<T>&, const void*, int, bool, cmblStream_t);                 \

@@ -54,7 +54,6 @@ template <class T, bool ADJ> struct FlowRowBody {
     Fft1D<T> fx, fy; const T* mult; const T* mult_sign_y; T cN;
     int Ny, Nx, L, logL, tiles_per_plane, Npol, Nbphi, cbase;
     const T* u; const T* pk; T* tmp; T* nline; T* jn; T* nacc; T wgt; int* counter;
-    int G = 0;                           // > 0: planes are in the row-grouped layout with G = 2L rows per group (a tile = one contiguous run)
     static HD size_t smem_bytes(const Fft1D<T>& fx, const Fft1D<T>& fy, int L) {
         size_t a = Tile<T, false>::bytes(fx.N, L, fx.sk), b = Tile<T, false>::bytes(fy.N, 1, fy.sk);
         return (a > b ? a : b) + 16;
@@ -64,13 +63,12 @@ template <class T, bool ADJ> struct FlowRowBody {
         const size_t nmap = (size_t)Ny * Nx;
         Tile<T, false> tv = line_tile<T>(smem, L, fx);
         int* flag = reinterpret_cast<int*>(smem + smem_bytes(fx, fy, L) - 16);
-        const size_t tile0 = G ? (size_t)(y0 / G) * Nx * G : (size_t)y0;           // row-grouped: rows y0 .. y0+2L-1 are one group
-        const T* uc = u + (size_t)c * nmap + tile0;
-        const T* p1 = ADJ ? p_plane(pk, c, Npol, Nbphi, 0, nmap) + tile0 : nullptr;
+        const T* uc = u + (size_t)c * nmap + y0;
+        const T* p1 = ADJ ? p_plane(pk, c, Npol, Nbphi, 0, nmap) + y0 : nullptr;
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < (Nx << logL); e += NT) {
                 const int x = e >> logL, l = e & (L - 1);
-                const size_t idx = G ? (size_t)e * 2 : (size_t)x * Ny + 2 * l;
+                const size_t idx = (size_t)x * Ny + 2 * l;
                 C2<T> v = *reinterpret_cast<const C2<T>*>(uc + idx);
                 if (ADJ) { C2<T> pp = *reinterpret_cast<const C2<T>*>(p1 + idx); v.x *= pp.x; v.y *= pp.y; }
                 tv.at(l, x) = v;
@@ -79,11 +77,11 @@ template <class T, bool ADJ> struct FlowRowBody {
         CMBL_SYNC();
         RowMid<T, ADJ> mid{mult, nline + (size_t)c * Ny, ADJ ? nacc + (size_t)c * Ny : nullptr, wgt, y0};
         fft_spectral_op<T, false, NT>(tv, fx, mid);
-        T* tc = tmp + (size_t)c * nmap + tile0;
+        T* tc = tmp + (size_t)c * nmap + y0;
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < (Nx << logL); e += NT) {
                 const int x = e >> logL, l = e & (L - 1);
-                *reinterpret_cast<C2<T>*>(tc + (G ? (size_t)e * 2 : (size_t)x * Ny + 2 * l)) = tv.at(l, x);
+                *reinterpret_cast<C2<T>*>(tc + (size_t)x * Ny + 2 * l) = tv.at(l, x);
             }
         }
         // ---- last block of this plane: jn = cN · J[N] ------------------------------------------------------------
@@ -137,32 +135,19 @@ template <class T, bool ADJ> struct FlowColBody {
     int Ny, Nx, L, logNyv, tiles_per_plane, Npol, Nbphi, cbase;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
     const T* ybase; const T* acc_in; T* acc_out; T* u_out; T ca, cb;
-    int G = 0;                           // > 0: planes are in the row-grouped layout (G rows per group, G a multiple of the vector width)
-    // offsets of the vector (column 2l, rows y..y+V-1) and of the same rows of column 2l+1, relative to the tile origin
-    HD void pair_index(int l, int y, size_t& ia, size_t& ib) const {
-        if (G) { ia = ((size_t)(y / G) * Nx + 2 * l) * G + (y % G); ib = ia + G; }
-        else { ia = (size_t)(2 * l) * Ny + y; ib = ia + Ny; }
-    }
-    // e-th vector task of a tile -> (line l, first row y).  Row-grouped: the vectors of one group of rows are taken across the
-    // tile's columns first, so that neighbouring threads read the contiguous run of 2L columns x G rows.
-    HD void task_of(int e, int& l, int& y) const {
-        constexpr int V = Vec<T>::N;
-        if (G) { const int gv = G / V, sub = e % gv, r = e / gv; l = r % L; y = (r / L) * G + sub * V; }
-        else { l = e >> logNyv; y = (e & ((1 << logNyv) - 1)) * V; }
-    }
     DEV void operator()(int blk, unsigned char* smem) const {
         constexpr int V = Vec<T>::N;
         const int c = cbase + blk / tiles_per_plane, x0 = (blk % tiles_per_plane) * 2 * L;
-        const size_t nmap = (size_t)Ny * Nx, xoff = G ? (size_t)x0 * G : (size_t)x0 * Ny, off = (size_t)c * nmap + xoff;
+        const size_t nmap = (size_t)Ny * Nx, off = (size_t)c * nmap + (size_t)x0 * Ny;
         Tile<T, false> tv = line_tile<T>(smem, L, fy);
         const T* uc = u + off;
-        const T* p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap) + xoff;
-        const T* p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap) + xoff;
+        const T* p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap) + (size_t)x0 * Ny;
+        const T* p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap) + (size_t)x0 * Ny;
         const int nvec = L << logNyv;                                   // vectors per tile column-set
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < nvec; e += NT) {
-                int l, y; task_of(e, l, y);
-                size_t ia, ib; pair_index(l, y, ia, ib);
+                const int l = e >> logNyv, y = (e & ((1 << logNyv) - 1)) * V;
+                const size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
                 Vec<T> a = vload(uc + ia), b = vload(uc + ib);
                 if (ADJ) {
                     Vec<T> pa = vload(p2 + ia), pb = vload(p2 + ib);
@@ -181,8 +166,8 @@ template <class T, bool ADJ> struct FlowColBody {
         const T* jc = jn + (size_t)c * Ny;
         CMBL_FOR_THREADS(tid, NT) {
             for (int e = tid; e < nvec; e += NT) {
-                int l, y; task_of(e, l, y);
-                size_t ia, ib; pair_index(l, y, ia, ib);
+                const int l = e >> logNyv, y = (e & ((1 << logNyv) - 1)) * V;
+                const size_t ia = (size_t)(2 * l) * Ny + y, ib = ia + Ny;
                 const C2<T>* src = &tv.at(l, y);
                 Vec<T> j = vload(jc + y), ta = vload(tc + ia), tb = vload(tc + ib), ka, kb;
                 if (ADJ) {

@@ -59,7 +59,7 @@ def test_lenseflow_all_ops(cuda_pkg, Ny, Nx, pol, nb, nbphi, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi,path", [(1024, 512, "P", 2, 2, 3), (512, 1024, "I", 3, 1, 3), (256, 512, "P", 5, 5, 3),
-                                                      (1024, 1024, "I", 1, 1, 3), (64, 1024, "I", 2, 2, 0), (1024, 32, "P", 2, 1, 0), (256, 256, "P", 2, 2, 3), (512, 512, "IP", 2, 2, 3), (2048, 2048, "I", 1, 1, 1), (128, 2048, "P", 2, 2, 1)])
+                                                      (1024, 1024, "I", 1, 1, 3), (64, 1024, "I", 2, 2, 0), (1024, 32, "P", 2, 1, 0), (256, 256, "P", 2, 2, 3), (512, 512, "IP", 2, 2, 3)])
 def test_lenseflow_fast_path(cuda_pkg, Ny, Nx, pol, nb, nbphi, path, dtype):
     """The persistent cp.async stage kernels (csrc/flow_fast.cuh) on the device, all four ops, against the oracle."""
     pkg = cuda_pkg
@@ -72,7 +72,7 @@ def test_lenseflow_fast_path(cuda_pkg, Ny, Nx, pol, nb, nbphi, path, dtype):
     Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
     fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, {"I": "Fourier", "P": "QUFourier", "IP": "IQUFourier"}[pol])
     assert pkg.load().cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == path
-    tol = TOL[dtype] if (dtype == "f64" or max(Ny, Nx) <= 1024) else 5e-5          # fp32 rounding grows with the transform length
+    tol = TOL[dtype]
     for _ in range(2):                                   # twice: persistent-kernel state (tickets, buffers) must reset cleanly
         assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
         assert relerr((L.H * ffour).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LH, Fn)) < tol

@@ -108,11 +108,10 @@ def test_lenseflow_all_ops(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi,path", [(256, 256, "P", 2, 2, 3), (512, 256, "I", 1, 1, 3), (256, 1024, "I", 2, 1, 3),
-                                                      (1024, 512, "I", 1, 1, 3), (256, 256, "IP", 2, 2, 3), (64, 2048, "P", 2, 2, 1), (128, 2048, "I", 2, 1, 1), (2048, 64, "I", 1, 1, -1), (64, 256, "I", 1, 1, 0), (256, 32, "P", 1, 1, 0), (512, 64, "I", 1, 1, 0), (128, 64, "P", 1, 1, 0)])
+                                                      (1024, 512, "I", 1, 1, 3), (256, 256, "IP", 2, 2, 3), (64, 256, "I", 1, 1, 0), (256, 32, "P", 1, 1, 0), (512, 64, "I", 1, 1, 0), (128, 64, "P", 1, 1, 0)])
 def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
     """The persistent cp.async kernels of csrc/flow_fast.cuh (lengths 256/512/1024), all four ops, against the oracle;
-    `path` = 3 when the pair of fast kernels (row-grouped internal layout) must have been used, 1 for the generic pair on the
-    row-grouped layout (transform lengths above 1024), 0 for the generic pair on the reference layout."""
+    `path` = 3 when the pair of fast kernels (row-grouped internal layout) must have been used, 0 for the generic pair."""
     pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=2, mask=False, seed=11, lib=emu)
     L = pkg.LenseFlow(pr["phi"], 2)
     Lo, oproj = pr["Lo"], pr["oproj"]
@@ -121,8 +120,8 @@ def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
     F0 = O.rfft2(fm)
     Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
     fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, {"I": "Fourier", "P": "QUFourier", "IP": "IQUFourier"}[pol])
-    assert path < 0 or emu.cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == path      # -1: depends on the precision (group size)
-    tol = 1e-11 if dtype == "f64" else (2e-5 if max(Ny, Nx) <= 1024 else 5e-5)      # fp32 rounding grows with the transform length
+    assert emu.cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == path
+    tol = 1e-11 if dtype == "f64" else 2e-5
     assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
     assert relerr(L.ldiv(fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LINV, fm)) < tol
     assert relerr((L.H * ffour).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LH, Fn)) < tol
