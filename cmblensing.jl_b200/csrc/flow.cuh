@@ -15,6 +15,15 @@
 #pragma once
 #include "fft2d.cuh"
 
+// launch shape of the two generic stage kernels: 256 threads per tile, two blocks per SM (128 registers) — at Nside=2048 18 % (fp64) /
+// 11 % (fp32) faster than 128 threads x 3 blocks (profiles/r01_generic_flow_launch_shape.log)
+#ifndef CMBL_FLOW_NT
+#define CMBL_FLOW_NT 256
+#endif
+#ifndef CMBL_FLOW_MINB
+#define CMBL_FLOW_MINB 2
+#endif
+
 namespace cmbl {
 
 // p[k] pointer for plane c:  pcache layout [k][Nbphi][2][Nx][Ny]
@@ -49,7 +58,7 @@ template <class T> struct SignMid {                                // J: multipl
 };
 
 template <class T, bool ADJ> struct FlowRowBody {
-    static constexpr int NT = 128, MINB = 3;
+    static constexpr int NT = CMBL_FLOW_NT, MINB = CMBL_FLOW_MINB;
     static const char* name() { return "flow_rows"; }
     Fft1D<T> fx, fy; const T* mult; const T* mult_sign_y; T cN;
     int Ny, Nx, L, logL, tiles_per_plane, Npol, Nbphi, cbase;
@@ -129,7 +138,7 @@ template <class T, bool ADJ> struct ColMid {
 };
 
 template <class T, bool ADJ> struct FlowColBody {
-    static constexpr int NT = 128, MINB = 3;
+    static constexpr int NT = CMBL_FLOW_NT, MINB = CMBL_FLOW_MINB;
     static const char* name() { return "flow_cols"; }
     Fft1D<T> fy; const T* mult_d;
     int Ny, Nx, L, logNyv, tiles_per_plane, Npol, Nbphi, cbase;
