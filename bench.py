@@ -78,6 +78,7 @@ class ClockSampler:
 
     def begin(self):
         if self.nv is not None:
+            sys.setswitchinterval(0.0005)             # let the poll thread in between the launch calls of the timed loop
             self._run = True
             self._thr = threading.Thread(target=self._poll, daemon=True)
             self._thr.start()
@@ -86,6 +87,7 @@ class ClockSampler:
         if self.nv is not None:
             self._run = False
             self._thr.join()
+            sys.setswitchinterval(0.005)
             try:
                 self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
             except Exception:
