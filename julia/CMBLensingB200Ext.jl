@@ -69,12 +69,41 @@ end
 \(L::CachedLenseFlow, f::CuLambertField)                    = (g = Ł(f); apply(L, 2, g, similar(g)))
 \(L::Adjoint{<:Any,<:CachedLenseFlow}, f::CuLambertField)   = (g = Ð(f); apply(parent(L), 3, g, similar(g)))
 
+# ---- pullbacks of L*f and L\f (src/flowops.jl:40-68): the transpose flow negδvelocityᴴ on the device --------------------------
+# (the handle must have been precomputed with with_minv = 1, as `handle` above does)
+function lenseflow_pullback(L::CachedLenseFlow, op, f_out, Δ; bug_compat=true)
+    g, δ = Ł(f_out), Ð(Δ)
+    δf = similar(δ); δϕ = similar(Ð(L.ϕ[]), f_out.Nbatch)
+    check(ccall((:cmbl_lenseflow_grad, lib), Cint, (Ptr{Cvoid}, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Cvoid}),
+                handle(L, g), op, g.arr, δ.arr, δf.arr, δϕ.arr, bug_compat, stream()))
+    δf, δϕ
+end
+@adjoint *(L::CachedLenseFlow, f::CuLambertField) = (Lf = L * f; (Lf, Δ -> reverse(lenseflow_pullback(L, 0, Lf, Δ))))
+@adjoint \(L::CachedLenseFlow, f::CuLambertField) = (Lf = L \ f; (Lf, Δ -> reverse(lenseflow_pullback(L, 2, Lf, Δ))))
+
+# ---- precompute!! (src/lenseflow.jl:80-129): refill the SAME device cache when ϕ changes (no reallocation in a line search) ----
+function precompute!(L::CachedLenseFlow{<:Any,<:Any,<:Any,<:CuLambertField}, f)
+    ϕ = Map(L.ϕ[])
+    check(ccall((:cmbl_lenseflow_precompute, lib), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Cint, Cint, Ptr{Cvoid}), handle(L, f), ϕ.arr, 0, 1, stream())); L
+end
+
+# ---- BlockDiagIEB (src/specialops.jl:77-82,87-88): [ΣTT ΣTE; ΣTE ΣEE] ⊕ ΣBB as four real half-planes --------------------------
+blockplanes(L::BlockDiagIEB) = cat(real.(L.ΣTE[1,1].diag.arr), real.(L.ΣTE[2,1].diag.arr), real.(L.ΣTE[2,2].diag.arr), real.(L.ΣB.diag.arr); dims=3)
+function blockdiag_apply(L::BlockDiagIEB, f::CuLambertField, mode)      # mode 0: L*f, 1: L\f = pinv(L)*f, 2: sqrt(L)*f
+    g = IEBFourier(f); out = similar(g)
+    check(ccall((:cmbl_blockdiag_ieb, lib), Cint, (Ptr{Cvoid}, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Cint, Ptr{Cvoid}),
+                plan(g.metadata), mode, blockplanes(L), g.arr, out.arr, g.Nbatch, stream())); out
+end
+*(L::BlockDiagIEB, f::CuLambertField)  = blockdiag_apply(L, f, 0)
+\(L::BlockDiagIEB, f::CuLambertField) = blockdiag_apply(L, f, 1)
+
 # ---- argmaxf_logpdf for a BaseDataSet on the GPU (src/maximization.jl:17-42) ------------------------------------------
 struct DatasetDesc
     Npol::Cint; Nb::Cint
     Cf::CuPtr{Cvoid}; Cn::CuPtr{Cvoid}; Cnhat::CuPtr{Cvoid}; B::CuPtr{Cvoid}; Bhat::CuPtr{Cvoid}; Mf::CuPtr{Cvoid}
     mask_pix::CuPtr{Cvoid}; d::CuPtr{Cvoid}
 end
+# (for pol = :IP every operator pointer is `blockplanes(op)`, Npol = 3)
 # (construction of the descriptor from ds.Cf, ds.Cn, ds.Cn̂, ds.B, ds.B̂, ds.M (= Mfourier * Mpix) and ds.d, then
 #  cmbl_cg_create + cmbl_wiener_cg; returns (f, history) with history[i] = (i=i, res=batch(res_hist[:,i])).)
 
