@@ -906,14 +906,20 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
     }
     // the three parts of one twiddled radix-R sweep of one thread (butterfly index fixed: element m at x0 + m*xs; chunk-row
     // pairs g0, g0+gs, ...)
-    template <int R, int NP, bool LIN> DEV void sw_load(const T* buf, const T* pbuf, int g0, int gs, int x0, int xs, Chunk (&x)[NP][2][R]) const {
+    // `par` XOR-permutes which chunk row a thread keeps in which slot.  The rows are independent lines, so any consistent choice
+    // is valid; in the sweeps that touch the LINEAR landing order (chunk (x, row) at (x·CPX + row)·16 B: a stride of CPX·16 bytes
+    // across the threads of a quarter-warp, i.e. a CPX-way bank conflict for a fixed row) letting the row depend on the lane makes
+    // the eight 128-bit accesses of a quarter-warp hit eight different 16-byte bank groups.  (The work layout is unaffected: a row
+    // is a multiple of 4 KB there.)
+    static DEV int lane_par(int tid) { return CPX == 2 ? ((tid >> 2) & 1) : CPX == 4 ? ((tid >> 1) & 3) : (tid & 7); }
+    template <int R, int NP, bool LIN> DEV void sw_load(const T* buf, const T* pbuf, int g0, int gs, int x0, int xs, Chunk (&x)[NP][2][R], int par = 0) const {
 #pragma unroll
         for (int i = 0; i < NP; ++i)
 #pragma unroll
             for (int m = 0; m < R; ++m)
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
-                    const int o = off<LIN>(2 * (g0 + i * gs) + s, x0 + m * xs);
+                    const int o = off<LIN>((2 * (g0 + i * gs) + s) ^ par, x0 + m * xs);
                     x[i][s][m] = ld(buf + o);
                     if (pbuf) {
                         Vec<T> p = vload(pbuf + o), a; memcpy(&a, &x[i][s][m], 16);
@@ -946,13 +952,13 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
                     for (int m = 0; m < R; ++m) x[i][s][m].c[h] = v[m];
                 }
     }
-    template <int R, int NP, bool LIN> DEV void sw_store(T* buf, int g0, int gs, int x0, int xs, const Chunk (&x)[NP][2][R]) const {
+    template <int R, int NP, bool LIN> DEV void sw_store(T* buf, int g0, int gs, int x0, int xs, const Chunk (&x)[NP][2][R], int par = 0) const {
 #pragma unroll
         for (int i = 0; i < NP; ++i)
 #pragma unroll
             for (int m = 0; m < R; ++m)
 #pragma unroll
-                for (int s = 0; s < 2; ++s) st(buf + off<LIN>(2 * (g0 + i * gs) + s, x0 + m * xs), x[i][s][m]);
+                for (int s = 0; s < 2; ++s) st(buf + off<LIN>((2 * (g0 + i * gs) + s) ^ par, x0 + m * xs), x[i][s][m]);
     }
     DEV void middle(T* buf, int tid, const T* mlt, T* nline_c, T* nacc_c, int y0) const {
         const int j = tid % NBM;
@@ -1022,19 +1028,19 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
             CMBL_FOR_THREADS(tid, NT) {
                 load_w1(tid, w1);
                 Chunk x[NP1][2][R1];
-                sw_load<R1, NP1, true>(snap, ADJ ? pbuf : nullptr, tid / S1, NT / S1, tid % S1, S1, x);
+                sw_load<R1, NP1, true>(snap, ADJ ? pbuf : nullptr, tid / S1, NT / S1, tid % S1, S1, x, lane_par(tid));
                 sw_compute<R1, NP1, false>(x, w1);
-                sw_store<R1, NP1, false>(buf, tid / S1, NT / S1, tid % S1, S1, x);
+                sw_store<R1, NP1, false>(buf, tid / S1, NT / S1, tid % S1, S1, x, lane_par(tid));
             }
 #else
             {
                 mbar_wait(bars + cur, (unsigned)((it >> 1) & 1));
                 if (ADJ) mbar_wait(bars + 2, (unsigned)(it & 1));
                 Chunk x[NP1][2][R1];
-                sw_load<R1, NP1, true>(buf, ADJ ? pbuf : nullptr, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+                sw_load<R1, NP1, true>(buf, ADJ ? pbuf : nullptr, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x, lane_par(threadIdx.x));
                 __syncthreads();
                 sw_compute<R1, NP1, false>(x, w1);
-                sw_store<R1, NP1, false>(buf, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+                sw_store<R1, NP1, false>(buf, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x, lane_par(threadIdx.x));
             }
 #endif
             CMBL_SYNC();
@@ -1076,17 +1082,17 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
             CMBL_FOR_THREADS(tid, NT) {
                 load_w1(tid, w1);
                 Chunk x[NP1][2][R1];
-                sw_load<R1, NP1, false>(snap, nullptr, tid / S1, NT / S1, tid % S1, S1, x);
+                sw_load<R1, NP1, false>(snap, nullptr, tid / S1, NT / S1, tid % S1, S1, x, lane_par(tid));
                 sw_compute<R1, NP1, true>(x, w1);
-                sw_store<R1, NP1, true>(buf, tid / S1, NT / S1, tid % S1, S1, x);
+                sw_store<R1, NP1, true>(buf, tid / S1, NT / S1, tid % S1, S1, x, lane_par(tid));
             }
 #else
             {
                 Chunk x[NP1][2][R1];
-                sw_load<R1, NP1, false>(buf, nullptr, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+                sw_load<R1, NP1, false>(buf, nullptr, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x, lane_par(threadIdx.x));
                 __syncthreads();
                 sw_compute<R1, NP1, true>(x, w1);
-                sw_store<R1, NP1, true>(buf, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x);
+                sw_store<R1, NP1, true>(buf, threadIdx.x / S1, NT / S1, threadIdx.x % S1, S1, x, lane_par(threadIdx.x));
                 fence_proxy_async();
             }
 #endif
