@@ -29,7 +29,14 @@ namespace cmbl {
 DEV void cp_async16(void* smem_dst, const void* gsrc) {
 #ifdef __CUDA_ARCH__
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    // .ca, not .cg: the L1-bypassing form (LDGSTS.BYPASS) writes shared memory one 32-byte sector per wavefront — exactly 4x the
+    // ideal wavefront count in the ncu source page, a third of the column kernel's shared-memory traffic; through L1 the landing
+    // costs less (column kernel 188 -> 183 us fp64, 100 -> 97 us fp32; profiles/r01_cpasync_ca.log)
+#ifdef CMBL_CPASYNC_CG
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
 #else
     memcpy(smem_dst, gsrc, 16);
 #endif
