@@ -50,11 +50,12 @@ static int fast_block_cap(int full) {     // experiment knob: cap the persistent
     return v > 0 ? std::min(full, v * device_sms()) : full;
 }
 // L2 prefetch of the column kernel's epilogue operands: 0 off, 1-4 = issued before sweep 2 / the middle / sweep 4 / sweep 5.
-// Default: before sweep 4 for fp64 (measured at Nside=1024 batch 8: L*f 7.12 -> 7.04 ms, L'*f 8.11 -> 7.63 ms, Nside=512 -4 %),
-// off for fp32 (neutral to slightly negative).  CMBL_FLOW_PF overrides both.
-static int fast_pf(size_t elem_bytes) {
+// Default: before sweep 4 for fp64 and for the adjoint kernels of both precisions (measured at Nside=1024 batch 8, fp64: L*f
+// 7.12 -> 7.04 ms, L'*f 8.11 -> 7.63 ms, Nside=512 -4 %; fp32: L'*f 4.47 -> 4.32 ms), off for the fp32 forward kernel (neutral to
+// slightly negative).  CMBL_FLOW_PF overrides all.  (profiles/r01_prefetch_sweep.log)
+static int fast_pf(size_t elem_bytes, bool adj) {
     static const int v = [] { const char* e = getenv("CMBL_FLOW_PF"); return e ? atoi(e) : -1; }();
-    return v >= 0 ? v : (elem_bytes == 8 ? 3 : 0);
+    return v >= 0 ? v : ((elem_bytes == 8 || adj) ? 3 : 0);
 }
 
 template <class T, int LOGN, bool ADJ>
@@ -91,7 +92,7 @@ static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, co
     b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv; b.mult_sign = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
     b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / (2 * B::L); b.ntiles = nC * b.tiles_per_plane;
     b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
-    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T)); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
+    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T), ADJ); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
     b.nline = reinterpret_cast<T*>(F.nline.p); b.jn_blk = reinterpret_cast<T*>(F.jn.p); b.jn = nullptr;
     if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
