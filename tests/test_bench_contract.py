@@ -1,0 +1,47 @@
+"""bench.py prints exactly ONE JSON line on stdout with the keys the driver reads (both arms)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+             "config", "e2e", "cpu_baseline"}
+
+
+def _run(args, timeout):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines                       # library chatter goes to stderr
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    """`--impl reference`: the oracle port timed on the host cores, same metric / unit / config as the B200 arm."""
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], 600)
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "lenseflow_batched_applies_per_sec" and d["unit"] == "applies/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.gpu
+def test_b200_arm_line():
+    d = _run(["--steps", "3", "--warmup", "3", "--cg-iters", "2"], 900)
+    assert BASE_KEYS <= set(d) and d.get("impl") != "reference"
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3 and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["gpu_launches"] > 0 and d["value"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.05 < r["frac"] < 1.2
+    assert r["traffic"] is None or r["traffic"] > 0
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] == 8 * 2 * 1024 * 1024 * 8 and 0 < e["value"] < d["value"]
+    c = d["clocks"]
+    assert c["sm_max_mhz"] and c["samples"] >= 1 and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["gpu_vs_oracle_rel_l2"] < 1e-11
