@@ -395,6 +395,13 @@ class CachedLenseFlow:
         self.ϕ = ϕ
         return self
 
+    def get_p(self, k: int) -> np.ndarray:
+        """p[τ_k] = M⁻¹ᵀ∇ϕ at stage k of the 2n+1 cached times (src/lenseflow.jl:131-142), as a host array [Nb_ϕ, 2, Nx, Ny] in the
+        reference's layout (the library may hold it row-grouped internally)."""
+        out = np.empty((self.Nb_ϕ, 2, self.proj.Nx, self.proj.Ny), dtype=_NP_REAL[self.proj.dtype_code])
+        self.proj.lib.call("cmbl_lenseflow_get_p", self.handle, int(k), out.ctypes.data_as(c_void_p))
+        return out
+
     def __del__(self):
         try:
             self.proj.lib.call("cmbl_lenseflow_destroy", self.handle)

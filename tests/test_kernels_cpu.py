@@ -128,6 +128,26 @@ def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
     assert relerr(L.H.ldiv(ffour).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LHINV, Fn)) < tol
 
 
+@pytest.mark.parametrize("Ny,Nx", [(16, 32), (256, 256)])
+def test_precompute_p_cache(pkg, emu, Ny, Nx):
+    """precompute! (src/lenseflow.jl:131-142): p[τ] = M⁻¹ᵀ∇ϕ at all 2n+1 times against the oracle, through both cache layouts
+    (reference layout for the generic kernels, row-grouped for the fast ones), and refilled in place for a new ϕ (precompute!!)."""
+    pr = make_problem(pkg, Ny, Nx, "I", "f64", nb=2, nsteps=3, mask=False, seed=5, lib=emu)
+    L = pkg.LenseFlow(pr["phi"], 3)
+    cache = L.cache(pkg.LenseBasis(pr["f"]))
+    for k in range(7):
+        p = cache.get_p(k)
+        po = np.concatenate([pr["Lo"].p[k][0], pr["Lo"].p[k][1]], axis=1)
+        assert relerr(p, po) < 1e-12
+    with pytest.raises(pkg.CmblError):
+        cache.get_p(7)
+    phi2 = pr["phi"] * 0.5
+    c2 = pkg.LenseFlow(phi2, 3).cache(pkg.LenseBasis(pr["f"]))
+    assert c2 is cache and c2.ϕ is phi2                                    # same handle, refilled
+    Lo2 = O.precompute(pr["oproj"], 0.5 * pr["sim"]["phi"], 3, phi_is_fourier=True)
+    assert relerr(c2.get_p(3), np.concatenate([Lo2.p[3][0], Lo2.p[3][1]], axis=1)) < 1e-12
+
+
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("pol", ["I", "P"])
 def test_lenseflow_adjoint_identity(pkg, emu, pol, dtype):
