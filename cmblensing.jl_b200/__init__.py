@@ -914,10 +914,21 @@ def quadratic_estimate(ds: BaseDataSet, which: str | None = None, wiener_filtere
     d = ds.d
     p = d.proj
     which = which or ("TT" if d.Npol == 1 else "EB")
-    if which not in ("TT", "EE", "EB") or d.Npol != (1 if which == "TT" else 2):
-        raise CmblError(f"which='{which}' not implemented for {d.basis} data")
+    if which not in ("TT", "EE", "EB"):
+        raise CmblError(f"which='{which}' not implemented")
     if ds.Cf̃ is None or ds.Cϕ is None:
         raise CmblError("quadratic_estimate needs BaseDataSet(..., Cf̃=..., Cϕ=...)")
+    if d.Npol == 3:
+        # ds.d[pol], Cf[pol], ... (src/quadratic_estimate.jl:44): the I or the P part of an IQU dataset;
+        # BlockDiagIEB[:P] = Diagonal(EBFourier(E, B)), [:I] = ΣTT (src/specialops.jl:107-113)
+        sl_op = (lambda L: L._real[:, 0:1]) if which == "TT" else (lambda L: L._real[:, 2:4])
+        basis = "Fourier" if which == "TT" else "EBFourier"
+        D = lambda L: DiagOp(Field(basis, sl_op(L).contiguous().to(p.cT), p))
+        dsub = Field(basis, (d.arr[:, 0:1] if which == "TT" else d.arr[:, 1:3]).contiguous(), p)
+        sub = BaseDataSet(dsub, D(ds.Cf), D(ds.Cn), D(ds.B), D(ds.Mf), None, D(ds.Cnhat), D(ds.Bhat), L=ds.L, nsteps=ds.nsteps, Cϕ=ds.Cϕ, Cf̃=D(ds.Cf̃))
+        return quadratic_estimate(sub, which, wiener_filtered, weights, AL, abs_each_term)
+    if d.Npol != (1 if which == "TT" else 2):
+        raise CmblError(f"which='{which}' not implemented for {d.basis} data")
     dev, cT = p.device, p.cT
     lx = torch.from_numpy(p.ℓx).to(dev)[:, None]; ly = torch.from_numpy(p.ℓy).to(dev)[None, :]
     grad = {1: (1j * lx).to(cT).expand(p.Nx, p.Nyh), 2: (1j * ly).to(cT).expand(p.Nx, p.Nyh)}

@@ -758,7 +758,14 @@ def quadratic_estimate(ds: DataSet, which: str | None = None, wiener_filtered: b
     proj, pol = ds.proj, ds.pol
     assert weights in ("lensed", "unlensed")
     which = which or ("TT" if pol == "I" else "EB")
-    assert which in ("TT", "EE", "EB") and pol in (("I",) if which == "TT" else ("P",))
+    assert which in ("TT", "EE", "EB")
+    if pol == "IP":          # ds.d[pol], Cf[pol], ... (:44): the I or the P part of an IQU dataset; BlockDiagIEB[:P] = Diagonal(E, B), [:I] = ΣTT
+        part = (lambda A: A[:, 0:1]) if which == "TT" else (lambda A: A[:, 2:4])
+        dpart = (lambda F: F[:, 0:1]) if which == "TT" else (lambda F: F[:, 1:3])
+        sub = DataSet(proj, "I" if which == "TT" else "P", part(ds.Cf), part(ds.Cn), part(ds.Cnhat), part(ds.B), part(ds.Bhat), part(ds.Mf), None,
+                      dpart(ds.d), ds.L, Cphi=ds.Cphi, Cftilde=part(ds.Cftilde))
+        return quadratic_estimate(sub, which, wiener_filtered, weights, AL, None if d2 is None else dpart(d2), abs_each_term)
+    assert pol in (("I",) if which == "TT" else ("P",))
     leg = _QELegs(proj)
     grad = {1: leg.d1, 2: leg.d2}
     TF = ds.Mf * ds.Bhat
@@ -924,7 +931,7 @@ def make_dataset(Ny, Nx, theta_pix, pol="I", T=np.float64, nb=1, seed=0, nsteps=
     ds = DataSet(proj, pol, Cf, Cn, Cn.copy(), B, B.copy(), Mf, Mpix, None, L)
     ds.Cphi = Cphi
     ds.Nphi = (Cphi * 0 + np.median(Cphi[Cphi > 0]) if np.any(Cphi > 0) else Cphi + 1).astype(proj.T)   # stand-in; load_sim's value is quadratic_estimate(ds).Nϕ / 2 (:316), see `nphi_from_qe`
-    if pol != "IP" and "tot_TT" in cls:
+    if "tot_TT" in cls:
         ds.Cftilde = np.stack([cl_to_cov(proj, ell, cls["tot_" + k]) for k in keys])[None]
     ft = lenseflow_apply(L, OP_L, to_lense_basis(pol, proj, f))
     d = (apply_M(ds, op_mul(pol, B, to_harmonic_basis(pol, proj, ft))) + n).astype(proj.cT)

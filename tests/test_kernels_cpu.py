@@ -294,7 +294,7 @@ def test_logpdf_mixed_gradient_and_map_joint(pkg, emu, pol):
     assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum()
 
 
-@pytest.mark.parametrize("pol,which", [("I", "TT"), ("P", "EE"), ("P", "EB")])
+@pytest.mark.parametrize("pol,which", [("I", "TT"), ("P", "EE"), ("P", "EB"), ("IP", "EB"), ("IP", "TT")])
 def test_quadratic_estimate(pkg, emu, pol, which):
     """quadratic_estimate (src/quadratic_estimate.jl:30-199): AL = Nϕ and the (Wiener-filtered) estimate against the oracle, with the
     reference's per-term abs.() normalisation and with the exact one."""
@@ -310,7 +310,8 @@ def test_quadratic_estimate(pkg, emu, pol, which):
     assert relerr(r2["ϕqe"].cpu_numpy() * (pr["oproj"].lmag < 5000), ro2["phi_qe"] * (pr["oproj"].lmag < 5000)) < 1e-8
     with pytest.raises(pkg.CmblError):
         pkg.quadratic_estimate(pr["ds"], "TE")
-    assert relerr(pkg.mixing_D(pr["ds"])._real.numpy(), O.mixing_D(pr["dso"])) < 1e-13
+    if pol != "IP":
+        assert relerr(pkg.mixing_D(pr["ds"])._real.numpy(), O.mixing_D(pr["dso"])) < 1e-13
 
 
 def test_hmc_step_phi(pkg, emu):
