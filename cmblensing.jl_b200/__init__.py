@@ -704,9 +704,19 @@ def mixing_D(ds: BaseDataSet, σ_len_arcmin: float = 5.0) -> DiagOp:
     """The mixing matrix load_sim attaches to a dataset: D = sqrt((Cf + (σ²len + 2Cn̂)) · pinv(Cf)), σ²len = deg2rad(5/60)²
     (src/dataset.jl:325-332).  It decorrelates f° from ϕ°, which is what makes pinv(Cϕ)+pinv(Nϕ) a usable ϕ° Hessian in MAP_joint
     (with D = 1 the line search collapses to α ~ 1e-4)."""
-    if not isinstance(ds.Cf, DiagOp):
-        raise CmblError("mixing_D is implemented for diagonal Cf (pol = I, P)")
     σ2 = float(np.deg2rad(σ_len_arcmin / 60.0) ** 2)
+    if isinstance(ds.Cf, BlockDiagIEB):
+        # BlockDiagIEB algebra (src/specialops.jl:99-105: UniformScaling adds to the diagonal entries and to B, `*` is the 2×2 matrix
+        # product) and the 2×2 sqrt of src/field_vectors.jl:62-67, which reads the off-diagonal of the product from [2,1]
+        pinv = lambda t: torch.where(t == 0, torch.zeros_like(t), 1 / t)
+        cf, cn = ds.Cf._real[0], ds.Cnhat._real[0]
+        idet = pinv(cf[0] * cf[2] - cf[1] * cf[1])
+        pa, pc, pd, pe = cf[2] * idet, -(cf[1] * idet), cf[0] * idet, pinv(cf[3])
+        a, c, d, e = cf[0] + (σ2 + 2 * cn[0]), cf[1] + 2 * cn[1], cf[2] + (σ2 + 2 * cn[2]), cf[3] + (σ2 + 2 * cn[3])
+        A, C, D_, E = a * pa + c * pc, c * pa + d * pc, c * pc + d * pd, e * pe                   # [1,1], [2,1], [2,2], B of the product
+        s_ = torch.sqrt(A * D_ - C * C)
+        t_ = pinv(torch.sqrt(A + (D_ + 2 * s_)))
+        return BlockDiagIEB(t_ * (A + s_), t_ * C, t_ * (D_ + s_), torch.sqrt(E), proj=ds.Cf.proj)
     cf, cn = ds.Cf._real, ds.Cnhat._real
     r = torch.sqrt((cf + (σ2 + 2 * cn)) * torch.where(cf == 0, torch.zeros_like(cf), 1 / cf))
     return DiagOp(Field(ds.Cf.diag.basis, r.to(ds.Cf.diag.arr.dtype), ds.Cf.diag.proj))

@@ -211,12 +211,19 @@ def block_hess_sandwich(X: np.ndarray, M: np.ndarray, Y: np.ndarray) -> np.ndarr
 
 
 def op_mul(pol: str, A: np.ndarray, F: np.ndarray) -> np.ndarray:
-    """Harmonic-basis operator times field: DiagOp for I / P, BlockDiagIEB (4 planes) for IP."""
-    return block_mul(A, F).astype(F.dtype) if pol == "IP" else A * F
+    """Harmonic-basis operator times field: DiagOp (Npol planes), or BlockDiagIEB (4 planes) for IP."""
+    return block_mul(A, F).astype(F.dtype) if (pol == "IP" and A.shape[1] == 4) else A * F
 
 
 def op_pinv(pol: str, A: np.ndarray) -> np.ndarray:
     return block_pinv(A) if pol == "IP" else pinv_diag(A)
+
+
+def op_ldiv(pol: str, A: np.ndarray, F: np.ndarray) -> np.ndarray:
+    """A \\ f: nan2zero(f ./ diag) for a DiagOp, pinv(L) * f for a BlockDiagIEB (src/specialops.jl:10,78)."""
+    if pol == "IP" and A.shape[1] == 4:
+        return block_mul(block_pinv(A), F).astype(F.dtype)
+    return diag_ldiv(A, F)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -533,7 +540,7 @@ def gradientf_logpdf(ds: DataSet, f_harm: np.ndarray, d: np.ndarray) -> np.ndarr
 def mix(ds: DataSet, proj: ProjLambert, pol: str, f_harm: np.ndarray, phi_four: np.ndarray, D=None, G=None, nsteps: int = 7):
     """mix(ds; f, ϕ) (src/dataset.jl:96-101): f° = L(ϕ)·D·f (returned in the Map/QUMap basis), ϕ° = G·ϕ."""
     L = precompute(proj, phi_four, nsteps, phi_is_fourier=True)
-    Df = f_harm if D is None else diag_mul(D, f_harm)
+    Df = f_harm if D is None else op_mul(pol, D, f_harm)
     return lenseflow_apply(L, OP_L, to_lense_basis(pol, proj, Df)), (phi_four if G is None else diag_mul(G, phi_four))
 
 
@@ -542,7 +549,7 @@ def unmix(ds: DataSet, proj: ProjLambert, pol: str, f_mixed_map: np.ndarray, phi
     phi = phi_mixed if G is None else diag_ldiv(G, phi_mixed)
     L = precompute(proj, phi, nsteps, phi_is_fourier=True)
     f = to_harmonic_basis(pol, proj, lenseflow_apply(L, OP_LINV, f_mixed_map))
-    return (f if D is None else diag_ldiv(D, f)), phi
+    return (f if D is None else op_ldiv(pol, D, f)), phi
 
 
 def hess_preconditioner(ds: DataSet) -> np.ndarray:
@@ -649,8 +656,15 @@ def logpdf(ds: DataSet, f_harm: np.ndarray, phi_four: np.ndarray, d=None) -> np.
 
 
 def mixing_D(ds: DataSet, sigma_len_arcmin: float = 5.0) -> np.ndarray:
-    """load_sim's D = sqrt((Cf + (σ²len + 2Cn̂)) pinv(Cf)), σ²len = deg2rad(5/60)² (src/dataset.jl:325-332)."""
+    """load_sim's D = sqrt((Cf + (σ²len + 2Cn̂)) pinv(Cf)), σ²len = deg2rad(5/60)² (src/dataset.jl:325-332).  For pol = IP the
+    BlockDiagIEB algebra of src/specialops.jl:99-105 (UniformScaling adds to the diagonal entries and to B; `*` is the 2×2 matrix
+    product) followed by the 2×2 sqrt of src/field_vectors.jl:62-67, which reads the off-diagonal of the product from [2,1]."""
     s2 = ds.proj.T(np.deg2rad(sigma_len_arcmin / 60.0) ** 2)
+    if ds.pol == "IP":
+        cf, cn, pi = ds.Cf, ds.Cnhat, block_pinv(ds.Cf)
+        a, c, d, e = cf[:, 0] + (s2 + 2 * cn[:, 0]), cf[:, 1] + 2 * cn[:, 1], cf[:, 2] + (s2 + 2 * cn[:, 2]), cf[:, 3] + (s2 + 2 * cn[:, 3])
+        P = np.stack([a * pi[:, 0] + c * pi[:, 1], c * pi[:, 0] + d * pi[:, 1], c * pi[:, 1] + d * pi[:, 2], e * pi[:, 3]], axis=1)   # [1,1], [2,1], [2,2], B
+        return block_sqrt(P).astype(ds.proj.T)
     return np.sqrt((ds.Cf + (s2 + 2 * ds.Cnhat)) * pinv_diag(ds.Cf)).astype(ds.proj.T)
 
 
@@ -670,7 +684,7 @@ def gradient_logpdf_mixed(ds: DataSet, f_mixed_map: np.ndarray, phi_mixed: np.nd
     L = precompute(proj, phi, ds.L.nsteps, phi_is_fourier=True)
     f1 = lenseflow_apply(L, OP_LINV, f_mixed_map)                                   # Map
     f1h = to_harmonic_basis(ds, proj, f1)
-    f = f1h if ds.D is None else diag_ldiv(ds.D, f1h)
+    f = f1h if ds.D is None else op_ldiv(pol, ds.D, f1h)
     ft = lenseflow_apply(L, OP_L, to_lense_basis(ds, proj, f))
     r = ds.d - apply_M(ds, op_mul(pol, ds.B, to_harmonic_basis(ds, proj, ft)))
     x, is_map = apply_MH(ds, op_mul(pol, op_pinv(pol, ds.Cn), r))
@@ -681,7 +695,7 @@ def gradient_logpdf_mixed(ds: DataSet, f_mixed_map: np.ndarray, phi_mixed: np.nd
     df_a, dphi_a = lenseflow_grad(L, OP_L, ft, deriv(g_ft), bug_compat)
     df_a = qu_to_eb(proj, df_a, pol0) if pol != "I" else df_a
     g_f = df_a - op_mul(pol, op_pinv(pol, ds.Cf), f)
-    g_f1 = g_f if ds.D is None else diag_ldiv(ds.D, g_f)                            # D real, diagonal: D⁻ᵀ = D⁻¹
+    g_f1 = g_f if ds.D is None else op_ldiv(pol, ds.D, g_f)                         # D real and symmetric: D⁻ᵀ = D⁻¹
     df0, dphi_b = lenseflow_grad(L, OP_LINV, f1, deriv(g_f1), bug_compat)
     g_phi = dphi_a + dphi_b - pinv_diag(ds.Cphi) * phi
     if ds.G is not None:
