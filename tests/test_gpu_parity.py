@@ -212,6 +212,28 @@ def test_quadratic_estimate(cuda_pkg, pol, which):
     assert relerr(r["ϕqe"].cpu_numpy(), ro["phi_qe"]) < 1e-8
 
 
+def test_map_joint_iqu_with_block_mixing(cuda_pkg):
+    """Config 4's algorithm at a small size on the device: IQU data, load_sim's mixing matrix as a BlockDiagIEB, Nϕ from the EB
+    quadratic estimate; gradient parity with the oracle and two MAP_joint steps with a fixed CG iteration count."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, 64, 64, "IP", "f64", nb=1, nsteps=5, mask=True, seed=3, theta=2.0, device=DEV)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    dso.D = O.mixing_D(dso); ds.D = pkg.mixing_D(ds)
+    assert relerr(ds.D._real.cpu().numpy(), dso.D) < 1e-12
+    dso.Nphi = (O.quadratic_estimate(dso)["Nphi"] / 2).astype(oproj.T)
+    ds.Nϕ = pkg.DiagOp(pr["F"](pkg.quadratic_estimate(ds)["Nϕ"]._real.cpu().numpy() / 2, "Fourier"))
+    fm, pm = pkg.mix(ds, pr["f"], pr["phi"])
+    fmo, pmo = O.mix(dso, oproj, "IP", pr["sim"]["f"], pr["sim"]["phi"], D=dso.D, G=None, nsteps=5)
+    gf, gp = pkg.gradient_logpdf_mixed(ds, fm, pm)
+    gfo, gpo = O.gradient_logpdf_mixed(dso, fmo, pmo)
+    assert relerr(gf.cpu_numpy(), gfo) < 1e-9 and relerr(gp.cpu_numpy(), gpo) < 1e-9
+    f, ϕ, hist = pkg.MAP_joint(ds, nsteps=2, conjgrad_kwargs=dict(tol=0.0, nsteps=40))
+    f_o, ϕ_o, histo = O.MAP_joint(dso, nsteps=2, conjgrad_kwargs=dict(tol=0.0, nsteps=40))
+    for h, ho in zip(hist, histo):
+        assert h["cg_iters"] == ho["cg_iters"] == 40 and abs(h["α"] - ho["alpha"]) < 1e-4 and 0.05 < h["α"] < 4
+    assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum() and relerr(ϕ.cpu_numpy(), ϕ_o) < 1e-4
+
+
 def test_hmc_step_phi(cuda_pkg):
     """gibbs_sample_ϕ! / hmc_step / symplectic_integrate (src/sampling.jl:14-55,397-425) on the device vs the oracle, same draws."""
     pkg = cuda_pkg
