@@ -29,7 +29,7 @@ __all__ = [
     "LenseFlow", "CachedLenseFlow", "DiagOp", "Diagonal", "BlockDiagIEB", "dot", "BaseDataSet", "gradientf_logpdf",
     "Hessian_logpdf_preconditioner", "mix", "unmix", "argmaxf_logpdf", "argmaxf_lnP", "conjugate_gradient_wiener", "batch", "unbatch",
     "Cℓ_to_2D", "Cℓ_to_Cov", "Cl_to_Cov", "simulate", "sample_f", "convert",
-    "quadratic_estimate", "mixing_D", "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint", "symplectic_integrate", "hmc_step", "mass_matrix_ϕ", "gibbs_sample_ϕ",
+    "quadratic_estimate", "mixing_D", "logdet", "logpdf", "Mixed", "gradient_logpdf_mixed", "MAP_joint", "symplectic_integrate", "hmc_step", "mass_matrix_ϕ", "gibbs_sample_ϕ", "sample_joint",
     "CmblError", "load",
 ]
 
@@ -1015,3 +1015,23 @@ def quadratic_estimate(ds: BaseDataSet, which: str | None = None, wiener_filtere
         ϕ = Cp * pinv(Cp + ALr) * ϕ
     ALop = DiagOp(Field("Fourier", ALr.to(cT), p))
     return {"ϕqe": Field("Fourier", ϕ.to(cT), p), "AL": ALop, "Nϕ": ALop}      # string keys: identifiers would be NFKC-normalised (ϕ → φ)
+
+
+def sample_joint(ds: BaseDataSet, ϕstart: Field, nsamps_per_chain: int | None = None, symp_kwargs=(dict(N=25, ϵ=0.01),), nburnin_always_accept: int = 10,
+                 conjgrad_kwargs=dict(tol=1e-1, nsteps=500), draws=None, generator=None, bug_compat: bool = True):
+    """sample_joint (src/sampling.jl:180-336) for (f, ϕ) at fixed θ: the Gibbs passes gibbs_sample_f! (sample_f), gibbs_mix!,
+    gibbs_sample_ϕ! (one HMC update of ϕ° per entry of symp_kwargs), gibbs_unmix! (:388-451).  The batch dimension carries independent
+    chains (the reference's `Nbatch` chains per worker); steps are numbered from 2 and proposals are always accepted while
+    step < nburnin_always_accept, like the reference.  `draws` (optional, one dict(wf, wn, wp, u) per step) fixes the random numbers.
+    Returns the chain as a list of dicts (f, ϕ, ΔH, accept, logpdf)."""
+    nsteps = len(draws) if draws is not None else (nsamps_per_chain - 1)
+    ϕ, chain = Fourier(ϕstart), []
+    for i in range(nsteps):
+        step = i + 2
+        dr = draws[i] if draws is not None else {}
+        f, _ = sample_f(ds, ϕ, dr.get("wf"), dr.get("wn"), generator, conjgrad_kwargs)
+        f_m, ϕ_m = mix(ds, f, ϕ)
+        ϕ_m, ΔH, acc = gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs, step < nburnin_always_accept, dr.get("wp"), dr.get("u"), bug_compat)
+        f, ϕ = unmix(ds, f_m, ϕ_m)
+        chain.append({"step": step, "f": f, "ϕ": ϕ, "ΔH": ΔH, "accept": acc, "logpdf": logpdf(ds, f, ϕ)})      # string keys (no NFKC folding)
+    return chain

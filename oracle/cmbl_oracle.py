@@ -882,6 +882,25 @@ def hmc_step_phi(ds: DataSet, f_mixed_map, phi_mixed, white_map, uniforms, N: in
     return (a * xt + (1 - a) * phi_mixed).astype(proj.cT), dH, accept
 
 
+def sample_joint(ds: DataSet, phi_start, draws, symp_N: int = 25, symp_eps: float = 0.01, nburnin_always_accept: int = 10,
+                 conjgrad_kwargs=dict(tol=1e-1, nsteps=500), bug_compat: bool = True):
+    """The (f, ϕ) Gibbs sampler of sample_joint (src/sampling.jl:180-336) without θ: per step gibbs_sample_f! (sample_f), gibbs_mix!,
+    gibbs_sample_ϕ! (one HMC update of ϕ°), gibbs_unmix! (:388-451); steps are numbered from 2 like the reference and proposals
+    are always accepted while step < nburnin_always_accept.  `draws[i]` = dict(wf, wn, wp, u): the white maps of sample_f, the
+    momentum white map and the accept uniforms of step i.  Returns the chain as a list of dicts."""
+    proj, pol = ds.proj, ds.pol
+    phi, chain = phi_start, []
+    for i, dr in enumerate(draws):
+        step = i + 2
+        ds.L = precompute(proj, phi, ds.L.nsteps, phi_is_fourier=True)
+        f, _ = sample_f(ds, dr["wf"], dr["wn"], **conjgrad_kwargs)
+        fm, pm = mix(ds, proj, pol, f, phi, D=ds.D, G=ds.G, nsteps=ds.L.nsteps)
+        pm, dH, acc = hmc_step_phi(ds, fm, pm, dr["wp"], dr["u"], N=symp_N, eps=symp_eps, always_accept=(step < nburnin_always_accept), bug_compat=bug_compat)
+        f, phi = unmix(ds, proj, pol, fm, pm, D=ds.D, G=ds.G, nsteps=ds.L.nsteps)
+        chain.append(dict(step=step, f=f, phi=phi, dH=dH, accept=acc, logpdf=logpdf(ds, f, phi)))
+    return chain
+
+
 # ----------------------------------------------------------------------------------------------
 # Synthetic flat-sky inputs (harness; mirrors load_sim defaults, src/dataset.jl:186-338)
 # ----------------------------------------------------------------------------------------------

@@ -353,6 +353,27 @@ def test_hmc_step_phi(pkg, emu):
     assert np.all(np.abs(dH) < 5.0)                                # |ΔH| ≪ |H| ~ 1e5: the integrator is symplectic
 
 
+def test_sample_joint_gibbs_chain(pkg, emu):
+    """Two Gibbs steps of sample_joint (src/sampling.jl:180-336: sample_f, mix, HMC in ϕ°, unmix) for two chains in the batch, fed
+    the same random draws as the oracle."""
+    pr = make_problem(pkg, 32, 32, "P", "f64", nb=2, nsteps=4, mask=True, seed=16, theta=3.0, lib=emu)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    dso.D = O.mixing_D(dso); ds.D = pkg.mixing_D(ds)
+    rng = np.random.default_rng(9)
+    w = lambda npol: rng.standard_normal((2, npol) + oproj.map_shape)
+    draws = [dict(wf=w(2), wn=w(2), wp=w(1), u=np.array([0.2, 0.7])) for _ in range(2)]
+    F = pr["F"]
+    dd = [dict(wf=F(d["wf"], "QUMap"), wn=F(d["wn"], "QUMap"), wp=F(d["wp"], "Map"), u=d["u"]) for d in draws]
+    kw = dict(tol=0.0, nsteps=12)
+    chain = pkg.sample_joint(ds, pr["phi"], symp_kwargs=(dict(N=2, ϵ=0.005),), conjgrad_kwargs=kw, draws=dd)
+    chain_o = O.sample_joint(dso, pr["sim"]["phi"], draws, symp_N=2, symp_eps=0.005, conjgrad_kwargs=kw)
+    assert len(chain) == len(chain_o) == 2 and [c["step"] for c in chain] == [2, 3]
+    for c, co in zip(chain, chain_o):
+        assert np.all(c["accept"]) and np.all(co["accept"])                       # burn-in: always accepted
+        assert relerr(c["ϕ"].cpu_numpy(), co["phi"]) < 1e-7 and relerr(pkg.HarmonicBasis(c["f"]).cpu_numpy(), co["f"]) < 1e-7
+        assert np.allclose(c["logpdf"], co["logpdf"], rtol=1e-8)
+
+
 def test_cg_stops_on_tol_like_reference(pkg, emu):
     pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=emu)
     _, h0 = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=0.0)
