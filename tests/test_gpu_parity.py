@@ -234,6 +234,26 @@ def test_map_joint_iqu_with_block_mixing(cuda_pkg):
     assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum() and relerr(ϕ.cpu_numpy(), ϕ_o) < 1e-4
 
 
+def test_sample_joint_gibbs_chain(cuda_pkg):
+    """Two Gibbs steps of sample_joint (sample_f, mix, HMC in ϕ°, unmix; src/sampling.jl:180-336,388-451) on the device, two chains
+    in the batch, same random draws as the oracle."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, 64, 64, "P", "f64", nb=2, nsteps=5, mask=True, seed=16, theta=3.0, device=DEV)
+    ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
+    dso.D = O.mixing_D(dso); ds.D = pkg.mixing_D(ds)
+    rng = np.random.default_rng(9)
+    w = lambda npol: rng.standard_normal((2, npol) + oproj.map_shape)
+    draws = [dict(wf=w(2), wn=w(2), wp=w(1), u=np.array([0.2, 0.7])) for _ in range(2)]
+    F = pr["F"]
+    dd = [dict(wf=F(d["wf"], "QUMap"), wn=F(d["wn"], "QUMap"), wp=F(d["wp"], "Map"), u=d["u"]) for d in draws]
+    kw = dict(tol=0.0, nsteps=12)
+    chain = pkg.sample_joint(ds, pr["phi"], symp_kwargs=(dict(N=2, ϵ=0.002),), conjgrad_kwargs=kw, draws=dd)
+    chain_o = O.sample_joint(dso, pr["sim"]["phi"], draws, symp_N=2, symp_eps=0.002, conjgrad_kwargs=kw)
+    for c, co in zip(chain, chain_o):
+        assert relerr(c["ϕ"].cpu_numpy(), co["phi"]) < 1e-7 and relerr(pkg.HarmonicBasis(c["f"]).cpu_numpy(), co["f"]) < 1e-7
+        assert np.allclose(c["logpdf"], co["logpdf"], rtol=1e-8)
+
+
 def test_hmc_step_phi(cuda_pkg):
     """gibbs_sample_ϕ! / hmc_step / symplectic_integrate (src/sampling.jl:14-55,397-425) on the device vs the oracle, same draws."""
     pkg = cuda_pkg
