@@ -10,8 +10,16 @@ also carries the CG-Wiener iteration rate (`cg`), measured in the same run on th
 
 N>1: launched by torchrun, one rank per GPU; every rank applies its own independent batch-8 field (weak scaling — the path
 shards over independent batch items with no data-path collective); time = max over ranks.
-`--impl reference`: the reference algorithm on the host cores (the NumPy/pocketfft oracle port — Julia is not installed, see
-DESIGN.md), same metric and config, each step a bounded sample (1 of the 8 batch items) scaled to the batch.
+`--impl reference`: the reference algorithm on the host cores (the NumPy oracle port — Julia is not installed; FFT
+provider = the faster of scipy.fft/pocketfft and torch.fft/MKL, timed on the spot), same metric and workload string; each step
+is the WHOLE batch-8 apply (unscaled) whenever K+W such steps fit in ~4 minutes, otherwise the stated subset of items.  Under
+torchrun only rank 0 runs it (one CPU job on the box, NOT multiplied by N); the other ranks exit 0.
+
+Extra keys of the b200 line (all measured in the same run, at the N ranks of the launch):
+  cg        CG-Wiener iterations/s on the headline workload (>= 20 iterations timed) + its own cpu_baseline
+  map_joint BASELINE configs[3]: Nside=2048 IQU, one batch item per GPU, MAP_joint steps with the scalar all-reduce of the line
+            search (and the CG stop flag) inside the timed region
+  hmc       BASELINE configs[4]: Nside=512, 8 chains per GPU, leap-frog steps/s of the HMC update of ϕ°
 """
 import argparse
 import ctypes
@@ -26,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NSIDE, NPOL, NB, NSTEPS_RK, THETA = 1024, 2, 8, 7, 2.0
+WORKLOAD = f"LenseFlow apply Lphi*f, Nside={NSIDE} QU batch={NB} (Cphi={NB}) per GPU, RK4 n={NSTEPS_RK}, theta_pix={THETA}'"
 
 
 def algorithmic_bytes(s):
@@ -118,38 +127,95 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def reference_arm(args, rank):
-    """The reference's CPU algorithm (oracle port) on all host threads; bounded sample per step."""
+def reference_arm(args, rank, world):
+    """The reference's CPU algorithm (oracle port) on all host threads of the box, rank 0 only."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import cmbl_oracle as O
     cores = os.cpu_count() or 1
-    O.set_workers(cores)
     npT = np.float64 if args.dtype == "f64" else np.float32
     proj = O.ProjLambert(NSIDE, NSIDE, THETA, npT)
     rng = np.random.default_rng(0)
-    phi = (rng.standard_normal((1, 1, NSIDE, NSIDE)) * 1e-6).astype(npT)
-    L = O.precompute(proj, phi, NSTEPS_RK)
-    f = rng.standard_normal((1, NPOL, NSIDE, NSIDE)).astype(npT)
-    for _ in range(min(args.warmup, 1)):
-        O.lenseflow_apply(L, O.OP_L, f)
+    cls = O.load_fiducial_cls(); ell = cls["ell"].astype(float)
+    # same synthetic inputs as the b200 arm: ϕ and (E,B) drawn from the fiducial spectra (SURVEY §8d), 8 distinct ϕ
+    phi = O.simulate_diag(proj, O.cl_to_cov(proj, ell, cls["pp"])[None, None], rng, nb=NB)
+    Cf = np.stack([O.cl_to_cov(proj, ell, cls[k]) for k in ("ut_EE", "ut_BB")])[None]
+    f = O.to_lense_basis("P", proj, O.simulate_diag(proj, Cf, rng, nb=NB)).astype(npT)
+    # FFT provider: pocketfft vs MKL (the reference's recommended provider, README.md:56) on one item, keep the faster
+    t_be = {}
+    for be in ("pocketfft", "mkl"):
+        try:
+            O.set_fft_backend(be); O.set_workers(cores)
+            L1 = O.precompute(proj, phi[:1], 1, phi_is_fourier=True)
+            O.lenseflow_apply(L1, O.OP_L, f[:1])
+            t0 = time.perf_counter(); O.lenseflow_apply(L1, O.OP_L, f[:1]); t_be[be] = time.perf_counter() - t0
+        except Exception as e:                                     # torch missing on the box: pocketfft only
+            t_be[be] = float("inf")
+    best = min(t_be, key=t_be.get)
+    O.set_fft_backend(best); O.set_workers(cores)
+    est_item = t_be[best] * NSTEPS_RK                               # one item, n = 7
+    W = 1
+    nit = NB
+    while nit > 1 and est_item * nit * (args.steps + W) > 240.0:    # keep the whole run within ~4 minutes
+        nit //= 2
+    L = O.precompute(proj, phi[:nit], NSTEPS_RK, phi_is_fourier=True)
+    for _ in range(W):
+        O.lenseflow_apply(L, O.OP_L, f[:nit])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.lenseflow_apply(L, O.OP_L, f)
-    dt = (time.perf_counter() - t0) / args.steps          # one batch item
-    ms = dt * NB * 1e3
+        O.lenseflow_apply(L, O.OP_L, f[:nit])
+    dt = (time.perf_counter() - t0) / args.steps
+    ms = dt * (NB / nit) * 1e3
     val = 1e3 / ms
-    sample = f"1 of {NB} batch items per step (QU pair, Nside={NSIDE}, n={NSTEPS_RK}), time scaled x{NB}; scipy.fft/pocketfft workers={cores}"
+    sample = (f"the whole workload per step (all {NB} batch items, unscaled)" if nit == NB else
+              f"{nit} of {NB} batch items per step, time scaled x{NB // nit} (the whole batch would not fit {args.steps}+{W} steps in 4 minutes)")
+    sample += f"; NumPy + {best} ({'scipy.fft' if best == 'pocketfft' else 'torch.fft/MKL'}) on {cores} threads; one-item n=1 probe: " + \
+              ", ".join(f"{k} {v*1e3:.0f} ms" for k, v in t_be.items())
     print_line({
         "impl": "reference", "metric": "lenseflow_batched_applies_per_sec", "value": val, "unit": "applies/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"LenseFlow apply Lphi*f, Nside={NSIDE} QU batch={NB} (Cphi={NB}), RK4 n={NSTEPS_RK}, theta_pix={THETA}'"},
-        "cpu_baseline": {"value": val, "unit": "applies/s", "cores": cores, "kind": "port", "sample": sample},
+        "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": val, "unit": "applies/s", "cores": cores, "kind": "port", "sample": sample, "fft": best},
         "e2e": {"value": val, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ranks": {"world": world, "ran_on": "rank 0 only",
+                  "note": "ONE CPU job on the box's host cores whatever N is: the value is per batch-8 apply and is not multiplied by the number of GPUs"},
     })
+
+
+def build_sim_dataset(pkg, O, N, pol, nb, tT, dev, gen, theta=THETA):
+    """load_sim-like synthetic dataset on the device (src/dataset.jl:186-340): fiducial spectra, 3 µK-arcmin noise with a knee,
+    LowPass(3000) Fourier mask, cosine-apodised 1° pixel mask, d = M B L(ϕ) f + n; Nϕ = quadratic_estimate(ds).Nϕ / 2 and the
+    mixing matrix D of load_sim (:316-332).  Returns (ds, ϕ_true)."""
+    import numpy as np
+    import torch
+    proj = pkg.ProjLambert(N, N, theta, tT, dev)
+    cls = O.load_fiducial_cls(); ell = cls["ell"].astype(float)
+    npol = {"P": 2, "IP": 3}[pol]; lense = ("Map", "QUMap", "IQUMap")[npol - 1]
+    w = lambda p: pkg.Field(("Map", "QUMap", "IQUMap")[p - 1], torch.randn((nb, p, N, N), dtype=tT, device=dev, generator=gen), proj)
+    nT = O.noise_cls(ell); zero = np.zeros_like(nT); one = np.ones_like(nT); lb, wl = O.lowpass_wl(3000)
+    if pol == "IP":
+        Cf = pkg.Cℓ_to_Cov("IP", proj, ell, cls["ut_TT"], cls["ut_EE"], cls["ut_BB"], cls["ut_TE"])
+        Cft = pkg.Cℓ_to_Cov("IP", proj, ell, cls["tot_TT"], cls["tot_EE"], cls["tot_BB"], cls["tot_TE"])
+        Cn = pkg.Cℓ_to_Cov("IP", proj, ell, nT, 2 * nT, 2 * nT, zero)
+        Mf = pkg.Cℓ_to_Cov("IP", proj, lb, wl, wl, wl, np.zeros_like(wl), units=1)
+        B = pkg.Cℓ_to_Cov("IP", proj, ell, one, one, one, zero, units=1)
+    else:
+        Cf = pkg.Cℓ_to_Cov("P", proj, ell, cls["ut_EE"], cls["ut_BB"]); Cft = pkg.Cℓ_to_Cov("P", proj, ell, cls["tot_EE"], cls["tot_BB"])
+        Cn = pkg.Cℓ_to_Cov("P", proj, ell, 2 * nT, 2 * nT); Mf = pkg.Cℓ_to_Cov("P", proj, lb, wl, wl, units=1)
+        B = pkg.Cℓ_to_Cov("P", proj, ell, one, one, units=1)
+    Cϕ = pkg.Cℓ_to_Cov("I", proj, ell, cls["pp"])
+    mask = torch.from_numpy(O.cosine_border_mask(O.ProjLambert(N, N, theta, np.float32 if tT == torch.float32 else np.float64), 1.0))
+    Mpix = pkg.DiagOp(pkg.Field(lense, mask[None, None].expand(1, npol, N, N).contiguous(), proj))
+    ϕ_true = pkg.DiagOp(pkg.Field("Fourier", torch.sqrt(Cϕ._real), proj)) * w(1)
+    ds0 = pkg.BaseDataSet(pkg.HarmonicBasis(w(npol)), Cf, Cn, B, Mf, Mpix, nsteps=NSTEPS_RK, Cϕ=Cϕ, Cf̃=Cft)
+    sim = pkg.simulate(ds0, ϕ_true, generator=gen)
+    ds = pkg.BaseDataSet(sim["d"], Cf, Cn, B, Mf, Mpix, nsteps=NSTEPS_RK, Cϕ=Cϕ, Cf̃=Cft)
+    qe = pkg.quadratic_estimate(ds)
+    ds.Nϕ = pkg.DiagOp(pkg.Field("Fourier", (qe["Nϕ"]._real / 2).to(proj.cT), proj))
+    ds.D = pkg.mixing_D(ds)
+    return ds, ϕ_true
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -160,9 +226,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cg-iters", type=int, default=4)
+    ap.add_argument("--cg-iters", type=int, default=20)
+    ap.add_argument("--skip", default="", help="comma list of optional sections to skip: cg,map_joint,hmc,other,cpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    skip = set(x for x in args.skip.split(",") if x)
+    if args.no_cpu_baseline:
+        skip.add("cpu")
     # stdout carries exactly ONE JSON line: library chatter (e.g. "NCCL version ..." printed at communicator creation) is sent
     # to stderr by pointing fd 1 at fd 2 for the duration of the run; the line itself is written to the saved descriptor.
     sys.stdout.flush()
@@ -173,7 +243,7 @@ def main():
         _real_stdout.write(json.dumps(obj) + "\n"); _real_stdout.flush()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return reference_arm(args, rank)
+        return reference_arm(args, rank, world)
 
     import numpy as np
     import torch
@@ -189,6 +259,8 @@ def main():
     tT = torch.float64 if args.dtype == "f64" else torch.float32
     s = 8 if args.dtype == "f64" else 4
     AB = algorithmic_bytes(s)
+    peak, peak_src = measured_peak()
+    peak_gbs = peak
     proj = pkg.ProjLambert(NSIDE, NSIDE, THETA, tT, dev)
 
     # ---- synthetic inputs (seeded per rank), SURVEY §8(d): ϕ, f drawn from the fiducial spectra ---------------------
@@ -271,21 +343,53 @@ def main():
 
     def step_host():
         lib.call("cmbl_lenseflow_apply_host", cache.handle, 0, P(hin), P(hout), st)
-    ms_e2e, _ = timed(step_host, max(3, args.steps // 2), 2)
+    ms_e2e, _ = timed(step_host, max(3, args.steps // 2), 3)
     assert float((hout.to(dev) - out).abs().max()) == 0.0, "host path and device path disagree"
+    # the same bytes with no compute in between (H2D and D2H back to back on one stream): what the host link alone costs
+    stage = torch.empty_like(fmap.arr)
+
+    def step_copy():
+        stage.copy_(hin, non_blocking=True); hout.copy_(stage, non_blocking=True); torch.cuda.current_stream().synchronize()
+    ms_copy, _ = timed(step_copy, max(3, args.steps // 2), 2)
+    del stage
 
     # ---- CG-Wiener iterations on the same workload ------------------------------------------------------------------
-    ft = L * fmap
-    d = pkg.gradientf_logpdf  # noqa (keep name visible)
-    data = pkg.HarmonicBasis(ft)                                           # d = M B L f + n  (mask applied inside M)
-    data = pkg.Field("EBFourier", data.arr + noise.arr, proj)
-    ds = pkg.BaseDataSet(data, D(Cf_np), D(Cn_np), D(B_np), D(Mf_np), D(mask_np, "QUMap"), L=L, nsteps=NSTEPS_RK)
-    h, *_ = ds._solver(ϕ)
-    res = (ctypes.c_double * NB)()
-    lib.call("cmbl_cg_begin", h, ctypes.c_void_p(0), 0, res, st)
-    res0 = list(res)
-    ms_cg, launches_cg = timed(lambda: lib.call("cmbl_cg_step", h, res, st), args.cg_iters, 2)
-    res1 = list(res)
+    cg_line = None
+    if "cg" not in skip:
+        ft = L * fmap
+        data = pkg.HarmonicBasis(ft)                                           # d = M B L f + n  (mask applied inside M)
+        data = pkg.Field("EBFourier", data.arr + noise.arr, proj)
+        ds = pkg.BaseDataSet(data, D(Cf_np), D(Cn_np), D(B_np), D(Mf_np), D(mask_np, "QUMap"), L=L, nsteps=NSTEPS_RK)
+        h, *_ = ds._solver(ϕ)
+        res = (ctypes.c_double * NB)()
+        lib.call("cmbl_cg_begin", h, ctypes.c_void_p(0), 0, res, st)
+        res0 = list(res)
+        nul = ctypes.POINTER(ctypes.c_double)()                                # NULL: residuals stay on the device between polls
+        def cg_iter():
+            lib.call("cmbl_cg_step", h, nul, st)
+        ms_cg, launches_cg = timed(cg_iter, max(args.cg_iters, 20), 3)
+        ms_cg_poll, _ = timed(lambda: lib.call("cmbl_cg_step", h, res, st), 8, 1)      # host reads res after every iteration
+        res1 = list(res)
+        assert all(r == r and r > 0 for r in res1), "CG residual went non-finite"
+        cg_line = {"metric": "cg_wiener_iters_per_sec", "value": world * 1e3 / ms_cg, "unit": "iters/s", "ms_per_iter": ms_cg,
+                   "iters_timed": max(args.cg_iters, 20), "gpu_launches": launches_cg, "algorithmic_GBs": AB["cg_iter"] / ms_cg / 1e6,
+                   "frac": AB["cg_iter"] / ms_cg / 1e6 / peak_gbs, "frac_of_8TBs_nominal": AB["cg_iter"] / ms_cg / 1e6 / 8000.0,
+                   "res_first": res0[0], "res_last": res1[0], "cpu_baseline": None, "ms_per_iter_host_poll_every_iter": ms_cg_poll,
+                   "residual_polling": "cmbl_cg_step(res_host=NULL): α, β, res stay on the device; the host reads them only when it asks"}
+        if rank == 0 and world == 1 and "cpu" not in skip:
+            # the oracle's CG operator on ONE batch item, one iteration's worth of work (A·p = gradientf_logpdf(p, d=0): Lϕ, the
+            # masking chain, Lϕ'), scaled to the batch of 8
+            cores = os.cpu_count() or 1
+            O.set_workers(cores)
+            dso = O.DataSet(proj=op, pol="P", d=data.arr[:1].cpu().numpy(), Cf=Cf_np, Cn=Cn_np, B=B_np, Mf=Mf_np, Mpix=mask_np,
+                            L=O.precompute(op, ϕ.arr[:1].cpu().numpy(), NSTEPS_RK, phi_is_fourier=True))
+            pvec = f.arr[:1].cpu().numpy()
+            t0 = time.perf_counter()
+            O.gradientf_logpdf(dso, pvec, np.zeros_like(pvec))
+            dtc = time.perf_counter() - t0
+            cg_line["cpu_baseline"] = {"value": 1.0 / (dtc * NB), "unit": "iters/s", "cores": cores, "kind": "port", "seconds_sample": dtc,
+                                       "sample": f"1 of {NB} batch items, one operator application A*p (the >97 % of a CG iteration, numerical_algorithms.jl:99), time scaled x{NB}; NumPy + scipy.fft workers={cores}",
+                                       "gpu_over_cpu": (1e3 / ms_cg) * dtc * NB}
 
     # ---- per-kernel durations (CUDA events around each launch, on the launching stream) for the roofline ------------
     barrier()
@@ -295,7 +399,6 @@ def main():
     for line in lib.cdll.cmbl_profile_end().decode().strip().splitlines():
         nm, cnt, tot = line.split()
         prof[nm] = (int(cnt), float(tot))
-    peak, peak_src = measured_peak()
     tot_prof = sum(v[1] for v in prof.values())
     # algorithmic bytes per launch: row kernel 2C passes, column kernel 5C + 2Cϕ passes; the two layout
     # conversions of an apply (2C passes each) are overhead outside the model
@@ -308,17 +411,24 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes,
                 "kernels": {k: {"launches_per_step": v[0] // 2, "avg_ms": v[1] / v[0], "share": v[1] / tot_prof,
                                 "algorithmic_GBs": (kbytes[k] / (v[1] / v[0]) / 1e6 if k in kbytes else None)} for k, v in prof.items()}}
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture — reported only when that capture
+    # was taken from the very binary that is loaded now (sha256 of libcmbl_b200.so recorded next to the numbers), else null
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(args.dtype, {}).get(dom)
+            import hashlib
+            tj = json.load(open(traffic_file))
+            sha = hashlib.sha256(open(lib.path, "rb").read()).hexdigest()[:16]
+            roofline["traffic_capture"] = {"binary_sha16": tj.get("binary_sha16"), "loaded_sha16": sha, "source": tj.get("source")}
+            if tj.get("binary_sha16") == sha:
+                roofline["traffic"] = tj.get(args.dtype, {}).get(dom)
         except Exception:
             pass
     apply_gbs = AB["apply"] / ms_step / 1e6
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample --------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and "cpu" not in skip:
         cores = os.cpu_count() or 1
         O.set_workers(cores)
         nit = 2
@@ -335,7 +445,7 @@ def main():
 
     # ---- the same apply in the other precision (context for the headline; Float32 is what the reference runs on GPUs) ----
     other = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and "other" not in skip:
         oT, odt, osz = (torch.float32, "f32", 4) if args.dtype == "f64" else (torch.float64, "f64", 8)
         proj2 = pkg.ProjLambert(NSIDE, NSIDE, THETA, oT, dev)
         ϕ2 = pkg.Field("Fourier", ϕ.arr.to(torch.complex64 if oT == torch.float32 else torch.complex128), proj2)
@@ -348,27 +458,77 @@ def main():
                  "apply_frac_of_measured_peak": AB2["apply"] / ms2 / 1e6 / peak}
         del c2, out2, f2, ϕ2
 
+    # free the headline workload before the other configs
+    del cache, L, ds, noise, hin, hout
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[3]: Nside=2048 IQU MAP_joint, one batch item per GPU, scalar all-reduces inside the timed region -------
+    mj_line = None
+    if "map_joint" not in skip:
+        gen2 = torch.Generator(device=dev).manual_seed(4321 + rank)
+        ds4, ϕ4 = build_sim_dataset(pkg, O, 2048, "IP", 1, tT, dev, gen2)
+        grp = dist.group.WORLD if world > 1 else None
+        kw = dict(tol=0.0, nsteps=20)                                          # fixed CG length: identical work on every rank and run
+        f0, p0, _ = pkg.MAP_joint(ds4, nsteps=1, conjgrad_kwargs=kw, group=grp)            # warm-up step (allocations, caches)
+        box = {}
+        def mj_steps():
+            box["r"] = pkg.MAP_joint(ds4, ϕstart=p0, fstart=f0, nsteps=2, conjgrad_kwargs=kw, group=grp)
+        ms_mj, launches_mj = timed(mj_steps, 1, 0)
+        hist = box["r"][2]
+        a_, b_ = pkg.Map(box["r"][1]).arr, pkg.Map(ϕ4).arr
+        q = slice(512, 1536)
+        cc = float(torch.corrcoef(torch.stack([a_[0, 0, q, q].flatten(), b_[0, 0, q, q].flatten()]))[0, 1])
+        mj_line = {"metric": "map_joint_seconds_per_step", "value": ms_mj / 2e3, "unit": "s/step", "higher_is_better": False,
+                   "workload": f"MAP_joint, Nside=2048 IQU (BlockDiagIEB operators), 1 batch item per GPU x {world} GPUs, CG fixed at 20 iterations per step, Brent line search on the batch-summed logpdf",
+                   "steps_timed": 2, "gpu_launches_per_step": launches_mj // 2, "dtype": args.dtype,
+                   "collectives": ("none (1 rank)" if world == 1 else f"NCCL all-reduce of 1 scalar per line-search evaluation + 1 flag per CG iteration over {world} ranks, inside the timed region"),
+                   "linesearch_evals": [h["linesearch_evals"] for h in hist], "alpha": [round(float(h["α"]), 5) for h in hist],
+                   "corr_phi_map_vs_truth_rank0": cc, "items_per_sec_aggregate": world / (ms_mj / 2e3)}
+        del ds4, ϕ4, f0, p0, box
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: Nside=512, 8 chains per GPU, HMC leap-frog steps ---------------------------------------------------
+    hmc_line = None
+    if "hmc" not in skip:
+        gen3 = torch.Generator(device=dev).manual_seed(8765 + rank)
+        NCH, NL = 8, 5
+        ds5, ϕ5 = build_sim_dataset(pkg, O, 512, "P", NCH, tT, dev, gen3)
+        f5, _ = pkg.argmaxf_logpdf(ds5, ϕ5, conjgrad_kwargs=dict(tol=0.0, nsteps=10))
+        fm5, pm5 = pkg.mix(ds5, f5, ϕ5)
+        box = {}
+        def hmc_steps():
+            box["r"] = pkg.gibbs_sample_ϕ(ds5, fm5, pm5, symp_kwargs=(dict(N=NL, ϵ=0.01),), always_accept=False)
+        ms_h, launches_h = timed(hmc_steps, 2, 1)
+        dH = box["r"][1]
+        hmc_line = {"metric": "hmc_leapfrog_chain_steps_per_sec", "value": world * NCH * NL * 1e3 / ms_h, "unit": "chain-steps/s", "higher_is_better": True,
+                    "workload": f"HMC update of phi° (sample_joint's gibbs_sample_phi), Nside=512 QU, {NCH} chains per GPU x {world} GPUs = {NCH * world} chains, {NL} leap-frog steps per update (each: gradient of logpdf(Mixed) = 2 flows + 2 delta-flows)",
+                    "ms_per_leapfrog_step": ms_h / NL, "gpu_launches_per_leapfrog_step": launches_h // (2 * NL), "dtype": args.dtype,
+                    "collectives": "none: chains are independent (pmap over chains, src/sampling.jl:292-307)", "abs_dH_max_rank0": float(np.max(np.abs(dH)))}
+        del ds5, ϕ5, f5, fm5, pm5, box
+        torch.cuda.empty_cache()
+
     if rank == 0:
         nbytes = fmap.arr.numel() * fmap.arr.element_size()
         line = {
             "metric": "lenseflow_batched_applies_per_sec", "value": world * 1e3 / ms_step, "unit": "applies/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"LenseFlow apply Lphi*f, Nside={NSIDE} QU batch={NB} (Cphi={NB}) per GPU, RK4 n={NSTEPS_RK}, theta_pix={THETA}'",
+            "config": {"workload": WORKLOAD,
                        "l2": "working set (4 state buffers 4x%.0f MB + p-cache %.1f GB) exceeds the 126 MB L2" % (nbytes / 1e6, 15 * NB * 2 * AB["pass_bytes"] / 1e9),
                        "map_applies_per_sec": world * NB * 1e3 / ms_step},
             "clocks": clocks,
             "e2e": {"value": world * 1e3 / ms_e2e, "unit": "applies/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e,
-                    "api": "cmbl_lenseflow_apply_host (pinned host buffers, H2D + apply + D2H)"},
+                    "api": "cmbl_lenseflow_apply_host (pinned host buffers, H2D + apply + D2H)",
+                    "copies_alone_ms_per_step": ms_copy, "device_apply_ms_per_step": ms_step},
             "gpu_launches": launches,
             "roofline": roofline,
             "roofline_apply": {"bound": "hbm", "achieved": apply_gbs, "peak": peak, "unit": "GB/s", "frac": apply_gbs / peak, "frac_of_8TBs_nominal": apply_gbs / 8000.0,
                                "algorithmic_bytes_per_apply": AB["apply"]},
             "cpu_baseline": cpu,
             "other_precision": other,
-            "cg": {"metric": "cg_wiener_iters_per_sec", "value": world * 1e3 / ms_cg, "unit": "iters/s", "ms_per_iter": ms_cg, "iters_timed": args.cg_iters,
-                   "gpu_launches": launches_cg, "algorithmic_GBs": AB["cg_iter"] / ms_cg / 1e6, "frac": AB["cg_iter"] / ms_cg / 1e6 / peak,
-                   "res_first": res0[0], "res_last": res1[0]},
+            "cg": cg_line,
+            "map_joint": mj_line,
+            "hmc": hmc_line,
         }
         print_line(line)
     if world > 1:

@@ -846,7 +846,9 @@ def MAP_joint(ds: BaseDataSet, ϕstart: Field | None = None, nsteps: int = 20, f
             α, _, nev = _brent_bounded(obj, 0.0, float(amax), αtol)
             ϕ_m = ϕ_m + Δ * float(α)
             lp = logpdf(mds, f_m, ϕ_m)
-            f, ϕ = unmix(ds, f_m, ϕ_m)
+            # :206 deletes :f from unmix(...): f stays the CG solution (the next step's fstart, :230, and the value returned, :224),
+            # so only the ϕ half of unmix is evaluated (G = 1 here, :137)
+            ϕ = ds.G.ldiv(ϕ_m) if ds.G is not None else ϕ_m
             history.append(dict(step=step, logpdf=lp, α=α, cg_iters=len(cg_hist), linesearch_evals=nev))
     finally:
         ds.G = G_save

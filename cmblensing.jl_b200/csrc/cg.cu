@@ -173,8 +173,12 @@ template <class T> void cg_step(CgT<T>& G, double* res_host, cmblStream_t st) {
     CgUpdate2Body<T> u2{G.nf() * G.Npol, G.res_cur(), G.res_part(), G.res_next(), (const C2<T>*)G.z.p, p};
     launch(u2, G.Nb * RED_BLOCKS, 0, st);
     G.flip = 1 - G.flip;
-    read_scalars(G.h_res.data(), G.res_cur(), G.Nb, st);
-    if (res_host) for (int i = 0; i < G.Nb; ++i) res_host[i] = G.h_res[i];
+    // res_host == NULL: α, β and res stay on the device and nothing synchronises — the caller polls when it wants to (every k-th
+    // iteration, or only at the end of a fixed-length solve); the Nb doubles are read back only when asked for
+    if (res_host) {
+        read_scalars(G.h_res.data(), G.res_cur(), G.Nb, st);
+        for (int i = 0; i < G.Nb; ++i) res_host[i] = G.h_res[i];
+    }
 }
 
 #define INST(T)                                                                                             \

@@ -45,6 +45,8 @@ static int device_sms() {
     return v;
 #endif
 }
+// tile order of the fast column kernel: 1 = contiguous tile range per block (default), 0 = round-robin (see FastColBody)
+static int fast_cols_contig() { static const int v = [] { const char* e = getenv("CMBL_COL_CONTIG"); return e ? atoi(e) : 1; }(); return v; }
 static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
     static const int v = [] { const char* e = getenv("CMBL_FLOW_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     return v > 0 ? std::min(full, v * device_sms()) : full;
@@ -94,9 +96,8 @@ static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, co
     b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
     b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T), ADJ); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
-    b.nline = reinterpret_cast<T*>(F.nline.p); b.jn_blk = reinterpret_cast<T*>(F.jn.p); b.jn = nullptr;
-    if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
-    b.jn_flag = reinterpret_cast<int*>(F.jnflag.p); b.epoch = ++F.jn_epoch;
+    b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = nullptr;
+    b.jn_blk = reinterpret_cast<T*>(F.jnblk.reserve(sizeof(T) * (size_t)b.nblocks * F.Npol * B::N)); b.contig = fast_cols_contig();
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
     launch(b, b.nblocks, B::SMEM, st);
 }

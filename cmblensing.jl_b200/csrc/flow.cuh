@@ -340,7 +340,7 @@ template <class T> struct FlowT : FlowBase {
     int pcache_G = 0;                    // layout of pcache / minv: 0 = reference layout, else rows per row group
     DevBuf yrg;                          // row-grouped copy of the ODE state
     DevBuf g_yf, g_yd, g_yp, g_uf, g_ud, g_up, g_af, g_ad, g_ap, g_kf, g_kd, g_kp, g_ldf, g_gxy, g_a12, g_six, g_spec, g_spec2;   // δ-flow scratch (flow_grad.cu)
-    DevBuf jnflag; int jn_epoch = 0;     // per-plane publication flags of J[N] inside the fast column kernel (value = launch epoch)
+    DevBuf jnblk;                        // per-block J[N] scratch lines of the fast column kernel
     DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, jn, counter, nacc, macc, rows0, spec, gh;
     size_t nmap() const { return P->map_elems(); }
     const T* pk(int k) const { return reinterpret_cast<T*>(pcache.p) + (size_t)k * Nbphi * 2 * nmap(); }

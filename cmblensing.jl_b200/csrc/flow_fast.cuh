@@ -143,26 +143,6 @@ DEV void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
-// publish / await a per-plane flag inside one persistent launch (all blocks are resident, so the producer always runs)
-DEV void flag_publish(int* p, int v) {
-#ifdef __CUDA_ARCH__
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-#else
-    __atomic_store_n(p, v, __ATOMIC_RELEASE);
-#endif
-}
-DEV void flag_await(const int* p, int v) {
-#ifdef __CUDA_ARCH__
-    int got;
-    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p) : "memory"); if (got != v) __nanosleep(200); } while (got != v);
-#else
-    while (__atomic_load_n(p, __ATOMIC_ACQUIRE) != v) {
-#ifdef CMBL_EMU
-        std::this_thread::yield();
-#endif
-    }
-#endif
-}
 DEV int ticket_release(int* p, int n) {
 #ifdef __CUDA_ARCH__
     unsigned old;
@@ -259,7 +239,8 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     static constexpr int TILE = FAST_TILE_BYTES / (int)sizeof(T);                   // reals per tile buffer
     static constexpr int L = TILE / (2 * N);                                         // complex lines (column pairs) per tile
     static constexpr int NB1 = S1 / V, NB2 = N / (R2 * V);                           // bundles per line in pass 1 / pass 2
-    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2);
+    static constexpr int NBUF = ADJ ? 3 : 2;
+    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * NBUF;
     static constexpr bool PDL = true;
     static const char* name() { return "flow_cols"; }
 
@@ -267,8 +248,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     static_assert((1 << LGM) == M, "columns per tile must be a power of two <= 64");
 
     const T* tw1; const T* tw2; const T* mult_d; const T* mult_sign; T cN;     // mult_sign, cN: the Nyquist line operator J (flow.cuh)
-    const T* nline; T* jn_blk;                       // N(y) per plane (row kernel); J[N] lines: [plane][N] (shared by a plane's blocks)
-    int* jn_flag; int epoch;                         // jn_flag[plane] == epoch  <=>  this launch's J[N] of the plane is published
+    const T* nline; T* jn_blk; int contig;           // N(y) per plane (row kernel of this stage); per-block J[N] scratch [block][Npol][N]
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
@@ -342,7 +322,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             const int l = task / NB1, b = task % NB1;
             if (task != tid) load_tw1(w, task);
             T* re = buf + (2 * l) * N; T* im = re + N;
-            const T* pre = (ADJ && !INV) ? pbuf + (2 * l) * N : nullptr;
+            const T* pre = (ADJ && !INV && pbuf) ? pbuf + (2 * l) * N : nullptr;
             bundle_pass<R1, INV>(re, im, pxor(2 * l), pxor(2 * l + 1), b, S1 / V, w, pre, pre ? pre + N : nullptr);
         }
     }
@@ -419,7 +399,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
                 if (!ADJ) { vload_stream2(p1 + g, p1a[k][0], p1a[k][1]); vload_stream2(p2 + g, p2a[k][0], p2a[k][1]); }
                 if (YB) vload_stream2(yb + g, ya[k][0], ya[k][1]);
                 if (AI) vload_stream2(ai + g, aa[k][0], aa[k][1]);
-                jv[k][0] = vload(jc + ch * V); jv[k][1] = vload(jc + (ch + 1) * V);   // published by a peer block before this block's first read (flag), L1 starts empty
+                jv[k][0] = vload(jc + ch * V); jv[k][1] = vload(jc + (ch + 1) * V);   // this block's own lines (L1 / L2)
             }
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
@@ -457,33 +437,41 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         }
     }
 
-    // jn = cN · J[N] of plane c into this block's scratch line: one more spectral operator on a single (real) line, done in
-    // the tile buffer that is not in use (block start: while the first tile is in flight; later: only when the plane changes).
-    DEV void jn_line(T* ws, int c, T* jdst, Tw<R1>& w1, Tw<R2>& w2) const {
-        const T* nl = nline + (size_t)c * N;
+    // jn = cN · J[N] of the Npol planes of one batch item into this block's own scratch lines jdst[Npol][N] (global memory, read
+    // back through L1): one more spectral operator on ceil(Npol/2) complex lines — J maps real lines to real lines, so two planes'
+    // N(y) ride as the real and imaginary part of one line — done in the tile buffer that is not in use (block start: while the
+    // first tile is in flight; later: only when the batch item changes, before the next tile is requested).  Every block computes
+    // the lines it needs itself, so no block ever waits for another block of the launch: the kernel is correct under ANY
+    // residency (concurrent streams, MPS, a partially occupied device).
+    DEV void jn_lines(T* ws, int c0, T* jdst, Tw<R1>& w1, Tw<R2>& w2) const {
+        const int nl = (Npol + 1) / 2;
+        const T* nl0 = nline + (size_t)c0 * N;
         CMBL_FOR_THREADS(tid, NT) {
-            for (int ch = tid; ch < CH; ch += NT) {
+            for (int i = tid; i < 2 * nl * CH; i += NT) {
+                const int pl = i / CH, ch = i % CH;
                 Vec<T> z; for (int e = 0; e < V; ++e) z.v[e] = 0;
-                vstore(ws + swzp(ch, 0) * V, vload(nl + ch * V)); vstore(ws + N + swzp(ch, 1) * V, z);
+                if (pl < Npol) z = vload(nl0 + (size_t)pl * N + ch * V);
+                vstore(ws + pl * N + swzp(ch, pl) * V, z);
             }
             load_tw1(w1, tid);
         }
         CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(ws, nullptr, tid, w1, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(ws, nullptr, tid, w1, nl); CMBL_PRE_END(load_tw2(w2, tid)); }
         CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(ws, tid, w2, 1); }
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(ws, tid, w2, nl); }
         CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { middle(ws, tid, nullptr, 0, mult_sign, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        CMBL_FOR_THREADS(tid, NT) { middle(ws, tid, nullptr, 0, mult_sign, nl); CMBL_PRE_END(load_tw2(w2, tid)); }
         CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(ws, tid, w2, 1); CMBL_PRE_END(load_tw1(w1, tid)); }
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(ws, tid, w2, nl); CMBL_PRE_END(load_tw1(w1, tid)); }
         CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(ws, nullptr, tid, w1, 1); }
+        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(ws, nullptr, tid, w1, nl); }
         CMBL_SYNC();
         CMBL_FOR_THREADS(tid, NT) {
-            for (int ch = tid; ch < CH; ch += NT) {
-                Vec<T> z = vload(ws + swzp(ch, 0) * V);
+            for (int i = tid; i < Npol * CH; i += NT) {
+                const int pl = i / CH, ch = i % CH;
+                Vec<T> z = vload(ws + pl * N + swzp(ch, pl) * V);
                 for (int e = 0; e < V; ++e) z.v[e] *= cN;
-                vstore(jdst + ch * V, z);
+                vstore(jdst + (size_t)pl * N + ch * V, z);
             }
         }
         CMBL_SYNC();
@@ -497,46 +485,51 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         Tw<R1> w1; Tw<R2> w2;
         pdl_launch_dependents();
         pdl_wait();
-        // Tile assignment: round-robin over all tiles of the launch (neighbouring blocks work on neighbouring column tiles at
-        // the same time: their 128/256-byte runs share DRAM pages; the launch sweeps through the batch items in order).
-        // The polarisation index runs fastest: the Q and U (I, Q, U) tiles of the same columns are in flight together, so
-        // the p maps they share are fetched from DRAM once.
-        // J[N] of every plane is computed at the start of the launch by the blocks with the highest indices (they have the
-        // fewest tiles) and published through a per-plane flag; a block waits for the flag of a plane (only thread 0 polls)
-        // right before the first epilogue it runs on that plane — by then the line has normally long been published.
-        const int nC = ntiles / tiles_per_plane;
-        auto plane_of = [&](int t) { return cbase + ((t / Npol) / tiles_per_plane) * Npol + t % Npol; };
+        // Tile order: batch item, column tile, polarisation (fastest): the Q and U (I, Q, U) tiles of the same columns follow each
+        // other, so the p maps they share are fetched from DRAM once if they survive in L2 in between.
+        //   contig != 0: block b owns the contiguous tile range [b·ntiles/nblocks, (b+1)·ntiles/nblocks) — a block stays inside one
+        //                batch item for (almost) its whole launch, so it computes that item's J[N] lines once;
+        //   contig == 0: round-robin t = b, b + nblocks, ... (neighbouring blocks work on neighbouring column tiles at the same time);
+        //                correct as well, but a block changes batch item — and recomputes the J[N] lines — almost every tile.
+        T* const jmine = jn_blk + (size_t)blk * Npol * N;
+        auto item_of = [&](int t) { return (t / Npol) / tiles_per_plane; };
         auto x0_of = [&](int t) { return ((t / Npol) % tiles_per_plane) * M; };
-        int tile = blk, cur = 0, cj = -1;
-        if (tile < ntiles) {
-            const int c = plane_of(tile), x0 = x0_of(tile);
+        const int tstep = contig ? 1 : nblocks;
+        const int tend = contig ? (int)((long long)(blk + 1) * ntiles / nblocks) : ntiles;
+        int tile = contig ? (int)((long long)blk * ntiles / nblocks) : blk;
+        int cur = 0, ij = -1;
+        if (tile < tend) {
+            const int it = item_of(tile), c = cbase + it * Npol + tile % Npol, x0 = x0_of(tile);
             CMBL_FOR_THREADS(tid, NT) {
                 issue_tile(u + (size_t)c * nmap, x0, sbase, tid);
                 if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 1, nmap), x0, pbuf, tid);
                 cp_async_commit();
             }
-        }
-        for (int i = nblocks - 1 - blk; i < nC; i += nblocks) {       // while the first tile is in flight
-            jn_line(sbase + TILE, cbase + i, jn_blk + (size_t)(cbase + i) * N, w1, w2);
-            CMBL_FOR_THREADS(tid, NT) { if (tid == 0) flag_publish(jn_flag + cbase + i, epoch); }
+            jn_lines(sbase + TILE, cbase + it * Npol, jmine, w1, w2);          // while the first tile is in flight
+            ij = it;
         }
         CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
-        for (; tile < ntiles; tile += nblocks, cur ^= 1) {
+        for (; tile < tend; tile += tstep, cur ^= 1) {
             T* const buf = sbase + cur * TILE;
             T* const nbuf = sbase + (cur ^ 1) * TILE;
-            const int c = plane_of(tile), x0 = x0_of(tile), next = tile + nblocks;
-            const int cn = plane_of(next), x0n = x0_of(next);
+            const int it = item_of(tile), c = cbase + it * Npol + tile % Npol, x0 = x0_of(tile), next = tile + tstep;
+            const int cn = cbase + item_of(next) * Npol + next % Npol, x0n = x0_of(next);
             const T* const p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
             const T* const p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
-            const T* const jline = jn_blk + (size_t)c * N;
+            const T* const jline = jmine + (size_t)(tile % Npol) * N;
             CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
             CMBL_SYNC();
-            if (next < ntiles) {
+            if (it != ij) {                                            // batch item change: the other tile buffer is free right now
+                jn_lines(nbuf, cbase + it * Npol, jmine, w1, w2);
+                ij = it;
+                CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
+            }
+            if (next < tend) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
-            if (ADJ && next < ntiles) {
+            if (ADJ && next < tend) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0n, pbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
@@ -547,9 +540,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
                 if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1);
-                if (c != cj && tid == 0) flag_await(jn_flag + c, epoch);
             }
-            cj = c;
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
                 if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);

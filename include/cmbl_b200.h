@@ -132,7 +132,8 @@ int cmbl_cg_create(cmbl_cg** cg, cmbl_flow* flow, const cmbl_dataset_desc* ds, v
 int cmbl_cg_destroy(cmbl_cg* cg);
 /* builds b (and a₀), x = fstart (or 0), r, z, p; returns res = dot(r,z) per batch item in res_host[Nb] (history entry i=1) */
 int cmbl_cg_begin(cmbl_cg* cg, const void* fstart_or_null, int offset, double* res_host, void* stream);
-/* one iteration of the loop body (numerical_algorithms.jl:99-121); returns the new res per batch item */
+/* one iteration of the loop body (numerical_algorithms.jl:99-121); returns the new res per batch item in res_host[Nb], or — with
+ * res_host == NULL — leaves it on the device and does not synchronise (poll with a later call that passes a buffer) */
 int cmbl_cg_step(cmbl_cg* cg, double* res_host, void* stream);
 /* record the current x as bestx (the caller implements the lock-step `all(res<bestres)` rule, possibly across ranks) */
 int cmbl_cg_mark_best(cmbl_cg* cg, void* stream);

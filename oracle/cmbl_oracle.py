@@ -34,9 +34,28 @@ import scipy.fft as sfft
 _WORKERS = int(os.environ.get("CMBL_ORACLE_WORKERS", "1"))
 
 
+_FFT_BACKEND = "pocketfft"
+
+
 def set_workers(n: int):
     global _WORKERS
     _WORKERS = max(1, int(n))
+    if _FFT_BACKEND == "mkl":
+        import torch
+        torch.set_num_threads(_WORKERS)
+
+
+def set_fft_backend(name: str):
+    """FFT provider of the restatement: "pocketfft" (scipy.fft, the default and the one every parity test uses) or "mkl"
+    (torch.fft on the CPU = Intel MKL, the provider the reference recommends, README.md:56).  Same transform definition either way;
+    bench.py's reference arm times both and runs the faster one."""
+    global _FFT_BACKEND
+    if name not in ("pocketfft", "mkl"):
+        raise ValueError("fft backend must be 'pocketfft' or 'mkl'")
+    _FFT_BACKEND = name
+    if name == "mkl":
+        import torch
+        torch.set_num_threads(_WORKERS)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -90,6 +109,9 @@ def rfft_degeneracy_fac(n: int) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------
 def rfft2(a: np.ndarray) -> np.ndarray:
     """m_rfft!(dst, arr, (1,2)): unnormalised batched 2-D R2C, halved dim = y (last NumPy axis)."""
+    if _FFT_BACKEND == "mkl":
+        import torch
+        return torch.fft.rfftn(torch.from_numpy(np.ascontiguousarray(a)), dim=(-2, -1)).numpy()
     return sfft.rfftn(a, axes=(-2, -1), workers=_WORKERS)
 
 
@@ -97,6 +119,9 @@ def irfft2(F: np.ndarray, Ny: int) -> np.ndarray:
     """m_irfft!(dst, arr, (1,2)) = ldiv!(dst, plan, arr): normalised 1/(Ny·Nx); complex IFFT along x
     then c2r along y, which ignores Im of the ky=0 and ky=Ny/2 rows (FFTW/MKL/cuFFT/pocketfft)."""
     Nx = F.shape[-2]
+    if _FFT_BACKEND == "mkl":
+        import torch
+        return torch.fft.irfftn(torch.from_numpy(np.ascontiguousarray(F)), s=(Nx, Ny), dim=(-2, -1)).numpy()
     return sfft.irfftn(F, s=(Nx, Ny), axes=(-2, -1), workers=_WORKERS)
 
 
@@ -726,7 +751,9 @@ def MAP_joint(ds: DataSet, nsteps: int = 5, conjgrad_kwargs=dict(tol=1e-1, nstep
             alpha = float(sol.x)
             phi_mixed = (phi_mixed + proj.T(alpha) * step_dir).astype(proj.cT)
             lp = logpdf_mixed(ds, f_mixed, phi_mixed)
-            f, phi = unmix(ds, proj, pol, f_mixed, phi_mixed, D=ds.D, G=None, nsteps=ds.L.nsteps)
+            # Ω = delete(unmix(...), (:f, :θ)) (src/maximization.jl:206): only ϕ is taken from unmix; f stays the CG solution, which is
+            # both the next step's fstart (prevf, :230) and the value returned (:224)
+            _, phi = unmix(ds, proj, pol, f_mixed, phi_mixed, D=ds.D, G=None, nsteps=ds.L.nsteps)
             hist.append(dict(step=step + 1, logpdf=lp, alpha=alpha, cg_iters=len(cg_hist), linesearch_evals=int(sol.nfev)))
     finally:
         ds.G = G_save

@@ -31,6 +31,24 @@ def emu(pkg):
     return pkg._lib.Library(EMU_PATH)
 
 
+class _BackEnd:
+    """Where a kernel test runs: `lib` is passed to ProjLambert (None = the product library), `device` is the torch device."""
+    def __init__(self, name, lib, device):
+        self.name, self.lib, self.device = name, lib, device
+
+    def library(self, pkg):
+        return self.lib if self.lib is not None else pkg.load()
+
+
+@pytest.fixture(scope="session", params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def be(request, pkg):
+    """Back end of tests/test_kernels.py: the host emulator (CPU suite) or the sm_100a library on cuda:0 (-m gpu)."""
+    if request.param == "emu":
+        return _BackEnd("emu", request.getfixturevalue("emu"), "cpu")
+    request.getfixturevalue("cuda_pkg")
+    return _BackEnd("cuda", None, "cuda:0")
+
+
 @pytest.fixture(scope="session")
 def cuda_pkg(pkg):
     import torch

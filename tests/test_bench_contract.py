@@ -28,6 +28,14 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["ranks"]["ran_on"] == "rank 0 only" and cb["fft"] in ("pocketfft", "mkl")
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs the CPU reference; every other rank prints nothing and exits 0."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
 
 
 @pytest.mark.gpu
@@ -45,3 +53,8 @@ def test_b200_arm_line():
     assert c["sm_max_mhz"] and c["samples"] >= 1 and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["gpu_vs_oracle_rel_l2"] < 1e-11
+    cg = d["cg"]
+    assert cg["iters_timed"] >= 20 and cg["value"] > 0 and cg["res_last"] > 0 and cg["cpu_baseline"]["value"] > 0
+    mj, hm = d["map_joint"], d["hmc"]
+    assert mj["value"] > 0 and mj["higher_is_better"] is False and 0.05 < min(mj["alpha"]) and mj["corr_phi_map_vs_truth_rank0"] > 0.2
+    assert hm["value"] > 0 and hm["abs_dH_max_rank0"] < 50

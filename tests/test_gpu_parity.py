@@ -175,6 +175,99 @@ def test_gradientf_and_cg(cuda_pkg, dtype, pol, mask):
     assert relerr(x.cpu_numpy(), xo) < (1e-9 if dtype == "f64" else 2e-3)
 
 
+@pytest.mark.parametrize("dtype,pol,Ny,Nx", [("f64", "P", 256, 256), ("f32", "P", 256, 256), ("f64", "IP", 256, 256),
+                                             ("f64", "P", 512, 256), ("f32", "IP", 512, 256), ("f64", "I", 256, 512)])
+def test_gradientf_and_cg_fast_path(cuda_pkg, dtype, pol, Ny, Nx):
+    """gradientf_logpdf and 6 CG-Wiener iterations, residual by residual, on the kernels the benchmark times (row-grouped
+    persistent stage kernels, kernel path 3) against the oracle — src/dataset.jl:76-80, src/numerical_algorithms.jl:99-121."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=2, nsteps=7, mask=True, seed=7, theta=2.0, device=DEV)
+    ds, dso = pr["ds"], pr["dso"]
+    assert pkg.load().cdll.cmbl_lenseflow_kernel_path(pkg.LenseFlow(pr["phi"], 7).cache(pkg.LenseBasis(pr["f"])).handle) == 3
+    g = pkg.gradientf_logpdf(ds, pr["f"], pr["phi"])
+    go = O.gradientf_logpdf(dso, pr["sim"]["f"], dso.d)
+    assert relerr(g.cpu_numpy(), go) < (1e-10 if dtype == "f64" else 1e-4)
+    n_it = 6
+    x, hist = pkg.argmaxf_logpdf(ds, pr["phi"], conjgrad_kwargs=dict(tol=0.0, nsteps=n_it))
+    xo, histo = O.argmaxf_logpdf(dso, nsteps=n_it, tol=0.0)
+    assert len(hist) == len(histo) == n_it
+    for (i, r), (io, ro) in zip(hist, histo):
+        assert i == io and np.allclose(r, ro, rtol=1e-9 if dtype == "f64" else 2e-3)
+    assert relerr(x.cpu_numpy(), xo) < (1e-9 if dtype == "f64" else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_headline_config_vs_oracle(cuda_pkg, dtype):
+    """BASELINE's metric config (Nside=1024, QU, 7 RK4 steps; two of the eight batch items so the oracle finishes in seconds):
+    Lϕ*f and Lϕ'*f against the oracle, plus one gradientf_logpdf (= one CG operator application) at that size."""
+    pkg = cuda_pkg
+    pr = make_problem(pkg, 1024, 1024, "P", dtype, nb=2, nsteps=7, mask=True, seed=31, theta=2.0, device=DEV)
+    L = pkg.LenseFlow(pr["phi"], 7)
+    Lo, oproj = pr["Lo"], pr["oproj"]
+    fm = O.to_lense_basis("P", oproj, pr["sim"]["f"])
+    fmap = pr["F"](fm, "QUMap")
+    assert pkg.load().cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == 3
+    tol = TOL[dtype]
+    assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
+    Fq = O.eb_to_qu(oproj, pr["sim"]["f"])
+    assert relerr((L.H * pr["F"](Fq, "QUFourier")).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LH, Fq)) < tol
+    g = pkg.gradientf_logpdf(pr["ds"], pr["f"], pr["phi"])
+    assert relerr(g.cpu_numpy(), O.gradientf_logpdf(pr["dso"], pr["sim"]["f"], pr["dso"].d)) < (1e-10 if dtype == "f64" else 1e-4)
+
+
+def test_concurrent_streams_no_stall(cuda_pkg):
+    """The stage kernels must make progress under ANY residency: two LenseFlow handles integrating at the same time on two
+    streams while a third stream keeps the SMs busy with unrelated kernels.  (Round 1's column kernel waited on flags published by
+    other blocks of the same launch and could stall for seconds here.)  Every apply returns the uncontended bits; no apply takes
+    longer than 10x the median."""
+    import ctypes
+    pkg = cuda_pkg
+    lib = pkg.load()
+    N, tT = 512, torch.float64
+    proj = pkg.ProjLambert(N, N, 2.0, tT, DEV)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    mk = lambda nb: (pkg.Field("Map", torch.randn((nb, 1, N, N), dtype=tT, device=DEV, generator=gen) * 1e-6, proj),
+                     pkg.Field("QUMap", torch.randn((nb, 2, N, N), dtype=tT, device=DEV, generator=gen), proj))
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    probs = []
+    for nb in (4, 3):
+        phi, f = mk(nb)
+        h = ctypes.c_void_p()
+        lib.call("cmbl_lenseflow_create", ctypes.byref(h), proj.handle, 7, 2, nb, nb)      # two private handles (not the pooled one)
+        lib.call("cmbl_lenseflow_precompute", h, P(phi.arr), 0, 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        out = torch.empty_like(f.arr); ref = torch.empty_like(f.arr)
+        lib.call("cmbl_lenseflow_apply", h, 0, P(f.arr), P(ref), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        probs.append((h, f, out, ref))
+    torch.cuda.synchronize()
+    s = [torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()]
+    a = torch.randn(4096, 4096, device=DEV)
+    iters, times = 500, []
+    evs = []
+    for it in range(iters):
+        with torch.cuda.stream(s[2]):
+            for _ in range(2):
+                a = torch.tanh(a @ a * 1e-3)                         # unrelated SM-filling work
+        row = []
+        for k, (h, f, out, ref) in enumerate(probs):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s[k])
+            lib.call("cmbl_lenseflow_apply", h, 0, P(f.arr), P(out), ctypes.c_void_p(s[k].cuda_stream))
+            e1.record(s[k])
+            row.append((e0, e1))
+        evs.append(row)
+        if it % 50 == 49:
+            torch.cuda.synchronize()
+            for (h, f, out, ref) in probs:
+                assert torch.equal(out, ref)
+    torch.cuda.synchronize()
+    for k in range(2):
+        t = np.array([r[k][0].elapsed_time(r[k][1]) for r in evs])
+        print(f"stream {k}: median {np.median(t):.3f} ms  p99 {np.percentile(t, 99):.3f}  max {t.max():.3f}")
+        assert t.max() < 10 * np.median(t), (k, float(np.median(t)), float(t.max()))
+    for (h, *_r) in probs:
+        lib.call("cmbl_lenseflow_destroy", h)
+
+
 @pytest.mark.parametrize("pol", ["P", "IP"])
 def test_logpdf_mixed_gradient_and_map_joint(cuda_pkg, pol):
     """logpdf(Mixed(ds)), its gradient through the device δ-flows and two MAP_joint steps (src/maximization.jl:115-222) vs the oracle."""

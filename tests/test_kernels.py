@@ -1,6 +1,7 @@
-"""CPU unit tests of the CUDA kernel sources through the host emulator build (same .cu files, g++ -DCMBL_EMU), checked
-against the oracle.  These validate index arithmetic / algorithm structure without a GPU; the `-m gpu` tests repeat the
-comparisons on the real sm_100a library."""
+"""Kernel tests against the oracle, run on two back ends (fixture `be`, tests/conftest.py):
+  * "emu"  (-m "not gpu"): the CUDA kernel sources through the host emulator build (same .cu files, g++ -DCMBL_EMU) — index
+    arithmetic / algorithm structure without a GPU;
+  * "cuda" (-m gpu): the very same comparisons on the real sm_100a library through the C ABI on cuda:0."""
 import ctypes
 
 import numpy as np
@@ -36,10 +37,10 @@ def test_no_cpu_fallback(pkg):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx", SIZES + [(256, 256), (512, 8), (8, 2048)])
-def test_rfft2_irfft2(pkg, emu, Ny, Nx, dtype):
+def test_rfft2_irfft2(pkg, be, Ny, Nx, dtype):
     npT, tT = T_of(dtype)
     rng = np.random.default_rng(0)
-    proj = pkg.ProjLambert(Ny, Nx, 2.0, tT, "cpu", emu)
+    proj = pkg.ProjLambert(Ny, Nx, 2.0, tT, be.device, be.lib)
     a = rng.standard_normal((3, 1, Nx, Ny)).astype(npT)
     f = pkg.batch([pkg.FlatMap(a[i], proj) for i in range(3)])
     F = pkg.Fourier(f)
@@ -56,10 +57,10 @@ def test_rfft2_irfft2(pkg, emu, Ny, Nx, dtype):
 
 
 @pytest.mark.parametrize("Ny,Nx", [(8, 8), (64, 32)])
-def test_grids_match_oracle(pkg, emu, Ny, Nx):
+def test_grids_match_oracle(pkg, be, Ny, Nx):
     for dtype in ("f64", "f32"):
         npT, tT = T_of(dtype)
-        p = pkg.ProjLambert(Ny, Nx, 3.0, tT, "cpu", emu)
+        p = pkg.ProjLambert(Ny, Nx, 3.0, tT, be.device, be.lib)
         o = O.ProjLambert(Ny, Nx, 3.0, npT)
         assert np.array_equal(p.ℓx, o.lx) and np.array_equal(p.ℓy, o.ly) and np.array_equal(p.λ_rfft, o.lam_rfft.astype(npT))
         assert p.ℓy[-1] < 0                                           # Nyquist carries negative ℓ (proj_lambert.jl:63)
@@ -68,8 +69,8 @@ def test_grids_match_oracle(pkg, emu, Ny, Nx):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_qu_eb_diag_dot(pkg, emu, dtype):
-    pr = make_problem(pkg, 32, 16, "P", dtype, nb=2, lib=emu)
+def test_qu_eb_diag_dot(pkg, be, dtype):
+    pr = make_problem(pkg, 32, 16, "P", dtype, nb=2, lib=be.lib, device=be.device)
     f, oproj = pr["f"], pr["oproj"]
     fo = pr["sim"]["f"]
     qu = pkg.QUFourier(f)
@@ -90,8 +91,8 @@ def test_qu_eb_diag_dot(pkg, emu, dtype):
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(8, 8, "I", 1, 1), (4, 8, "I", 2, 2), (8, 4, "P", 1, 1), (32, 16, "I", 1, 1),
                                                  (16, 64, "P", 2, 2), (64, 64, "P", 3, 1), (128, 64, "I", 2, 1), (16, 32, "IP", 2, 2), (32, 32, "IP", 2, 1)])
-def test_lenseflow_all_ops(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
-    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=4, mask=False, seed=3, lib=emu)
+def test_lenseflow_all_ops(pkg, be, Ny, Nx, pol, nb, nbphi, dtype):
+    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=4, mask=False, seed=3, lib=be.lib, device=be.device)
     L = pkg.LenseFlow(pr["phi"], 4)
     Lo, oproj = pr["Lo"], pr["oproj"]
     rng = np.random.default_rng(1)
@@ -109,10 +110,10 @@ def test_lenseflow_all_ops(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi,path", [(256, 256, "P", 2, 2, 3), (512, 256, "I", 1, 1, 3), (256, 1024, "I", 2, 1, 3),
                                                       (1024, 512, "I", 1, 1, 3), (256, 256, "IP", 2, 2, 3), (64, 256, "I", 1, 1, 0), (256, 32, "P", 1, 1, 0), (512, 64, "I", 1, 1, 0), (128, 64, "P", 1, 1, 0)])
-def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
+def test_lenseflow_fast_path(pkg, be, Ny, Nx, pol, nb, nbphi, path, dtype):
     """The persistent cp.async kernels of csrc/flow_fast.cuh (lengths 256/512/1024), all four ops, against the oracle;
     `path` = 3 when the pair of fast kernels (row-grouped internal layout) must have been used, 0 for the generic pair."""
-    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=2, mask=False, seed=11, lib=emu)
+    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=2, mask=False, seed=11, lib=be.lib, device=be.device)
     L = pkg.LenseFlow(pr["phi"], 2)
     Lo, oproj = pr["Lo"], pr["oproj"]
     rng = np.random.default_rng(4)
@@ -120,7 +121,7 @@ def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
     F0 = O.rfft2(fm)
     Fn = (F0 + 0.1 * np.abs(F0).mean() * (rng.standard_normal(F0.shape) + 1j * rng.standard_normal(F0.shape))).astype(oproj.cT)
     fmap = pr["F"](fm, pr["lense"]); ffour = pr["F"](Fn, {"I": "Fourier", "P": "QUFourier", "IP": "IQUFourier"}[pol])
-    assert emu.cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == path
+    assert be.library(pkg).cdll.cmbl_lenseflow_kernel_path(L.cache(fmap).handle) == path
     tol = 1e-11 if dtype == "f64" else 2e-5
     assert relerr((L * fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_L, fm)) < tol
     assert relerr(L.ldiv(fmap).cpu_numpy(), O.lenseflow_apply(Lo, O.OP_LINV, fm)) < tol
@@ -129,10 +130,10 @@ def test_lenseflow_fast_path(pkg, emu, Ny, Nx, pol, nb, nbphi, path, dtype):
 
 
 @pytest.mark.parametrize("Ny,Nx", [(16, 32), (256, 256)])
-def test_precompute_p_cache(pkg, emu, Ny, Nx):
+def test_precompute_p_cache(pkg, be, Ny, Nx):
     """precompute! (src/lenseflow.jl:131-142): p[τ] = M⁻¹ᵀ∇ϕ at all 2n+1 times against the oracle, through both cache layouts
     (reference layout for the generic kernels, row-grouped for the fast ones), and refilled in place for a new ϕ (precompute!!)."""
-    pr = make_problem(pkg, Ny, Nx, "I", "f64", nb=2, nsteps=3, mask=False, seed=5, lib=emu)
+    pr = make_problem(pkg, Ny, Nx, "I", "f64", nb=2, nsteps=3, mask=False, seed=5, lib=be.lib, device=be.device)
     L = pkg.LenseFlow(pr["phi"], 3)
     cache = L.cache(pkg.LenseBasis(pr["f"]))
     for k in range(7):
@@ -150,9 +151,9 @@ def test_precompute_p_cache(pkg, emu, Ny, Nx):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("pol", ["I", "P"])
-def test_lenseflow_adjoint_identity(pkg, emu, pol, dtype):
+def test_lenseflow_adjoint_identity(pkg, be, pol, dtype):
     """f'(Lϕ g) ≈ (f'Lϕ) g  (runtests.jl:556,570)."""
-    pr = make_problem(pkg, 64, 32, pol, dtype, nb=1, nsteps=7, mask=False, seed=5, lib=emu)
+    pr = make_problem(pkg, 64, 32, pol, dtype, nb=1, nsteps=7, mask=False, seed=5, lib=be.lib, device=be.device)
     L = pkg.LenseFlow(pr["phi"], 7)
     g = pkg.LenseBasis(pr["f"])
     rng = np.random.default_rng(2)
@@ -164,10 +165,10 @@ def test_lenseflow_adjoint_identity(pkg, emu, pol, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(16, 32, "I", 1, 1), (32, 16, "P", 2, 2), (256, 256, "P", 1, 1)])
-def test_lenseflow_pullback(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
+def test_lenseflow_pullback(pkg, be, Ny, Nx, pol, nb, nbphi, dtype):
     """negδvelocityᴴ transpose flow (src/lenseflow.jl:176-214) against the oracle, reference-compatible (aliased) and exact."""
     nst = 3 if Ny < 256 else 1
-    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=nst, mask=False, seed=17, lib=emu)
+    pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=nst, mask=False, seed=17, lib=be.lib, device=be.device)
     L = pkg.LenseFlow(pr["phi"], nst)
     Lo, oproj = pr["Lo"], pr["oproj"]
     rng = np.random.default_rng(6)
@@ -189,9 +190,9 @@ def test_lenseflow_pullback(pkg, emu, Ny, Nx, pol, nb, nbphi, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_blockdiag_ieb(pkg, emu, dtype):
+def test_blockdiag_ieb(pkg, be, dtype):
     """BlockDiagIEB * f, \\ f, sqrt (src/specialops.jl:61-118, src/field_vectors.jl:62-78) and IEB<->IQU (src/proj_lambert.jl:284,292)."""
-    pr = make_problem(pkg, 32, 16, "IP", dtype, nb=2, lib=emu)
+    pr = make_problem(pkg, 32, 16, "IP", dtype, nb=2, lib=be.lib, device=be.device)
     f, fo, oproj, Cf, Cfo = pr["f"], pr["sim"]["f"], pr["oproj"], pr["ds"].Cf, pr["dso"].Cf
     tol = TOL[dtype]
     assert relerr((Cf * f).cpu_numpy(), O.block_mul(Cfo, fo)) < tol
@@ -212,15 +213,15 @@ def test_blockdiag_ieb(pkg, emu, dtype):
 
 @pytest.mark.parametrize("dtype,pol,mask", [("f64", "I", False), ("f64", "P", True), ("f64", "I", True), ("f32", "P", True),
                                             ("f64", "IP", True), ("f64", "IP", False), ("f32", "IP", True)])
-def test_gradientf_and_cg(pkg, emu, dtype, pol, mask):
-    pr = make_problem(pkg, 32, 32, pol, dtype, nb=2, nsteps=3, mask=mask, seed=7, theta=3.0, lib=emu)
+def test_gradientf_and_cg(pkg, be, dtype, pol, mask):
+    pr = make_problem(pkg, 32, 32, pol, dtype, nb=2, nsteps=3, mask=mask, seed=7, theta=3.0, lib=be.lib, device=be.device)
     ds, dso, f = pr["ds"], pr["dso"], pr["f"]
     g = pkg.gradientf_logpdf(ds, f, pr["phi"])
     go = O.gradientf_logpdf(dso, pr["sim"]["f"], dso.d)
     tol = 1e-10 if dtype == "f64" else 1e-4
     assert relerr(g.cpu_numpy(), go) < tol
     pre = pkg.Hessian_logpdf_preconditioner(ds)
-    assert relerr(pre._real.numpy(), O.hess_preconditioner(dso)) < (1e-13 if dtype == "f64" else 1e-6)
+    assert relerr(pre._real.cpu().numpy(), O.hess_preconditioner(dso)) < (1e-13 if dtype == "f64" else 1e-6)
     n_it = 6
     x, hist = pkg.argmaxf_logpdf(ds, pr["phi"], conjgrad_kwargs=dict(tol=0.0, nsteps=n_it))
     xo, histo = O.argmaxf_logpdf(dso, nsteps=n_it, tol=0.0)
@@ -231,9 +232,9 @@ def test_gradientf_and_cg(pkg, emu, dtype, pol, mask):
 
 
 @pytest.mark.parametrize("pol", ["I", "P"])
-def test_mix_unmix(pkg, emu, pol):
+def test_mix_unmix(pkg, be, pol):
     """mix / unmix (src/dataset.jl:96-117) with diagonal mixing matrices D, G: parity with the oracle and round trip."""
-    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=5, mask=False, seed=23, theta=3.0, lib=emu)
+    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=5, mask=False, seed=23, theta=3.0, lib=be.lib, device=be.device)
     ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
     rng = np.random.default_rng(8)
     Dn = (1.0 + rng.random(dso.Cf.shape)).astype(np.float64)
@@ -249,9 +250,9 @@ def test_mix_unmix(pkg, emu, pol):
 
 
 @pytest.mark.parametrize("pol", ["P", "IP"])
-def test_sample_f_and_cl_to_cov(pkg, emu, pol):
+def test_sample_f_and_cl_to_cov(pkg, be, pol):
     """sample_f (src/maximization.jl:56-62) fed the same white-noise draws as the oracle; Cℓ_to_Cov (src/proj_lambert.jl:361-371)."""
-    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=3, mask=True, seed=5, theta=3.0, lib=emu)
+    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=3, mask=True, seed=5, theta=3.0, lib=be.lib, device=be.device)
     ds, dso, oproj, proj = pr["ds"], pr["dso"], pr["oproj"], pr["proj"]
     rng = np.random.default_rng(3)
     wf = rng.standard_normal((2, dso.npol) + oproj.map_shape); wn = rng.standard_normal((2, dso.npol) + oproj.map_shape)
@@ -261,16 +262,16 @@ def test_sample_f_and_cl_to_cov(pkg, emu, pol):
     cls = O.load_fiducial_cls(); ell = cls["ell"]
     keys = ("ut_EE", "ut_BB") if pol == "P" else ("ut_TT", "ut_EE", "ut_BB", "ut_TE")
     C = pkg.Cℓ_to_Cov(pol, proj, ell, *(cls[k] for k in keys))
-    assert relerr(C._real.numpy(), dso.Cf) < 1e-14                              # TE sits in plane 2 of the block
+    assert relerr(C._real.cpu().numpy(), dso.Cf) < 1e-14                              # TE sits in plane 2 of the block
     with pytest.raises(pkg.CmblError):
         pkg.Cℓ_to_Cov("Q", proj, ell, cls["ut_TT"])
 
 
 @pytest.mark.parametrize("pol", ["P", "IP"])
-def test_logpdf_mixed_gradient_and_map_joint(pkg, emu, pol):
+def test_logpdf_mixed_gradient_and_map_joint(pkg, be, pol):
     """logpdf, logpdf(Mixed(ds)), its gradient through the two pullbacks, and two MAP_joint steps (src/dataset.jl:60-117,
     src/maximization.jl:115-222) against the oracle on the same inputs."""
-    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=4, mask=True, seed=12, theta=3.0, lib=emu)
+    pr = make_problem(pkg, 32, 32, pol, "f64", nb=2, nsteps=4, mask=True, seed=12, theta=3.0, lib=be.lib, device=be.device)
     ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
     rng = np.random.default_rng(2)
     Dn = (1.0 + 0.5 * rng.random((1, dso.npol) + oproj.fourier_shape)); Gn = 1.0 + 0.5 * rng.random((1, 1) + oproj.fourier_shape)
@@ -295,32 +296,32 @@ def test_logpdf_mixed_gradient_and_map_joint(pkg, emu, pol):
 
 
 @pytest.mark.parametrize("pol,which", [("I", "TT"), ("P", "EE"), ("P", "EB"), ("IP", "EB"), ("IP", "TT")])
-def test_quadratic_estimate(pkg, emu, pol, which):
+def test_quadratic_estimate(pkg, be, pol, which):
     """quadratic_estimate (src/quadratic_estimate.jl:30-199): AL = Nϕ and the (Wiener-filtered) estimate against the oracle, with the
     reference's per-term abs.() normalisation and with the exact one."""
-    pr = make_problem(pkg, 32, 64, pol, "f64", nb=2, nsteps=4, mask=False, seed=8, theta=2.0, lib=emu)
+    pr = make_problem(pkg, 32, 64, pol, "f64", nb=2, nsteps=4, mask=False, seed=8, theta=2.0, lib=be.lib, device=be.device)
     for each in (True, False):
         r = pkg.quadratic_estimate(pr["ds"], which, abs_each_term=each)
         ro = O.quadratic_estimate(pr["dso"], which, abs_each_term=each)
         # compare 1/AL (the normalisation sum): beyond twice the band limit of the filters it is pure rounding noise, whose
         # reciprocal is arbitrary in the reference as well
-        assert relerr(O.pinv_diag(r["AL"]._real.numpy()), O.pinv_diag(ro["AL"])) < 1e-9 and relerr(r["ϕqe"].cpu_numpy(), ro["phi_qe"]) < 1e-8
+        assert relerr(O.pinv_diag(r["AL"]._real.cpu().numpy()), O.pinv_diag(ro["AL"])) < 1e-9 and relerr(r["ϕqe"].cpu_numpy(), ro["phi_qe"]) < 1e-8
     r2 = pkg.quadratic_estimate(pr["ds"], which, wiener_filtered=False, weights="lensed", AL=r["AL"])
     ro2 = O.quadratic_estimate(pr["dso"], which, wiener_filtered=False, weights="lensed", AL=ro["AL"])
     assert relerr(r2["ϕqe"].cpu_numpy() * (pr["oproj"].lmag < 5000), ro2["phi_qe"] * (pr["oproj"].lmag < 5000)) < 1e-8
     with pytest.raises(pkg.CmblError):
         pkg.quadratic_estimate(pr["ds"], "TE")
-    assert relerr(pkg.mixing_D(pr["ds"])._real.numpy(), O.mixing_D(pr["dso"])) < 1e-12
+    assert relerr(pkg.mixing_D(pr["ds"])._real.cpu().numpy(), O.mixing_D(pr["dso"])) < 1e-12
 
 
-def test_map_joint_iqu_with_block_mixing(pkg, emu):
+def test_map_joint_iqu_with_block_mixing(pkg, be):
     """MAP_joint on an IQU dataset with load_sim's mixing matrix as a BlockDiagIEB and Nϕ from the EB quadratic estimate (config 4's
     algorithm at a small size): gradient parity with the oracle, step lengths of order one, increasing posterior."""
-    pr = make_problem(pkg, 64, 64, "IP", "f64", nb=1, nsteps=5, mask=True, seed=3, theta=2.0, lib=emu)
+    pr = make_problem(pkg, 64, 64, "IP", "f64", nb=1, nsteps=5, mask=True, seed=3, theta=2.0, lib=be.lib, device=be.device)
     ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
     dso.D = O.mixing_D(dso); ds.D = pkg.mixing_D(ds)
     dso.Nphi = (O.quadratic_estimate(dso)["Nphi"] / 2).astype(oproj.T)
-    ds.Nϕ = pkg.DiagOp(pr["F"](pkg.quadratic_estimate(ds)["Nϕ"]._real.numpy() / 2, "Fourier"))
+    ds.Nϕ = pkg.DiagOp(pr["F"](pkg.quadratic_estimate(ds)["Nϕ"]._real.cpu().numpy() / 2, "Fourier"))
     fm, pm = pkg.mix(ds, pr["f"], pr["phi"])
     fmo, pmo = O.mix(dso, oproj, "IP", pr["sim"]["f"], pr["sim"]["phi"], D=dso.D, G=None, nsteps=5)
     assert relerr(fm.cpu_numpy(), fmo) < 1e-11
@@ -335,10 +336,10 @@ def test_map_joint_iqu_with_block_mixing(pkg, emu):
     assert hist[1]["logpdf"].sum() > hist[0]["logpdf"].sum() and relerr(ϕ.cpu_numpy(), ϕ_o) < 1e-4
 
 
-def test_hmc_step_phi(pkg, emu):
+def test_hmc_step_phi(pkg, be):
     """gibbs_sample_ϕ! / hmc_step / symplectic_integrate (src/sampling.jl:14-55,397-425) with the same momentum and accept draws
     as the oracle; the leap-frog nearly conserves H for a small step."""
-    pr = make_problem(pkg, 32, 32, "P", "f64", nb=2, nsteps=4, mask=True, seed=14, theta=3.0, lib=emu)
+    pr = make_problem(pkg, 32, 32, "P", "f64", nb=2, nsteps=4, mask=True, seed=14, theta=3.0, lib=be.lib, device=be.device)
     ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
     rng = np.random.default_rng(5)
     Gn = 1.0 + 0.5 * rng.random((1, 1) + oproj.fourier_shape)
@@ -353,10 +354,10 @@ def test_hmc_step_phi(pkg, emu):
     assert np.all(np.abs(dH) < 5.0)                                # |ΔH| ≪ |H| ~ 1e5: the integrator is symplectic
 
 
-def test_sample_joint_gibbs_chain(pkg, emu):
+def test_sample_joint_gibbs_chain(pkg, be):
     """Two Gibbs steps of sample_joint (src/sampling.jl:180-336: sample_f, mix, HMC in ϕ°, unmix) for two chains in the batch, fed
     the same random draws as the oracle."""
-    pr = make_problem(pkg, 32, 32, "P", "f64", nb=2, nsteps=4, mask=True, seed=16, theta=3.0, lib=emu)
+    pr = make_problem(pkg, 32, 32, "P", "f64", nb=2, nsteps=4, mask=True, seed=16, theta=3.0, lib=be.lib, device=be.device)
     ds, dso, oproj = pr["ds"], pr["dso"], pr["oproj"]
     dso.D = O.mixing_D(dso); ds.D = pkg.mixing_D(ds)
     rng = np.random.default_rng(9)
@@ -374,8 +375,8 @@ def test_sample_joint_gibbs_chain(pkg, emu):
         assert np.allclose(c["logpdf"], co["logpdf"], rtol=1e-8)
 
 
-def test_cg_stops_on_tol_like_reference(pkg, emu):
-    pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=emu)
+def test_cg_stops_on_tol_like_reference(pkg, be):
+    pr = make_problem(pkg, 32, 32, "I", "f64", nb=2, nsteps=3, mask=True, seed=9, theta=3.0, lib=be.lib, device=be.device)
     _, h0 = O.argmaxf_logpdf(pr["dso"], nsteps=30, tol=0.0)
     tol = float(np.max(h0[12][1])) * 1.0001              # reached (for all batch items) around iteration 13
     x, hist = pkg.argmaxf_logpdf(pr["ds"], pr["phi"], conjgrad_kwargs=dict(tol=tol, nsteps=30))
@@ -384,13 +385,13 @@ def test_cg_stops_on_tol_like_reference(pkg, emu):
     assert relerr(x.cpu_numpy(), xo) < 1e-9
 
 
-def test_error_behaviour(pkg, emu):
-    proj = pkg.ProjLambert(8, 8, 1.0, torch.float64, "cpu", emu)
+def test_error_behaviour(pkg, be):
+    proj = pkg.ProjLambert(8, 8, 1.0, torch.float64, be.device, be.lib)
     with pytest.raises(pkg.CmblError):                                    # size mismatch, runtests.jl:113 / base_fields.jl:19
         pkg.Field("Map", torch.zeros(1, 1, 8, 4, dtype=torch.float64), proj)
     with pytest.raises(pkg.CmblError):
-        pkg.ProjLambert(12, 8, 1.0, torch.float64, "cpu", emu)            # non power of two
-    p2 = pkg.ProjLambert(8, 8, 2.0, torch.float64, "cpu", emu)
+        pkg.ProjLambert(12, 8, 1.0, torch.float64, be.device, be.lib)            # non power of two
+    p2 = pkg.ProjLambert(8, 8, 2.0, torch.float64, be.device, be.lib)
     a = pkg.FlatMap(np.zeros((8, 8)), proj); b = pkg.FlatMap(np.zeros((8, 8)), p2)
     with pytest.raises(pkg.CmblError):                                    # mismatched metadata, proj_lambert.jl:111-114
         a + b
@@ -399,10 +400,10 @@ def test_error_behaviour(pkg, emu):
         pkg.LenseFlow(phi) * f
 
 
-def test_golden_fixture_emulator(pkg, emu):
+def test_golden_fixture(pkg, be):
     import os
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lenseflow_golden.npz"))
-    proj = pkg.ProjLambert(int(z["Ny"]), int(z["Nx"]), float(z["theta"]), torch.float64, "cpu", emu)
+    proj = pkg.ProjLambert(int(z["Ny"]), int(z["Nx"]), float(z["theta"]), torch.float64, be.device, be.lib)
     L = pkg.LenseFlow(pkg.Field("Fourier", torch.from_numpy(z["phi"]), proj), int(z["nsteps"]))
     f = pkg.Field("QUMap", torch.from_numpy(z["f_qumap"]), proj)
     assert relerr((L * f).cpu_numpy(), z["L_f"]) < 1e-12
