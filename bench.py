@@ -381,7 +381,7 @@ def main():
             # masking chain, Lϕ'), scaled to the batch of 8
             cores = os.cpu_count() or 1
             O.set_workers(cores)
-            dso = O.DataSet(proj=op, pol="P", d=data.arr[:1].cpu().numpy(), Cf=Cf_np, Cn=Cn_np, B=B_np, Mf=Mf_np, Mpix=mask_np,
+            dso = O.DataSet(proj=op, pol="P", d=data.arr[:1].cpu().numpy(), Cf=Cf_np, Cn=Cn_np, Cnhat=Cn_np, B=B_np, Bhat=B_np, Mf=Mf_np, Mpix=mask_np,
                             L=O.precompute(op, ϕ.arr[:1].cpu().numpy(), NSTEPS_RK, phi_is_fourier=True))
             pvec = f.arr[:1].cpu().numpy()
             t0 = time.perf_counter()

@@ -264,6 +264,24 @@ def dot(a: Field, b: Field) -> np.ndarray:
     return np.array(out[:], dtype=np.float64)
 
 
+def get_max_lensing_step(ϕ: Field, η: Field, per_batch: bool = False):
+    """get_max_lensing_step(ϕ, η) (src/lenseflow.jl:242-256): αmax such that 𝕀 + ∇∇(ϕ + α η) has non-zero determinant in every pixel for
+    all α in [0, αmax) — the largest step along η that keeps ϕ + α η in the weak-lensing regime LenseFlow can handle.  The reference
+    returns ONE number (the minimum over pixels and batch); `per_batch=True` returns the per-item values the device computes."""
+    ϕ._check(η)
+    if ϕ.Npol != 1 or η.Npol != 1:
+        raise CmblError("get_max_lensing_step expects spin-0 fields (ϕ, η)")
+    p = ϕ.proj
+    nb = max(ϕ.Nbatch, η.Nbatch)
+    if ϕ.Nbatch != η.Nbatch:
+        ϕ = ϕ._like(ϕ.arr.expand(nb, -1, -1, -1).contiguous()); η = η._like(η.arr.expand(nb, -1, -1, -1).contiguous())
+    out = (c_double * nb)()
+    p.lib.call("cmbl_max_lensing_step", p.handle, _ptr(ϕ.arr), FOURIER if ϕ.is_fourier else MAP, _ptr(η.arr), FOURIER if η.is_fourier else MAP,
+               nb, out, _stream(ϕ.arr))
+    v = np.array(out[:], dtype=np.float64)
+    return v if per_batch else float(v.min())
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # DiagOp (src/specialops.jl:9-22)
 # ------------------------------------------------------------------------------------------------------------------

@@ -158,6 +158,15 @@ int cmbl_lenseflow_grad(cmbl_flow* flow, int op, const void* f_out_map, const vo
     CMBL_API_END
 }
 
+int cmbl_max_lensing_step(cmbl_plan* plan, const void* phi, int phi_basis, const void* eta, int eta_basis, int Nb, double* out_host, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan && plan->p && phi && eta && out_host, "NULL argument");
+    CMBL_REQUIRE(Nb >= 1, "Nb must be >= 1");
+    CMBL_REQUIRE((phi_basis == CMBL_MAP || phi_basis == CMBL_FOURIER) && (eta_basis == CMBL_MAP || eta_basis == CMBL_FOURIER), "basis must be Map or Fourier");
+    CMBL_DISPATCH(plan->p.get(), cmbl::max_lensing_step<T>(P, phi, phi_basis, eta, eta_basis, Nb, out_host, as_stream(stream)));
+    CMBL_API_END
+}
+
 int cmbl_lenseflow_kernel_path(cmbl_flow* flow) {
     if (!flow || !flow->f) return 0;
     int r = 0;

@@ -26,6 +26,7 @@
 #define DEV inline
 typedef void* cmblStream_t;
 #define CMBL_FOR_THREADS(tid, NT) for (int tid = 0; tid < (NT); ++tid)
+#define CMBL_FOR_GROUP(tid, NG, goff) for (int tid = 0; tid < (NG); ++tid)
 #define CMBL_SYNC() ((void)0)
 #define CMBL_LDG(p) ::cmbl::ldg(p)
 #else
@@ -34,6 +35,8 @@ typedef void* cmblStream_t;
 #define DEV __device__ __forceinline__
 typedef cudaStream_t cmblStream_t;
 #define CMBL_FOR_THREADS(tid, NT) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
+// a thread GROUP of a warp-specialised block: NG consecutive threads starting at thread `goff` (tid counts from 0 inside the group)
+#define CMBL_FOR_GROUP(tid, NG, goff) for (int tid = (int)threadIdx.x - (goff), _once = 1; _once; _once = 0)
 #define CMBL_SYNC() __syncthreads()
 #define CMBL_LDG(p) ::cmbl::ldg(p)
 #endif
@@ -233,6 +236,34 @@ template <class Body> int persistent_blocks(size_t smem) {
         cached = per_sm * sms;
     }
     return cached;
+#endif
+}
+
+// named barriers of a warp-specialised block (bar.sync / bar.arrive / bar.red with an id and a participant count); id 0 with the
+// whole block is __syncthreads().  The host emulator runs the roles of a block one after another, so they are no-ops there.
+DEV void group_sync(int bar, int count) {
+#ifdef __CUDA_ARCH__
+    if (bar == 0) __syncthreads(); else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(count) : "memory");
+#else
+    (void)bar; (void)count;
+#endif
+}
+DEV void group_arrive(int bar, int count) {
+#ifdef __CUDA_ARCH__
+    asm volatile("bar.arrive %0, %1;" ::"r"(bar), "r"(count) : "memory");
+#else
+    (void)bar; (void)count;
+#endif
+}
+DEV int group_or(int bar, int count, int pred) {          // barrier + OR of `pred` over the group
+#ifdef __CUDA_ARCH__
+    if (bar == 0) return __syncthreads_or(pred);
+    int out;
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.s32 q, %1, 0;\n bar.red.or.pred p, %2, %3, q;\n selp.s32 %0, 1, 0, p;\n}"
+                 : "=r"(out) : "r"(pred), "r"(bar), "r"(count) : "memory");
+    return out;
+#else
+    (void)bar; (void)count; return pred;
 #endif
 }
 

@@ -45,8 +45,11 @@ static int device_sms() {
     return v;
 #endif
 }
-// tile order of the fast column kernel: 1 = contiguous tile range per block (default), 0 = round-robin (see FastColBody)
-static int fast_cols_contig() { static const int v = [] { const char* e = getenv("CMBL_COL_CONTIG"); return e ? atoi(e) : 1; }(); return v; }
+// tile order of the fast column kernel: 0 = round-robin (default), 1 = contiguous tile range per block (see FastColBody)
+static int fast_cols_contig() { static const int v = [] { const char* e = getenv("CMBL_COL_CONTIG"); return e ? atoi(e) : 0; }(); return v; }
+// blocks that compute and publish each J[N] plane pair at launch start (0 = none: every block computes private copies — test knob)
+static int fast_cols_jn_red() { static const int v = [] { const char* e = getenv("CMBL_COL_JN_RED"); return e ? atoi(e) : 3; }(); return v; }
+static int fast_cols_pgroup() { static const int v = [] { const char* e = getenv("CMBL_COL_PGROUP"); return e ? atoi(e) : 1; }(); return v; }
 static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
     static const int v = [] { const char* e = getenv("CMBL_FLOW_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     return v > 0 ? std::min(full, v * device_sms()) : full;
@@ -86,20 +89,30 @@ static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cm
     b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
     launch(b, b.nblocks, B::SMEM, st);
 }
-template <class T, int LOGN, bool ADJ>
-static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb, cmblStream_t st) {
+template <class T, class B>
+static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb,
+                             int private_lines, bool adj, cmblStream_t st) {
     PlanT<T>& P = *F.P;
-    typedef FastColBody<T, LOGN, ADJ> B;
     B b;
     b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv; b.mult_sign = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
-    b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / (2 * B::L); b.ntiles = nC * b.tiles_per_plane;
-    b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
-    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T), ADJ); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
+    b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / B::M; b.ntiles = nC * b.tiles_per_plane;
+    const int cap = fast_block_cap(persistent_blocks<B>(B::SMEM));
+    // polarisation groups (Q and U tiles of the same columns in one block, p maps shared through L2 hints) once every block has >= 2 groups
+    b.pgroup = (!adj && F.Npol > 1 && fast_cols_pgroup() && b.ntiles / F.Npol >= 2 * cap) ? F.Npol : 1;
+    b.nblocks = std::min(b.ntiles / b.pgroup, cap);
+    b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T), adj); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
     b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = nullptr;
-    b.jn_blk = reinterpret_cast<T*>(F.jnblk.reserve(sizeof(T) * (size_t)b.nblocks * F.Npol * B::N)); b.contig = fast_cols_contig();
+    b.jn_pub = reinterpret_cast<T*>(F.jn.p);
+    b.jn_blk = reinterpret_cast<T*>(F.jnblk.reserve(sizeof(T) * (size_t)b.nblocks * private_lines * B::N)); b.contig = fast_cols_contig(); b.jn_red = fast_cols_jn_red();
+    if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
+    b.jn_flag = reinterpret_cast<int*>(F.jnflag.p); b.epoch = ++F.jn_epoch;
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
     launch(b, b.nblocks, B::SMEM, st);
+}
+template <class T, int LOGN, bool ADJ>
+static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb, cmblStream_t st) {
+    fast_cols_launch<T, FastColBody<T, LOGN, ADJ>>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, 1, ADJ, st);
 }
 template <class T> static bool fast_rows_ok(const PlanT<T>& P) {
     if (!fast_enabled() || !fast_len_ok(P.Nx) || !P.ax.ftw1) return false;
@@ -262,6 +275,40 @@ template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* ou
     (void)nf;
 }
 
+template <class T> void max_lensing_step(PlanT<T>& P, const void* phi, int phi_basis, const void* eta, int eta_basis, int Nb, double* out_host, cmblStream_t st) {
+    const size_t nmap = P.map_elems(), nf = P.four_elems();
+    DevBuf spec, ws;
+    C2<T>* sp = reinterpret_cast<C2<T>*>(spec.reserve(sizeof(C2<T>) * nf * (size_t)Nb));
+    // per field: 5 spectra + 5 maps per batch item; [ϕ | η]
+    const size_t per = sizeof(C2<T>) * nf * 5 * Nb + sizeof(T) * nmap * 5 * Nb;
+    char* w = reinterpret_cast<char*>(ws.reserve(2 * per + sizeof(double) * (size_t)Nb * RED_BLOCKS));
+    const T* maps[2];
+    for (int k = 0; k < 2; ++k) {
+        const void* src = k ? eta : phi; const int basis = k ? eta_basis : phi_basis;
+        const C2<T>* four = reinterpret_cast<const C2<T>*>(src);
+        if (basis != CMBL_FOURIER) { rfft2<T>(P, reinterpret_cast<const T*>(src), sp, Nb, st); four = sp; }
+        C2<T>* s5 = reinterpret_cast<C2<T>*>(w + k * per);
+        T* m5 = reinterpret_cast<T*>(s5 + nf * 5 * Nb);
+        GradHessSpecBody<T> b{P.Nx, P.Nyh, P.lx, P.ly, four, s5, nf * (size_t)Nb};
+        launch(b, (int)((b.total + b.NT - 1) / b.NT), 0, st);
+        irfft2<T>(P, s5, m5, 5 * Nb, st);
+        maps[k] = m5;
+    }
+    double* part = reinterpret_cast<double*>(w + 2 * per);
+    MaxStepBody<T> mb{nmap, maps[0], maps[1], part};
+    launch(mb, Nb * RED_BLOCKS, sizeof(double) * mb.NT, st);
+    std::vector<double> h((size_t)Nb * RED_BLOCKS);
+    dev_download(h.data(), part, sizeof(double) * h.size(), st);
+    for (int b = 0; b < Nb; ++b) {
+        double m = HUGE_VAL;
+        for (int i = 0; i < RED_BLOCKS; ++i) m = std::min(m, h[(size_t)b * RED_BLOCKS + i]);
+        out_host[b] = m;
+    }
+#ifndef CMBL_EMU
+    CMBL_CUDA(cudaStreamSynchronize(st));            // the scratch buffers are released on return
+#endif
+}
+
 template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_rg_rows(*F.P) > 0 ? 3 : 0; }
 
 #define INST(T)                                                                                        \
@@ -269,7 +316,8 @@ template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_rg_rows(*F.P)
     template void flow_integrate<T>(FlowT<T>&, bool, T*, int, int, cmblStream_t);                      \
     template void flow_integrate_range<T>(FlowT<T>&, bool, T*, int, int, int, int, cmblStream_t);      \
     template void flow_apply<T>(FlowT<T>&, int, const void*, void*, cmblStream_t);                     \
-    template int flow_kernel_path<T>(FlowT<T>&);
+    template int flow_kernel_path<T>(FlowT<T>&);                                                       \
+    template void max_lensing_step<T>(PlanT<T>&, const void*, int, const void*, int, int, double*, cmblStream_t);
 INST(float)
 INST(double)
 

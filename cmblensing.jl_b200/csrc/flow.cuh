@@ -330,6 +330,41 @@ template <class T> struct PCacheBody {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// get_max_lensing_step (src/lenseflow.jl:242-256): per pixel the roots α of det(𝕀 + ∇∇(ϕ + α η)) = a α² + b α + c; per batch item the
+// smallest positive root.  gh_phi / gh_eta: the 5 maps per batch item of GradHessSpecBody (only the Hessian entries are used; the
+// reference reads ϕ₁₂ for both off-diagonal entries).  partial[b][RED_BLOCKS]: block minima (+inf when a block saw no positive root).
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct MaxStepBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "max_lensing_step"; }
+    size_t nmap; const T* gh_phi; const T* gh_eta; double* partial;
+    DEV void operator()(int blk, unsigned char* smem) const {
+        double* sm = reinterpret_cast<double*>(smem);
+        const int bi = blk / RED_BLOCKS, j = blk % RED_BLOCKS;
+        const T* P = gh_phi + (size_t)bi * 5 * nmap; const T* E = gh_eta + (size_t)bi * 5 * nmap;
+        CMBL_FOR_THREADS(tid, NT) {
+            double m = HUGE_VAL;
+            for (size_t e = (size_t)j * NT + tid; e < nmap; e += (size_t)RED_BLOCKS * NT) {
+                const T p11 = P[2 * nmap + e], p12 = P[3 * nmap + e], p22 = P[4 * nmap + e];
+                const T e11 = E[2 * nmap + e], e12 = E[3 * nmap + e], e22 = E[4 * nmap + e];
+                const T a = e11 * e22 - e12 * e12;
+                const T b = e11 * ((T)1 + p22) + e22 * ((T)1 + p11) - (T)2 * e12 * p12;
+                const T c = ((T)1 + p11) * ((T)1 + p22) - p12 * p12;
+                const T sq = sqrt(b * b - (T)4 * a * c);                  // NaN where there is no real root: fails every comparison below
+                const T a1 = (-b + sq) / ((T)2 * a), a2 = (-b - sq) / ((T)2 * a);
+                if (a1 > (T)0 && (double)a1 < m) m = (double)a1;
+                if (a2 > (T)0 && (double)a2 < m) m = (double)a2;
+            }
+            sm[tid] = m;
+        }
+        CMBL_SYNC();
+        CMBL_FOR_THREADS(tid, NT) {
+            if (tid == 0) { double m = HUGE_VAL; for (int i = 0; i < NT; ++i) m = sm[i] < m ? sm[i] : m; partial[blk] = m; }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 struct FlowBase { PlanBase* plan = nullptr; virtual ~FlowBase() {} };
 
 template <class T> struct FlowT : FlowBase {
@@ -340,7 +375,8 @@ template <class T> struct FlowT : FlowBase {
     int pcache_G = 0;                    // layout of pcache / minv: 0 = reference layout, else rows per row group
     DevBuf yrg;                          // row-grouped copy of the ODE state
     DevBuf g_yf, g_yd, g_yp, g_uf, g_ud, g_up, g_af, g_ad, g_ap, g_kf, g_kd, g_kp, g_ldf, g_gxy, g_a12, g_six, g_spec, g_spec2;   // δ-flow scratch (flow_grad.cu)
-    DevBuf jnblk;                        // per-block J[N] scratch lines of the fast column kernel
+    DevBuf jnblk;                        // per-block private J[N] line of the fast column kernel (fallback when the shared line is not published)
+    DevBuf jnflag; int jn_epoch = 0;     // per-plane publication flags of the shared J[N] lines (value = launch epoch)
     DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, jn, counter, nacc, macc, rows0, spec, gh;
     size_t nmap() const { return P->map_elems(); }
     const T* pk(int k) const { return reinterpret_cast<T*>(pcache.p) + (size_t)k * Nbphi * 2 * nmap(); }
@@ -352,5 +388,7 @@ template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int 
 template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* y, int k0, int k1, int c0, int nC, cmblStream_t st);
 template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st);
 template <class T> int flow_kernel_path(FlowT<T>& F);
+// smallest positive α per batch item with det(𝕀 + ∇∇(ϕ + α η)) = 0 somewhere (host doubles; +inf if none); synchronises
+template <class T> void max_lensing_step(PlanT<T>& P, const void* phi, int phi_basis, const void* eta, int eta_basis, int Nb, double* out_host, cmblStream_t st);
 
 }  // namespace cmbl

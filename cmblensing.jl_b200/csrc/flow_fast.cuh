@@ -103,6 +103,30 @@ template <> DEV void vload_stream2<double>(const double* p, Vec<double>& a, Vec<
     a = vload(p); b = vload(p + 2);
 #endif
 }
+// the same with an L2 eviction priority: 1 = evict_last (the line will be read once more soon: keep it), 2 = evict_first (last use)
+template <class T> DEV void vload_stream2h(const T* p, Vec<T>& a, Vec<T>& b, int hint);
+template <> DEV void vload_stream2h<float>(const float* p, Vec<float>& a, Vec<float>& b, int hint) {
+#ifdef __CUDA_ARCH__
+    if (hint == 1)
+        asm("ld.global.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3]),
+            "=f"(b.v[0]), "=f"(b.v[1]), "=f"(b.v[2]), "=f"(b.v[3]) : "l"(p));
+    else if (hint == 2)
+        asm("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3]),
+            "=f"(b.v[0]), "=f"(b.v[1]), "=f"(b.v[2]), "=f"(b.v[3]) : "l"(p));
+    else vload_stream2(p, a, b);
+#else
+    (void)hint; a = vload(p); b = vload(p + 4);
+#endif
+}
+template <> DEV void vload_stream2h<double>(const double* p, Vec<double>& a, Vec<double>& b, int hint) {
+#ifdef __CUDA_ARCH__
+    if (hint == 1) asm("ld.global.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.v[0]), "=d"(a.v[1]), "=d"(b.v[0]), "=d"(b.v[1]) : "l"(p));
+    else if (hint == 2) asm("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.v[0]), "=d"(a.v[1]), "=d"(b.v[0]), "=d"(b.v[1]) : "l"(p));
+    else vload_stream2(p, a, b);
+#else
+    (void)hint; a = vload(p); b = vload(p + 2);
+#endif
+}
 // two adjacent 16-byte chunks as one 256-bit store (sm_100: st.global.v8.f32 / v4.f64); p must be 32-byte aligned
 template <class T> DEV void vstore2(T* p, const Vec<T>& a, const Vec<T>& b);
 template <> DEV void vstore2<float>(float* p, const Vec<float>& a, const Vec<float>& b) {
@@ -141,6 +165,31 @@ DEV void pdl_wait() {
 DEV void pdl_launch_dependents() {
 #ifdef __CUDA_ARCH__
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// per-plane publication flag of a J[N] line inside one launch: the producer publishes with release semantics, a consumer LOOKS
+// (acquire) and never waits — if the line is not there yet it computes its own copy
+DEV void flag_publish(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#endif
+}
+DEV int flag_look(const int* p) {
+#ifdef __CUDA_ARCH__
+    int got; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p) : "memory"); return got;
+#else
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#endif
+}
+// block-wide OR of a per-thread predicate (includes a barrier); the host emulator runs the threads of a block one after another in
+// one host thread, so the value set by "thread 0" is already what every thread sees
+DEV int block_or(int v) {
+#ifdef __CUDA_ARCH__
+    return __syncthreads_or(v);
+#else
+    return v;
 #endif
 }
 DEV int ticket_release(int* p, int n) {
@@ -248,7 +297,9 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     static_assert((1 << LGM) == M, "columns per tile must be a power of two <= 64");
 
     const T* tw1; const T* tw2; const T* mult_d; const T* mult_sign; T cN;     // mult_sign, cN: the Nyquist line operator J (flow.cuh)
-    const T* nline; T* jn_blk; int contig;           // N(y) per plane (row kernel of this stage); per-block J[N] scratch [block][Npol][N]
+    const T* nline;                                  // N(y) per plane (row kernel of this stage)
+    T* jn_pub; int* jn_flag; int epoch;              // launch-wide J[N] lines [plane][N]; jn_flag[plane] == epoch <=> this launch's line is published
+    T* jn_blk; int contig, jn_red, pgroup;           // per-block private J[N] line [block][N] (fallback); tile order knob; publishers per plane pair; tiles per polarisation group
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
@@ -382,7 +433,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         p = (k >> lgU) & (M - 1); ch = (yb << lgGV) + 2 * h;
         goff = ((size_t)yb * Nx + x0 + p) * G + 2 * h * V;
     }
-    template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2) const {
+    template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2, int ph = 0) const {
         constexpr bool YB = KIND != 2, AI = KIND != 0, UO = KIND != 2;
         constexpr int ITER = M * CH / 2 / NT, UNR = (ITER % CMBL_COL_UNR == 0) ? CMBL_COL_UNR : 2;
         static_assert(ITER % UNR == 0, "epilogue unroll");
@@ -396,7 +447,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             for (int k = 0; k < UNR; ++k) {
                 int p, ch; size_t g; unit_of(tid + (it + k) * NT, x0, p, ch, g);
                 vload_stream2(tc + g, ta[k][0], ta[k][1]);
-                if (!ADJ) { vload_stream2(p1 + g, p1a[k][0], p1a[k][1]); vload_stream2(p2 + g, p2a[k][0], p2a[k][1]); }
+                if (!ADJ) { vload_stream2h(p1 + g, p1a[k][0], p1a[k][1], ph); vload_stream2h(p2 + g, p2a[k][0], p2a[k][1], ph); }
                 if (YB) vload_stream2(yb + g, ya[k][0], ya[k][1]);
                 if (AI) vload_stream2(ai + g, aa[k][0], aa[k][1]);
                 jv[k][0] = vload(jc + ch * V); jv[k][1] = vload(jc + (ch + 1) * V);   // this block's own lines (L1 / L2)
@@ -437,44 +488,60 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         }
     }
 
-    // jn = cN · J[N] of the Npol planes of one batch item into this block's own scratch lines jdst[Npol][N] (global memory, read
-    // back through L1): one more spectral operator on ceil(Npol/2) complex lines — J maps real lines to real lines, so two planes'
-    // N(y) ride as the real and imaginary part of one line — done in the tile buffer that is not in use (block start: while the
-    // first tile is in flight; later: only when the batch item changes, before the next tile is requested).  Every block computes
-    // the lines it needs itself, so no block ever waits for another block of the launch: the kernel is correct under ANY
-    // residency (concurrent streams, MPS, a partially occupied device).
-    DEV void jn_lines(T* ws, int c0, T* jdst, Tw<R1>& w1, Tw<R2>& w2) const {
-        const int nl = (Npol + 1) / 2;
-        const T* nl0 = nline + (size_t)c0 * N;
-        CMBL_FOR_THREADS(tid, NT) {
-            for (int i = tid; i < 2 * nl * CH; i += NT) {
-                const int pl = i / CH, ch = i % CH;
+    // jn = cN · J[N] for up to two planes at once: one more spectral operator on ONE complex line — J maps real lines to real lines,
+    // so plane ca's N(y) rides in the real part and plane cb's (cb < 0: none) in the imaginary part — done in a tile buffer that is
+    // not in use.  Results go to dst_a / dst_b (global memory).  Ends with a barrier.
+    DEV void jn_pair(T* ws, int ca, int cb, T* dst_a, T* dst_b, Tw<R1>& w1, Tw<R2>& w2, int goff = 0, int bar = 0) const {
+        CMBL_FOR_GROUP(tid, 128, goff) {
+            for (int i = tid; i < 2 * CH; i += NT) {
+                const int pl = i / CH, ch = i % CH, c = pl ? cb : ca;
                 Vec<T> z; for (int e = 0; e < V; ++e) z.v[e] = 0;
-                if (pl < Npol) z = vload(nl0 + (size_t)pl * N + ch * V);
+                if (c >= 0) z = vload(nline + (size_t)c * N + ch * V);
                 vstore(ws + pl * N + swzp(ch, pl) * V, z);
             }
             load_tw1(w1, tid);
         }
-        CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(ws, nullptr, tid, w1, nl); CMBL_PRE_END(load_tw2(w2, tid)); }
-        CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(ws, tid, w2, nl); }
-        CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { middle(ws, tid, nullptr, 0, mult_sign, nl); CMBL_PRE_END(load_tw2(w2, tid)); }
-        CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(ws, tid, w2, nl); CMBL_PRE_END(load_tw1(w1, tid)); }
-        CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(ws, nullptr, tid, w1, nl); }
-        CMBL_SYNC();
-        CMBL_FOR_THREADS(tid, NT) {
-            for (int i = tid; i < Npol * CH; i += NT) {
+        group_sync(bar, 128);
+        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(ws, nullptr, tid, w1, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        group_sync(bar, 128);
+        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(ws, tid, w2, 1); }
+        group_sync(bar, 128);
+        CMBL_FOR_GROUP(tid, 128, goff) { middle(ws, tid, nullptr, 0, mult_sign, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        group_sync(bar, 128);
+        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(ws, tid, w2, 1); CMBL_PRE_END(load_tw1(w1, tid)); }
+        group_sync(bar, 128);
+        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(ws, nullptr, tid, w1, 1); }
+        group_sync(bar, 128);
+        CMBL_FOR_GROUP(tid, 128, goff) {
+            for (int i = tid; i < 2 * CH; i += NT) {
                 const int pl = i / CH, ch = i % CH;
-                Vec<T> z = vload(ws + pl * N + swzp(ch, pl) * V);
-                for (int e = 0; e < V; ++e) z.v[e] *= cN;
-                vstore(jdst + (size_t)pl * N + ch * V, z);
+                T* dst = pl ? dst_b : dst_a;
+                if (dst) {
+                    Vec<T> z = vload(ws + pl * N + swzp(ch, pl) * V);
+                    for (int e = 0; e < V; ++e) z.v[e] *= cN;
+                    vstore(dst + ch * V, z);
+                }
             }
         }
-        CMBL_SYNC();
+        group_sync(bar, 128);
+    }
+
+    // publisher blocks: compute the lines of one plane pair into jn_pub and raise the flags (the block's first tile is in flight)
+    DEV void jn_publish(int blk, int nC, T* ws, Tw<R1>& w1, Tw<R2>& w2, int goff = 0, int bar = 0) const {
+        const int npairs = (nC + 1) / 2, np = jn_red * npairs;
+        int b0 = (ntiles / pgroup) % nblocks;                          // round-robin: blocks b0.. own one tile (group) less than blocks 0..b0-1
+        if (b0 + np > nblocks) b0 = 0;
+        if (blk < b0 || blk >= b0 + np || blk >= nblocks) return;
+        const int pr = (blk - b0) % npairs, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
+        jn_pair(ws, ca, cb, jn_pub + (size_t)ca * N, cb >= 0 ? jn_pub + (size_t)cb * N : nullptr, w1, w2, goff, bar);
+        CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) { flag_publish(jn_flag + ca, epoch); if (cb >= 0) flag_publish(jn_flag + cb, epoch); } }
+    }
+    // the J[N] line of plane c: the published one, or a private copy computed from the same plane pair (identical bits) in `ws`
+    DEV const T* jn_resolve(int published, int c, int nC, T* ws, T* mine, Tw<R1>& w1, Tw<R2>& w2, int goff = 0, int bar = 0) const {
+        if (published) return jn_pub + (size_t)c * N;
+        const int pr = (c - cbase) / 2, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
+        jn_pair(ws, ca, cb, c == ca ? mine : nullptr, c == cb ? mine : nullptr, w1, w2, goff, bar);
+        return mine;
     }
 
     DEV void operator()(int blk, unsigned char* smem) const {
@@ -485,52 +552,55 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         Tw<R1> w1; Tw<R2> w2;
         pdl_launch_dependents();
         pdl_wait();
-        // Tile order: batch item, column tile, polarisation (fastest): the Q and U (I, Q, U) tiles of the same columns follow each
-        // other, so the p maps they share are fetched from DRAM once if they survive in L2 in between.
-        //   contig != 0: block b owns the contiguous tile range [b·ntiles/nblocks, (b+1)·ntiles/nblocks) — a block stays inside one
-        //                batch item for (almost) its whole launch, so it computes that item's J[N] lines once;
-        //   contig == 0: round-robin t = b, b + nblocks, ... (neighbouring blocks work on neighbouring column tiles at the same time);
-        //                correct as well, but a block changes batch item — and recomputes the J[N] lines — almost every tile.
-        T* const jmine = jn_blk + (size_t)blk * Npol * N;
+        // Tile order: batch item, column tile, polarisation (fastest); tiles are taken round-robin t = b, b + nblocks, ... so that at any
+        // moment the launch works on a window of neighbouring column tiles (their 128/256-byte runs share DRAM pages and the window's
+        // pages fit the TLB reach; contiguous per-block ranges spread the blocks over the whole 0.7 GB working set and were measured
+        // 25 % slower) and the Q and U (I, Q, U) tiles of the same columns are in flight together and share the p maps.
+        //   contig != 0 (experiment knob): block b owns the contiguous tile range [b·ntiles/nblocks, (b+1)·ntiles/nblocks).
+        // J[N] lines: NO block ever waits for another block.  At launch start a few blocks (jn_red per plane pair; blocks of the first
+        // wave that own one tile less than the others) compute the lines of one plane pair each into the launch-wide array jn[plane][N]
+        // and publish a per-plane flag — while their first tile is in flight.  Before a block's first epilogue on a plane it LOOKS at
+        // the flag (thread 0 during the last sweep; the answer rides on the barrier that ends it): published (the normal case — the lines are ready a few
+        // microseconds into the launch) -> it reads the shared line; not published (the producers are not resident: another stream
+        // owns the SMs, MPS, ...) -> it computes a private copy of the same plane pair (identical bits) in the tile buffer that is
+        // free at that moment and goes on.  Correct and deterministic under any residency.
+        T* const jmine = jn_blk + (size_t)blk * N;
+        const int nC = (ntiles / tiles_per_plane);                     // planes of this launch
         auto item_of = [&](int t) { return (t / Npol) / tiles_per_plane; };
         auto x0_of = [&](int t) { return ((t / Npol) % tiles_per_plane) * M; };
-        const int tstep = contig ? 1 : nblocks;
-        const int tend = contig ? (int)((long long)(blk + 1) * ntiles / nblocks) : ntiles;
-        int tile = contig ? (int)((long long)blk * ntiles / nblocks) : blk;
-        int cur = 0, ij = -1;
+        // pg > 1: a block takes the pg = Npol tiles of the same columns one after the other (groups round-robin over the blocks), and
+        // reads their shared p maps with L2 eviction hints — keep on the first reads, release on the last — so they come from DRAM once
+        const int pg = pgroup, ngroups = ntiles / pg;
+        const int gstep = contig ? 1 : nblocks;
+        const int tend = (contig ? (int)((long long)(blk + 1) * ngroups / nblocks) : ngroups) * pg;
+        auto advance = [&](int t) { return (pg > 1 && (t % pg) + 1 < pg) ? t + 1 : t + 1 + (gstep - 1) * pg; };
+        int tile = (contig ? (int)((long long)blk * ngroups / nblocks) : blk) * pg;
+        int cur = 0, cj = -1;
+        const T* jline = nullptr;
         if (tile < tend) {
-            const int it = item_of(tile), c = cbase + it * Npol + tile % Npol, x0 = x0_of(tile);
+            const int c = cbase + item_of(tile) * Npol + tile % Npol, x0 = x0_of(tile);
             CMBL_FOR_THREADS(tid, NT) {
                 issue_tile(u + (size_t)c * nmap, x0, sbase, tid);
                 if (ADJ) issue_tile(p_plane(pk, c, Npol, Nbphi, 1, nmap), x0, pbuf, tid);
                 cp_async_commit();
             }
-            jn_lines(sbase + TILE, cbase + it * Npol, jmine, w1, w2);          // while the first tile is in flight
-            ij = it;
         }
+        jn_publish(blk, nC, sbase + TILE, w1, w2);                     // (publisher blocks only) first tile in flight
         CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
-        for (; tile < tend; tile += tstep, cur ^= 1) {
+        for (; tile < tend; tile = advance(tile), cur ^= 1) {
             T* const buf = sbase + cur * TILE;
-            T* const nbuf = sbase + (cur ^ 1) * TILE;
-            const int it = item_of(tile), c = cbase + it * Npol + tile % Npol, x0 = x0_of(tile), next = tile + tstep;
-            const int cn = cbase + item_of(next) * Npol + next % Npol, x0n = x0_of(next);
+            T* const nbuf = sbase + (cur ^ 1) * TILE;                   // free from the barrier below until the next tile is requested
+            const int c = cbase + item_of(tile) * Npol + tile % Npol, x0 = x0_of(tile), next = advance(tile);
+            const int ph = (ADJ || pg == 1) ? 0 : ((tile % pg) + 1 < pg ? 1 : 2);
             const T* const p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
             const T* const p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
-            const T* const jline = jmine + (size_t)(tile % Npol) * N;
             CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
             CMBL_SYNC();
-            if (it != ij) {                                            // batch item change: the other tile buffer is free right now
-                jn_lines(nbuf, cbase + it * Npol, jmine, w1, w2);
-                ij = it;
-                CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
-            }
-            if (next < tend) {
-                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
-            }
             CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
             if (ADJ && next < tend) {
-                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0n, pbuf, tid); cp_async_commit(); }
+                const int cn = cbase + item_of(next) * Npol + next % Npol;
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0_of(next), pbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
             CMBL_SYNC();
@@ -538,14 +608,21 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) { if (pf == 3) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
             CMBL_SYNC();
+            int fl = 0;
             CMBL_FOR_THREADS(tid, NT) {
+                if (tid == 0 && c != cj) fl = (flag_look(jn_flag + c) == epoch);      // is this plane's J[N] line published?  (answer rides on the barrier)
                 if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1);
             }
-            CMBL_SYNC();
+            fl = block_or(fl);
+            if (c != cj) { jline = jn_resolve(fl, c, nC, nbuf, jmine, w1, w2); cj = c; }
+            if (next < tend) {                                         // the next tile lands during the epilogue
+                const int cn = cbase + item_of(next) * Npol + next % Npol;
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0_of(next), nbuf, tid); cp_async_commit(); }
+            }
             CMBL_FOR_THREADS(tid, NT) {
-                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
-                else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
-                else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
+                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2, ph);
+                else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2, ph);
+                else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2, ph);
                 CMBL_PRE_END(load_tw1(w1, tid));                      // twiddles of the next tile's first sweep
             }
             // the next iteration's first barrier orders these shared-memory reads before the tile buffer is refilled

@@ -7,6 +7,8 @@
 
 namespace cmbl {
 
+constexpr int RED_BLOCKS = 64;      // partial results per batch item of every reduction (fixed → deterministic)
+
 // per-axis device tables
 template <class T> struct AxisTables {
     Fft1D<T> fft;

@@ -6,7 +6,6 @@
 
 namespace cmbl {
 
-constexpr int RED_BLOCKS = 64;      // partial sums per batch item (fixed → deterministic reductions)
 
 template <class T> HD T nan2zero(T v) { return (v - v == (T)0) ? v : (T)0; }          // isfinite(v) ? v : 0
 template <class T> HD C2<T> nan2zero(C2<T> v) {                                       // complex: both parts finite

@@ -103,6 +103,10 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
  * 2x2 product (src/lenseflow.jl:198-200 with src/field_vectors.jl:48-49). */
 int cmbl_lenseflow_grad(cmbl_flow* flow, int op, const void* f_out_map, const void* delta_four, void* dfield_four,
                         void* dphi_four, int bug_compat, void* stream);
+/* get_max_lensing_step(ϕ, η) (src/lenseflow.jl:242-256): per batch item the smallest α > 0 at which 𝕀 + ∇∇(ϕ + α η) becomes singular in
+ * some pixel (out_host[Nb], double, +inf if there is none) — ϕ + α η stays in the weak-lensing regime LenseFlow needs for α below it.
+ * ϕ, η: Nb planes each, Map or Fourier.  Synchronises. */
+int cmbl_max_lensing_step(cmbl_plan* plan, const void* phi, int phi_basis, const void* eta, int eta_basis, int Nb, double* out_host, void* stream);
 /* which stage kernels this flow runs (diagnostic): bit 0 = fast persistent row kernel, bit 1 = fast persistent column kernel
  * (csrc/flow_fast.cuh; transform length 256/512/1024), 0 = generic kernels of csrc/flow.cuh */
 int cmbl_lenseflow_kernel_path(cmbl_flow* flow);

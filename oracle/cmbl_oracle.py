@@ -420,6 +420,29 @@ def neg_delta_velocity_H(L: CachedLenseFlow, k: int, state, bug_compat: bool = T
     return (df_dt.astype(f.dtype), ddf_dt.astype(df.dtype), ddphi_dt.astype(dphi.dtype))
 
 
+def get_max_lensing_step(proj: ProjLambert, phi_four: np.ndarray, eta_four: np.ndarray) -> np.ndarray:
+    """get_max_lensing_step(ϕ, η) (src/lenseflow.jl:242-256): smallest positive root α of det(𝕀 + ∇∇(ϕ + α η)) = 0 over the pixels, per batch
+    item (the reference takes the minimum over the batch as well).  Both off-diagonal Hessian entries are ϕ₁₂ = H[2,1] as in the reference."""
+    T = proj.T
+    _, Hp = gradhess(proj, phi_four); _, He = gradhess(proj, eta_four)
+    m = lambda h: irfft2(h, proj.Ny).astype(T)
+    # `ϕ₁₁, ϕ₁₂, ϕ₂₁, ϕ₂₂ = Map.(H)` walks the SMatrix column-major: the variable called ϕ₁₂ is H[2,1] = ∇₁(∇₂ϕ)
+    p11, p12, p22 = m(Hp[0][0]), m(Hp[1][0]), m(Hp[1][1])
+    e11, e12, e22 = m(He[0][0]), m(He[1][0]), m(He[1][1])
+    one = T(1)
+    a = e11 * e22 - e12 * e12
+    b = e11 * (one + p22) + e22 * (one + p11) - T(2) * e12 * p12
+    c = (one + p11) * (one + p22) - p12 * p12
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sq = np.sqrt(b * b - T(4) * a * c)
+        a1 = (-b + sq) / (T(2) * a); a2 = (-b - sq) / (T(2) * a)
+    out = []
+    for i in range(a1.shape[0]):
+        cand = np.concatenate([a1[i][a1[i] > 0].ravel(), a2[i][a2[i] > 0].ravel()])
+        out.append(float(cand.min()) if cand.size else np.inf)
+    return np.array(out)
+
+
 def _axpy(y, a, k):
     if isinstance(y, tuple):
         return tuple(_axpy(yi, a, ki) for yi, ki in zip(y, k))

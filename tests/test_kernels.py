@@ -150,6 +150,29 @@ def test_precompute_p_cache(pkg, be, Ny, Nx):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_get_max_lensing_step(pkg, be, dtype):
+    """get_max_lensing_step(ϕ, η) (src/lenseflow.jl:242-256) against the oracle, per batch item and as the reference's single minimum;
+    the defining property: det(𝕀 + ∇∇(ϕ + α η)) keeps its sign for α < αmax and has changed it somewhere just above αmax."""
+    pr = make_problem(pkg, 64, 32, "I", dtype, nb=3, nsteps=2, mask=False, seed=4, lib=be.lib, device=be.device)
+    pr2 = make_problem(pkg, 64, 32, "I", dtype, nb=3, nsteps=2, mask=False, seed=9, lib=be.lib, device=be.device)
+    ϕ, η = pr["phi"], pr2["phi"] * 3.0
+    ref = O.get_max_lensing_step(pr["oproj"], pr["sim"]["phi"], 3.0 * pr2["sim"]["phi"])
+    got = pkg.get_max_lensing_step(ϕ, η, per_batch=True)
+    assert np.all(np.isfinite(ref)) and np.allclose(got, ref, rtol=1e-9 if dtype == "f64" else 2e-3)
+    assert np.isclose(pkg.get_max_lensing_step(ϕ, pkg.Map(η)), ref.min(), rtol=1e-9 if dtype == "f64" else 2e-3)    # any basis; one number like the reference
+    if dtype == "f64":
+        op = pr["oproj"]
+        def mindet(a):
+            _, H = O.gradhess(op, pr["sim"]["phi"] + a[:, None, None, None] * 3.0 * pr2["sim"]["phi"])
+            h11, h12, h22 = (O.irfft2(h, op.Ny) for h in (H[0][0], H[1][0], H[1][1]))
+            return ((1 + h11) * (1 + h22) - h12 * h12).reshape(3, -1).min(axis=1)
+        assert np.all(mindet(0.999 * ref) > 0) and np.all(mindet(1.001 * ref) < 0)
+    prP = make_problem(pkg, 64, 32, "P", dtype, nb=3, nsteps=2, mask=False, seed=4, lib=be.lib, device=be.device)
+    with pytest.raises(pkg.CmblError):                                   # spin-0 fields only
+        pkg.get_max_lensing_step(ϕ, prP["f"])
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("pol", ["I", "P"])
 def test_lenseflow_adjoint_identity(pkg, be, pol, dtype):
     """f'(Lϕ g) ≈ (f'Lϕ) g  (runtests.jl:556,570)."""
