@@ -586,8 +586,45 @@ def Hessian_logpdf_preconditioner(ds: BaseDataSet):
     return DiagOp(Field(ds.Cf.diag.basis, r.to(ds.Cf.diag.arr.dtype), ds.Cf.diag.proj))
 
 
+class Comm:
+    """cmbl_comm (include/cmbl_b200.h): the NCCL communicator of the C ABI for a batch sharded over the GPUs of a box — what a host
+    program without torch.distributed (the Julia shim) uses.  Rank 0 creates the 128-byte id with `Comm.unique_id(lib)` and hands
+    it to the other ranks by its own means; every rank then constructs `Comm(lib, nranks, rank, id)` on its device."""
+
+    def __init__(self, lib, nranks: int, rank: int, uid: bytes):
+        import ctypes
+        self.lib, self.nranks, self.rank = lib, nranks, rank
+        self.handle = c_void_p()
+        self._id = ctypes.create_string_buffer(bytes(uid), 128)
+        lib.call("cmbl_comm_init", byref(self.handle), nranks, rank, self._id)
+
+    @staticmethod
+    def unique_id(lib) -> bytes:
+        import ctypes
+        buf = ctypes.create_string_buffer(128)
+        lib.call("cmbl_comm_unique_id", buf)
+        return buf.raw
+
+    def allreduce(self, values, op: str = "sum", stream=None) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        arr = (c_double * len(v))(*v)
+        self.lib.call("cmbl_comm_allreduce", self.handle, arr, len(v), {"sum": 0, "min": 1, "max": 2}[op], stream or c_void_p(0))
+        return np.array(arr[:])
+
+    def close(self):
+        if self.handle:
+            self.lib.call("cmbl_comm_destroy", self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def conjugate_gradient_wiener(ds: BaseDataSet, ϕ: Field, fstart: Field | None = None, nsteps=500, tol=1e-1, offset=False,
-                              group=None):
+                              group=None, comm: Comm | None = None):
     """conjugate_gradient (src/numerical_algorithms.jl:73-134) specialised to the Wiener-filter Hessian.  Returns
     (bestx, history) with history = [(i, res[Nb]), ...].  With a torch.distributed `group` the batch is sharded over ranks and
     the lock-step rules `all(res<bestres)` / `all(res<tol)` are taken across ranks (one tiny all-reduce per iteration)."""
@@ -602,7 +639,10 @@ def conjugate_gradient_wiener(ds: BaseDataSet, ϕ: Field, fstart: Field | None =
     if group is None:
         hist = (c_double * (nsteps * nb))()
         iters = c_int(0)
-        p.lib.call("cmbl_wiener_cg", h, fs, _ptr(out), nsteps, c_double(tol), 1 if offset else 0, byref(iters), hist, st)
+        if comm is not None:                      # batch sharded over the ranks of a C-ABI communicator: the whole loop stays in the library
+            p.lib.call("cmbl_wiener_cg_sharded", h, comm.handle, fs, _ptr(out), nsteps, c_double(tol), 1 if offset else 0, byref(iters), hist, st)
+        else:
+            p.lib.call("cmbl_wiener_cg", h, fs, _ptr(out), nsteps, c_double(tol), 1 if offset else 0, byref(iters), hist, st)
         H = np.array(hist[: iters.value * nb]).reshape(iters.value, nb)
         return ds.d._like(out), [(i + 1, H[i]) for i in range(iters.value)]
     import torch.distributed as dist
@@ -628,9 +668,10 @@ def conjugate_gradient_wiener(ds: BaseDataSet, ϕ: Field, fstart: Field | None =
 
 
 def argmaxf_logpdf(ds: BaseDataSet, ϕ: Field, fstart: Field | None = None, offset=False,
-                   conjgrad_kwargs=dict(tol=1e-1, nsteps=500), group=None):
-    """argmaxf_logpdf(ds, (;ϕ)) (src/maximization.jl:17-42): the Wiener filter of ds.d at fixed ϕ; returns (f, history)."""
-    return conjugate_gradient_wiener(ds, ϕ, fstart=fstart, offset=offset, group=group, **conjgrad_kwargs)
+                   conjgrad_kwargs=dict(tol=1e-1, nsteps=500), group=None, comm=None):
+    """argmaxf_logpdf(ds, (;ϕ)) (src/maximization.jl:17-42): the Wiener filter of ds.d at fixed ϕ; returns (f, history).  `group` (a
+    torch.distributed group) or `comm` (a C-ABI `Comm`) shard the batch over ranks with the reference's lock-step stopping rule."""
+    return conjugate_gradient_wiener(ds, ϕ, fstart=fstart, offset=offset, group=group, comm=comm, **conjgrad_kwargs)
 
 
 argmaxf_lnP = argmaxf_logpdf          # the name BASELINE.json uses (pre-0.10 spelling)

@@ -59,6 +59,11 @@ SIGNATURES = {
     "cmbl_cg_result": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "cmbl_wiener_cg": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, POINTER(c_int), POINTER(c_double), c_void_p]),
     "cmbl_gradientf_logpdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "cmbl_comm_unique_id": (c_int, [c_void_p]),
+    "cmbl_comm_init": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p]),
+    "cmbl_comm_destroy": (c_int, [c_void_p]),
+    "cmbl_comm_allreduce": (c_int, [c_void_p, POINTER(c_double), c_int, c_int, c_void_p]),
+    "cmbl_wiener_cg_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, POINTER(c_int), POINTER(c_double), c_void_p]),
 }
 
 

@@ -97,29 +97,7 @@ int cmbl_cg_result(cmbl_cg* cg, int which, void* f_out, void* stream) {
 
 int cmbl_wiener_cg(cmbl_cg* cg, const void* fstart_or_null, void* f_out, int nsteps, double tol, int offset,
                    int* iters_out, double* res_hist_host, void* stream) {
-    CMBL_API_BEGIN
-    CMBL_REQUIRE(cg && cg->g && f_out, "NULL argument");
-    CMBL_REQUIRE(nsteps >= 1, "nsteps must be >= 1");
-    CMBL_DISPATCH(cg->g->plan, {
-        auto& G = CG_T(cg);
-        const int Nb = G.Nb;
-        std::vector<double> res(Nb), best(Nb);
-        cmbl::cg_begin<T>(G, (const cmbl::C2<T>*)fstart_or_null, offset != 0, res.data(), as_stream(stream));
-        best = res;
-        if (res_hist_host) for (int b = 0; b < Nb; ++b) res_hist_host[b] = res[b];
-        int i = 1;
-        for (i = 2; i <= nsteps; ++i) {                                   // numerical_algorithms.jl:99-121
-            cmbl::cg_step<T>(G, res.data(), as_stream(stream));
-            bool all_better = true, all_conv = true;
-            for (int b = 0; b < Nb; ++b) { all_better = all_better && (res[b] < best[b]); all_conv = all_conv && (res[b] < tol); }
-            if (all_better) { best = res; cmbl::dev_copy(G.bestx.p, G.x.p, sizeof(cmbl::C2<T>) * G.nf() * G.C, as_stream(stream)); }
-            if (res_hist_host) for (int b = 0; b < Nb; ++b) res_hist_host[(size_t)(i - 1) * Nb + b] = res[b];
-            if (all_conv) break;
-        }
-        if (iters_out) *iters_out = (i > nsteps) ? nsteps : i;
-        cmbl::dev_copy(f_out, G.bestx.p, sizeof(cmbl::C2<T>) * G.nf() * G.C, as_stream(stream));
-    });
-    CMBL_API_END
+    return cmbl_wiener_cg_sharded(cg, nullptr, fstart_or_null, f_out, nsteps, tol, offset, iters_out, res_hist_host, stream);
 }
 
 int cmbl_gradientf_logpdf(cmbl_cg* cg, const void* f, const void* d_or_null, int d_is_zero, void* out, void* stream) {

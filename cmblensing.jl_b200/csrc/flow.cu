@@ -49,7 +49,6 @@ static int device_sms() {
 static int fast_cols_contig() { static const int v = [] { const char* e = getenv("CMBL_COL_CONTIG"); return e ? atoi(e) : 0; }(); return v; }
 // blocks that compute and publish each J[N] plane pair at launch start (0 = none: every block computes private copies — test knob)
 static int fast_cols_jn_red() { static const int v = [] { const char* e = getenv("CMBL_COL_JN_RED"); return e ? atoi(e) : 3; }(); return v; }
-static int fast_cols_pgroup() { static const int v = [] { const char* e = getenv("CMBL_COL_PGROUP"); return e ? atoi(e) : 1; }(); return v; }
 static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
     static const int v = [] { const char* e = getenv("CMBL_FLOW_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     return v > 0 ? std::min(full, v * device_sms()) : full;
@@ -96,10 +95,7 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     B b;
     b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv; b.mult_sign = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
     b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / B::M; b.ntiles = nC * b.tiles_per_plane;
-    const int cap = fast_block_cap(persistent_blocks<B>(B::SMEM));
-    // polarisation groups (Q and U tiles of the same columns in one block, p maps shared through L2 hints) once every block has >= 2 groups
-    b.pgroup = (!adj && F.Npol > 1 && fast_cols_pgroup() && b.ntiles / F.Npol >= 2 * cap) ? F.Npol : 1;
-    b.nblocks = std::min(b.ntiles / b.pgroup, cap);
+    b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
     b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T), adj); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
     b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = nullptr;

@@ -103,30 +103,6 @@ template <> DEV void vload_stream2<double>(const double* p, Vec<double>& a, Vec<
     a = vload(p); b = vload(p + 2);
 #endif
 }
-// the same with an L2 eviction priority: 1 = evict_last (the line will be read once more soon: keep it), 2 = evict_first (last use)
-template <class T> DEV void vload_stream2h(const T* p, Vec<T>& a, Vec<T>& b, int hint);
-template <> DEV void vload_stream2h<float>(const float* p, Vec<float>& a, Vec<float>& b, int hint) {
-#ifdef __CUDA_ARCH__
-    if (hint == 1)
-        asm("ld.global.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3]),
-            "=f"(b.v[0]), "=f"(b.v[1]), "=f"(b.v[2]), "=f"(b.v[3]) : "l"(p));
-    else if (hint == 2)
-        asm("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3]),
-            "=f"(b.v[0]), "=f"(b.v[1]), "=f"(b.v[2]), "=f"(b.v[3]) : "l"(p));
-    else vload_stream2(p, a, b);
-#else
-    (void)hint; a = vload(p); b = vload(p + 4);
-#endif
-}
-template <> DEV void vload_stream2h<double>(const double* p, Vec<double>& a, Vec<double>& b, int hint) {
-#ifdef __CUDA_ARCH__
-    if (hint == 1) asm("ld.global.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.v[0]), "=d"(a.v[1]), "=d"(b.v[0]), "=d"(b.v[1]) : "l"(p));
-    else if (hint == 2) asm("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.v[0]), "=d"(a.v[1]), "=d"(b.v[0]), "=d"(b.v[1]) : "l"(p));
-    else vload_stream2(p, a, b);
-#else
-    (void)hint; a = vload(p); b = vload(p + 2);
-#endif
-}
 // two adjacent 16-byte chunks as one 256-bit store (sm_100: st.global.v8.f32 / v4.f64); p must be 32-byte aligned
 template <class T> DEV void vstore2(T* p, const Vec<T>& a, const Vec<T>& b);
 template <> DEV void vstore2<float>(float* p, const Vec<float>& a, const Vec<float>& b) {
@@ -188,6 +164,13 @@ DEV int flag_look(const int* p) {
 DEV int block_or(int v) {
 #ifdef __CUDA_ARCH__
     return __syncthreads_or(v);
+#else
+    return v;
+#endif
+}
+DEV int block_and(int v) {
+#ifdef __CUDA_ARCH__
+    return __syncthreads_and(v);
 #else
     return v;
 #endif
@@ -299,7 +282,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     const T* tw1; const T* tw2; const T* mult_d; const T* mult_sign; T cN;     // mult_sign, cN: the Nyquist line operator J (flow.cuh)
     const T* nline;                                  // N(y) per plane (row kernel of this stage)
     T* jn_pub; int* jn_flag; int epoch;              // launch-wide J[N] lines [plane][N]; jn_flag[plane] == epoch <=> this launch's line is published
-    T* jn_blk; int contig, jn_red, pgroup;           // per-block private J[N] line [block][N] (fallback); tile order knob; publishers per plane pair; tiles per polarisation group
+    T* jn_blk; int contig, jn_red;                   // per-block private J[N] line [block][N] (fallback); tile order knob; publishers per plane pair
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
@@ -433,7 +416,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         p = (k >> lgU) & (M - 1); ch = (yb << lgGV) + 2 * h;
         goff = ((size_t)yb * Nx + x0 + p) * G + 2 * h * V;
     }
-    template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2, int ph = 0) const {
+    template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2) const {
         constexpr bool YB = KIND != 2, AI = KIND != 0, UO = KIND != 2;
         constexpr int ITER = M * CH / 2 / NT, UNR = (ITER % CMBL_COL_UNR == 0) ? CMBL_COL_UNR : 2;
         static_assert(ITER % UNR == 0, "epilogue unroll");
@@ -447,7 +430,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             for (int k = 0; k < UNR; ++k) {
                 int p, ch; size_t g; unit_of(tid + (it + k) * NT, x0, p, ch, g);
                 vload_stream2(tc + g, ta[k][0], ta[k][1]);
-                if (!ADJ) { vload_stream2h(p1 + g, p1a[k][0], p1a[k][1], ph); vload_stream2h(p2 + g, p2a[k][0], p2a[k][1], ph); }
+                if (!ADJ) { vload_stream2(p1 + g, p1a[k][0], p1a[k][1]); vload_stream2(p2 + g, p2a[k][0], p2a[k][1]); }
                 if (YB) vload_stream2(yb + g, ya[k][0], ya[k][1]);
                 if (AI) vload_stream2(ai + g, aa[k][0], aa[k][1]);
                 jv[k][0] = vload(jc + ch * V); jv[k][1] = vload(jc + (ch + 1) * V);   // this block's own lines (L1 / L2)
@@ -529,7 +512,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     // publisher blocks: compute the lines of one plane pair into jn_pub and raise the flags (the block's first tile is in flight)
     DEV void jn_publish(int blk, int nC, T* ws, Tw<R1>& w1, Tw<R2>& w2, int goff = 0, int bar = 0) const {
         const int npairs = (nC + 1) / 2, np = jn_red * npairs;
-        int b0 = (ntiles / pgroup) % nblocks;                          // round-robin: blocks b0.. own one tile (group) less than blocks 0..b0-1
+        int b0 = ntiles % nblocks;                                     // round-robin: blocks b0.. own one tile less than blocks 0..b0-1
         if (b0 + np > nblocks) b0 = 0;
         if (blk < b0 || blk >= b0 + np || blk >= nblocks) return;
         const int pr = (blk - b0) % npairs, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
@@ -562,19 +545,15 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         // and publish a per-plane flag — while their first tile is in flight.  Before a block's first epilogue on a plane it LOOKS at
         // the flag (thread 0 during the last sweep; the answer rides on the barrier that ends it): published (the normal case — the lines are ready a few
         // microseconds into the launch) -> it reads the shared line; not published (the producers are not resident: another stream
-        // owns the SMs, MPS, ...) -> it computes a private copy of the same plane pair (identical bits) in the tile buffer that is
-        // free at that moment and goes on.  Correct and deterministic under any residency.
+        // owns the SMs, MPS, ...) -> it computes a private copy of the same plane pair (identical bits) and goes on.  Correct and
+        // deterministic under any residency.
         T* const jmine = jn_blk + (size_t)blk * N;
         const int nC = (ntiles / tiles_per_plane);                     // planes of this launch
         auto item_of = [&](int t) { return (t / Npol) / tiles_per_plane; };
         auto x0_of = [&](int t) { return ((t / Npol) % tiles_per_plane) * M; };
-        // pg > 1: a block takes the pg = Npol tiles of the same columns one after the other (groups round-robin over the blocks), and
-        // reads their shared p maps with L2 eviction hints — keep on the first reads, release on the last — so they come from DRAM once
-        const int pg = pgroup, ngroups = ntiles / pg;
-        const int gstep = contig ? 1 : nblocks;
-        const int tend = (contig ? (int)((long long)(blk + 1) * ngroups / nblocks) : ngroups) * pg;
-        auto advance = [&](int t) { return (pg > 1 && (t % pg) + 1 < pg) ? t + 1 : t + 1 + (gstep - 1) * pg; };
-        int tile = (contig ? (int)((long long)blk * ngroups / nblocks) : blk) * pg;
+        const int tstep = contig ? 1 : nblocks;
+        const int tend = contig ? (int)((long long)(blk + 1) * ntiles / nblocks) : ntiles;
+        int tile = contig ? (int)((long long)blk * ntiles / nblocks) : blk;
         int cur = 0, cj = -1;
         const T* jline = nullptr;
         if (tile < tend) {
@@ -587,20 +566,22 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
         }
         jn_publish(blk, nC, sbase + TILE, w1, w2);                     // (publisher blocks only) first tile in flight
         CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
-        for (; tile < tend; tile = advance(tile), cur ^= 1) {
+        for (; tile < tend; tile += tstep, cur ^= 1) {
             T* const buf = sbase + cur * TILE;
-            T* const nbuf = sbase + (cur ^ 1) * TILE;                   // free from the barrier below until the next tile is requested
-            const int c = cbase + item_of(tile) * Npol + tile % Npol, x0 = x0_of(tile), next = advance(tile);
-            const int ph = (ADJ || pg == 1) ? 0 : ((tile % pg) + 1 < pg ? 1 : 2);
+            T* const nbuf = sbase + (cur ^ 1) * TILE;
+            const int c = cbase + item_of(tile) * Npol + tile % Npol, x0 = x0_of(tile), next = tile + tstep;
+            const int cn = cbase + item_of(next) * Npol + next % Npol, x0n = x0_of(next);
             const T* const p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
             const T* const p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
             CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
             CMBL_SYNC();
+            if (next < tend) {                                         // the next tile lands while this one is transformed (DRAM is idle then)
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
+            }
             CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
             if (ADJ && next < tend) {
-                const int cn = cbase + item_of(next) * Npol + next % Npol;
-                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0_of(next), pbuf, tid); cp_async_commit(); }
+                CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0n, pbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
             CMBL_SYNC();
@@ -608,21 +589,30 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) { if (pf == 3) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
             CMBL_SYNC();
-            int fl = 0;
+            int fl = 1;
             CMBL_FOR_THREADS(tid, NT) {
-                if (tid == 0 && c != cj) fl = (flag_look(jn_flag + c) == epoch);      // is this plane's J[N] line published?  (answer rides on the barrier)
+                if (tid == 0 && c != cj) fl = (flag_look(jn_flag + c) == epoch);      // is this plane's J[N] line published?  (the answer rides on the barrier)
                 if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1);
             }
-            fl = block_or(fl);
-            if (c != cj) { jline = jn_resolve(fl, c, nC, nbuf, jmine, w1, w2); cj = c; }
-            if (next < tend) {                                         // the next tile lands during the epilogue
-                const int cn = cbase + item_of(next) * Npol + next % Npol;
-                CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0_of(next), nbuf, tid); cp_async_commit(); }
+            fl = block_and(fl);
+            if (c != cj) {
+                if (fl) jline = jn_pub + (size_t)c * N;
+                else {
+                    // RARE (the publishers are not resident: another stream owns the SMs, MPS, ...): compute a private copy of the line.
+                    // The work space is the other tile buffer: let the tile that is landing there arrive, use the buffer, request the tile again.
+                    CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
+                    CMBL_SYNC();
+                    jline = jn_resolve(0, c, nC, nbuf, jmine, w1, w2);
+                    if (next < tend) {
+                        CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
+                    }
+                }
+                cj = c;
             }
             CMBL_FOR_THREADS(tid, NT) {
-                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2, ph);
-                else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2, ph);
-                else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2, ph);
+                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
+                else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
+                else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
                 CMBL_PRE_END(load_tw1(w1, tid));                      // twiddles of the next tile's first sweep
             }
             // the next iteration's first barrier orders these shared-memory reads before the tile buffer is refilled

@@ -27,6 +27,7 @@ extern "C" {
 typedef struct cmbl_plan cmbl_plan;
 typedef struct cmbl_flow cmbl_flow;
 typedef struct cmbl_cg cmbl_cg;
+typedef struct cmbl_comm cmbl_comm;
 
 #define CMBL_OK 0
 #define CMBL_ERR_INVALID (-1)
@@ -148,6 +149,22 @@ int cmbl_wiener_cg(cmbl_cg* cg, const void* fstart_or_null, void* f_out, int nst
                    int* iters_out, double* res_hist_host, void* stream);
 /* gradientf_logpdf (src/dataset.jl:76-80) at f with data d (d_or_null = NULL: the dataset's d); all harmonic basis, device */
 int cmbl_gradientf_logpdf(cmbl_cg* cg, const void* f, const void* d_or_null, int d_is_zero, void* out, void* stream);
+
+/* ---- multi-GPU: the path shards over independent batch items / chains (src/batching.jl, pmap over chains src/sampling.jl:292-307) with no
+ * data-path collective.  What couples the shards is a handful of scalars: conjugate_gradient's lock-step rules all(res<bestres) /
+ * all(res<tol) over the batch (src/numerical_algorithms.jl:110-121) and MAP_joint's batch-summed line-search objective
+ * (src/maximization.jl:197).  One process per GPU; rank 0 calls cmbl_comm_unique_id and hands the 128 bytes to the other ranks by whatever
+ * the host program uses (MPI, Distributed.jl, torch.distributed); every rank then calls cmbl_comm_init on its device.  NCCL is loaded
+ * with dlopen at that moment (CMBL_NCCL_LIB overrides the path); single-GPU users never need it. */
+int cmbl_comm_unique_id(void* id128);
+int cmbl_comm_init(cmbl_comm** comm, int nranks, int rank, const void* id128);
+int cmbl_comm_destroy(cmbl_comm* comm);
+/* in-place all-reduce of n (<= 64) HOST doubles over the ranks; op 0 = sum, 1 = min, 2 = max.  Synchronises the stream. */
+int cmbl_comm_allreduce(cmbl_comm* comm, double* values_host, int n, int op, void* stream);
+/* cmbl_wiener_cg with the batch sharded over the ranks of `comm` (NULL: this rank alone): every rank runs the same number of iterations and
+ * keeps bestx by the rule evaluated over all batch items of all ranks — one 16-byte all-reduce per iteration. */
+int cmbl_wiener_cg_sharded(cmbl_cg* cg, cmbl_comm* comm_or_null, const void* fstart_or_null, void* f_out, int nsteps, double tol, int offset,
+                           int* iters_out, double* res_hist_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -215,6 +215,22 @@ def test_headline_config_vs_oracle(cuda_pkg, dtype):
     assert relerr(g.cpu_numpy(), O.gradientf_logpdf(pr["dso"], pr["sim"]["f"], pr["dso"].d)) < (1e-10 if dtype == "f64" else 1e-4)
 
 
+def test_comm_abi_single_rank_and_sharded_cg(cuda_pkg):
+    """cmbl_comm_* through the C ABI with one rank (NCCL loaded by dlopen): the all-reduce is the identity and cmbl_wiener_cg_sharded takes the
+    same iterations and returns the same bits as cmbl_wiener_cg.  (Two real ranks: scripts/comm_2gpu.py under torchrun, profiles/r02_comm_2gpu.log.)"""
+    pkg = cuda_pkg
+    lib = pkg.load()
+    comm = pkg.Comm(lib, 1, 0, pkg.Comm.unique_id(lib))
+    assert np.array_equal(comm.allreduce([1.5, -2.0, 7.0], "sum"), [1.5, -2.0, 7.0]) and np.array_equal(comm.allreduce([3.0], "min"), [3.0])
+    pr = make_problem(pkg, 64, 64, "P", "f64", nb=2, nsteps=5, mask=True, seed=9, theta=3.0, device=DEV)
+    x0, h0 = pkg.argmaxf_logpdf(pr["ds"], pr["phi"], conjgrad_kwargs=dict(tol=1e-1, nsteps=60))
+    x1, h1 = pkg.argmaxf_logpdf(pr["ds"], pr["phi"], conjgrad_kwargs=dict(tol=1e-1, nsteps=60), comm=comm)
+    assert len(h0) == len(h1) and torch.equal(x0.arr, x1.arr) and all(np.array_equal(a[1], b[1]) for a, b in zip(h0, h1))
+    comm.close()
+    with pytest.raises(pkg.CmblError):
+        pkg.Comm(lib, 2, 5, b"\0" * 128)                                   # rank out of range
+
+
 def test_concurrent_streams_no_stall(cuda_pkg):
     """The stage kernels must make progress under ANY residency: two LenseFlow handles integrating at the same time on two
     streams while a third stream keeps the SMs busy with unrelated kernels.  (Round 1's column kernel waited on flags published by
