@@ -368,18 +368,24 @@ def Cℓ_to_2D(proj: ProjLambert, ℓ, Cℓ) -> np.ndarray:
 def Cℓ_to_Cov(pol: str, proj: ProjLambert, ℓ, *Cℓs, units=None):
     """Cℓ_to_Cov(:I | :P | :IP, proj, Cℓ...; units=Ωpix): Diagonal(Fourier), Diagonal(EBFourier) from (EE, BB), or
     BlockDiagIEB from (TT, EE, BB, TE) — argument order as the reference (src/proj_lambert.jl:361-371)."""
-    units = proj.Ωpix if units is None else units
-    npT = _NP_REAL[proj.dtype_code]
-    planes = [(Cℓ_to_2D(proj, ℓ, c) / npT(units)).astype(npT) for c in Cℓs]
     want = {"I": 1, "P": 2, "IP": 4}.get(pol)
     if want is None:
         raise CmblError("`pol` should be one of I, P, or IP")                     # src/dataset.jl:263
-    if len(planes) != want:
+    if len(Cℓs) != want:
         raise CmblError(f"Cℓ_to_Cov({pol}) takes {want} spectra")
+    # the interpolation onto the ℓmag grid runs on the device (cmbl_cl_to_cov): one real half-plane per spectrum
+    ell = np.ascontiguousarray(ℓ, dtype=np.float64)
+    out = torch.empty((want,) + proj.fourier_shape(1, 1)[2:], dtype=proj.T, device=proj.device)
+    for i, c in enumerate(Cℓs):
+        cl = np.ascontiguousarray(c, dtype=np.float64)
+        if cl.shape != ell.shape:
+            raise CmblError("Cℓ_to_Cov: ℓ and Cℓ must have the same length")
+        proj.lib.call("cmbl_cl_to_cov", proj.handle, ell.ctypes.data_as(c_void_p), cl.ctypes.data_as(c_void_p), int(ell.size),
+                      c_double(0.0 if units is None else float(units)), c_void_p(out[i].data_ptr()), _stream(out))
     if pol == "IP":
-        TT, EE, BB, TE = planes
+        TT, EE, BB, TE = (out[i] for i in range(4))
         return BlockDiagIEB(TT, TE, EE, BB, proj=proj)
-    return DiagOp(Field("Fourier" if pol == "I" else "EBFourier", torch.from_numpy(np.stack(planes)[None]), proj))
+    return DiagOp(Field("Fourier" if pol == "I" else "EBFourier", out[None], proj))
 
 
 Cl_to_Cov = Cℓ_to_Cov
@@ -513,8 +519,13 @@ class BaseDataSet:
         p = d.proj
         L = self.L(ϕ, self.nsteps) if isinstance(self.L, type) else self.L
         cache = L.cache(d)                                                    # pooled per shape; precompute!! for L.ϕ
+        # the handle holds raw device pointers to d and to the operators' planes: reuse it only while every one of them is the same
+        # tensor (load_sim-style `ds.d = d` or a replaced operator builds a new handle); the key keeps the tensors alive
+        ops = (self.Cf, self.Cn, self.Cnhat, self.B, self.Bhat, self.Mf, self.Mpix)
+        key = (cache, d.arr) + tuple(None if D is None else D._real for D in ops)
         cur = self._cg.get("solver")
-        if cur is not None and cur[1] is cache:
+        old = self._cg.get("key")
+        if cur is not None and old is not None and len(old) == len(key) and all(a is b for a, b in zip(old, key)):
             self._cg["solver"] = (cur[0], cache, L, ϕ)
             return self._cg["solver"]
         want = BlockDiagIEB if d.Npol == 3 else DiagOp
@@ -526,6 +537,7 @@ class BaseDataSet:
         h = _CgHandle(p.lib)
         p.lib.call("cmbl_cg_create", byref(h.h), cache.handle, byref(desc), _stream(d.arr))
         self._cg["owner"] = h                                                  # previous owner (if any) is released here
+        self._cg["key"] = key
         self._cg["solver"] = (h.h, cache, L, ϕ)
         return self._cg["solver"]
 
@@ -949,11 +961,16 @@ def hmc_step(U, x: Field, Λ: DiagOp, δUδx, symp_kwargs=(dict(N=25, ϵ=0.01),)
     `white` (unit white Map field) and `uniforms` (one U(0,1) per batch item) may be passed in for reproducibility."""
     pr = x.proj
     ΔH = accept = None
-    for kw in symp_kwargs:
+    whites = list(white) if isinstance(white, (list, tuple)) else [white] * len(symp_kwargs)       # one momentum draw per entry (src/sampling.jl:408)
+    unis = list(uniforms) if (isinstance(uniforms, (list, tuple)) and len(uniforms) and np.ndim(uniforms[0]) > 0) else [uniforms] * len(symp_kwargs)
+    if len(whites) != len(symp_kwargs) or len(unis) != len(symp_kwargs):
+        raise CmblError("hmc_step: pass one `white` / `uniforms` per symp_kwargs entry (or a single one / None)")
+    for kw, white, uniforms in zip(symp_kwargs, whites, unis):
         w = white if white is not None else Field("Map", torch.randn(pr.map_shape(1, x.Nbatch), dtype=pr.T, device=pr.device, generator=generator), pr)
         p0 = DiagOp(Field("Fourier", torch.sqrt(Λ._real).to(pr.cT), pr)) * Fourier(w)          # simulate(rng, Λ)
         ΔH, xtest, _ = symplectic_integrate(x, p0, Λ, U, δUδx, **kw)
-        u = np.asarray(uniforms, dtype=np.float64) if uniforms is not None else torch.rand(x.Nbatch, generator=None).double().numpy()
+        u = np.asarray(uniforms, dtype=np.float64) if uniforms is not None else \
+            torch.rand(x.Nbatch, dtype=torch.float64, device=pr.device if generator is not None and generator.device.type != "cpu" else "cpu", generator=generator).cpu().numpy()
         accept = np.logical_or(always_accept, np.log(u) < ΔH)
         a = accept.astype(np.float64)
         x = xtest * a + x * (1 - a)
@@ -961,12 +978,13 @@ def hmc_step(U, x: Field, Λ: DiagOp, δUδx, symp_kwargs=(dict(N=25, ϵ=0.01),)
 
 
 def gibbs_sample_ϕ(ds: BaseDataSet, f_mixed: Field, ϕ_mixed: Field, symp_kwargs=(dict(N=25, ϵ=0.01),), always_accept=False,
-                   white: Field | None = None, uniforms=None, bug_compat: bool = True):
-    """gibbs_sample_ϕ! (src/sampling.jl:397-403): one HMC update of ϕ° at fixed f° under logpdf(Mixed(ds))."""
+                   white: Field | None = None, uniforms=None, bug_compat: bool = True, generator=None):
+    """gibbs_sample_ϕ! (src/sampling.jl:397-403): one HMC update of ϕ° at fixed f° under logpdf(Mixed(ds)).  `generator` seeds both the
+    momentum draw and the accept/reject uniforms when `white` / `uniforms` are not supplied."""
     mds = Mixed(ds)
     U = lambda x: logpdf(mds, f_mixed, x)
     δU = lambda x: gradient_logpdf_mixed(ds, f_mixed, x, bug_compat)[1]
-    return hmc_step(U, Fourier(ϕ_mixed), mass_matrix_ϕ(ds), δU, symp_kwargs, always_accept, white, uniforms)
+    return hmc_step(U, Fourier(ϕ_mixed), mass_matrix_ϕ(ds), δU, symp_kwargs, always_accept, white, uniforms, generator)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -1085,6 +1103,8 @@ def sample_joint(ds: BaseDataSet, ϕstart: Field, nsamps_per_chain: int | None =
     chains (the reference's `Nbatch` chains per worker); steps are numbered from 2 and proposals are always accepted while
     step < nburnin_always_accept, like the reference.  `draws` (optional, one dict(wf, wn, wp, u) per step) fixes the random numbers.
     Returns the chain as a list of dicts (f, ϕ, ΔH, accept, logpdf)."""
+    if draws is None and nsamps_per_chain is None:
+        raise CmblError("sample_joint: pass nsamps_per_chain (or explicit `draws`)")
     nsteps = len(draws) if draws is not None else (nsamps_per_chain - 1)
     ϕ, chain = Fourier(ϕstart), []
     for i in range(nsteps):
@@ -1092,7 +1112,7 @@ def sample_joint(ds: BaseDataSet, ϕstart: Field, nsamps_per_chain: int | None =
         dr = draws[i] if draws is not None else {}
         f, _ = sample_f(ds, ϕ, dr.get("wf"), dr.get("wn"), generator, conjgrad_kwargs)
         f_m, ϕ_m = mix(ds, f, ϕ)
-        ϕ_m, ΔH, acc = gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs, step < nburnin_always_accept, dr.get("wp"), dr.get("u"), bug_compat)
+        ϕ_m, ΔH, acc = gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs, step < nburnin_always_accept, dr.get("wp"), dr.get("u"), bug_compat, generator)
         f, ϕ = unmix(ds, f_m, ϕ_m)
         chain.append({"step": step, "f": f, "ϕ": ϕ, "ΔH": ΔH, "accept": acc, "logpdf": logpdf(ds, f, ϕ)})      # string keys (no NFKC folding)
     return chain

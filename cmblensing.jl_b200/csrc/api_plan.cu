@@ -1,6 +1,7 @@
 // extern "C": plan, FFT entry points, error reporting.
 #include "api_common.cuh"
 #include "fft2d.cuh"
+#include "pointwise.cuh"
 
 namespace cmbl {
 std::string prof_report();
@@ -56,6 +57,25 @@ int cmbl_plan_grids(cmbl_plan* plan, void* lx, void* ly, void* lam, void* s2, vo
         if (s2) memcpy(s2, P.h_sin2phi.data(), P.h_sin2phi.size() * sizeof(T));
         if (c2) memcpy(c2, P.h_cos2phi.data(), P.h_cos2phi.size() * sizeof(T));
         if (scalars) { scalars[0] = P.dx; scalars[1] = P.dlx; scalars[2] = P.dly; scalars[3] = P.omega_pix; scalars[4] = P.nyquist; }
+    });
+    CMBL_API_END
+}
+
+int cmbl_cl_to_cov(cmbl_plan* plan, const double* ell_host, const double* cl_host, int n, double units, void* out, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan && plan->p && ell_host && cl_host && out, "NULL argument");
+    CMBL_REQUIRE(n >= 2, "the Cl table needs at least two points");
+    for (int i = 1; i < n; ++i) CMBL_REQUIRE(ell_host[i] > ell_host[i - 1], "ell must be strictly ascending");
+    CMBL_DISPATCH(plan->p.get(), {
+        cmbl::DevBuf tab;
+        double* d = (double*)tab.reserve(sizeof(double) * 2 * (size_t)n);
+        cmbl::dev_upload(d, ell_host, sizeof(double) * n, as_stream(stream));
+        cmbl::dev_upload(d + n, cl_host, sizeof(double) * n, as_stream(stream));
+        cmbl::ClTo2DBody<T> b{P.Nx, P.Nyh, n, P.lx, P.ly, d, d + n, units == 0 ? P.omega_pix : (T)units, (T*)out};
+        cmbl::launch(b, (int)((P.four_elems() + b.NT - 1) / b.NT), 0, as_stream(stream));
+#ifndef CMBL_EMU
+        CMBL_CUDA(cudaStreamSynchronize(as_stream(stream)));                  // the table buffer is released on return
+#endif
     });
     CMBL_API_END
 }

@@ -90,9 +90,10 @@ static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cm
 }
 template <class T, class B>
 static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb,
-                             int private_lines, bool adj, cmblStream_t st) {
+                             int private_lines, bool adj, cmblStream_t st, T* dx_out = nullptr, T* dy_out = nullptr) {
     PlanT<T>& P = *F.P;
     B b;
+    b.dx_out = dx_out; b.dy_out = dy_out;
     b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv; b.mult_sign = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
     b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / B::M; b.ntiles = nC * b.tiles_per_plane;
     b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
@@ -107,7 +108,11 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     launch(b, b.nblocks, B::SMEM, st);
 }
 template <class T, int LOGN, bool ADJ>
-static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb, cmblStream_t st) {
+static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb, cmblStream_t st,
+                      T* dx_out, T* dy_out) {
+    if constexpr (!ADJ) {
+        if (dx_out) { fast_cols_launch<T, FastColBody<T, LOGN, false, true>>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, 1, false, st, dx_out, dy_out); return; }
+    }
     fast_cols_launch<T, FastColBody<T, LOGN, ADJ>>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, 1, ADJ, st);
 }
 template <class T> static bool fast_rows_ok(const PlanT<T>& P) {
@@ -126,15 +131,15 @@ template <class T> int flow_rg_rows(const PlanT<T>& P) {
     if (!fast_rows_ok(P) || !fast_cols_ok(P) || P.Ny % 64 != 0 || P.Nx % 32 != 0) return 0;
     return (FAST_TILE_BYTES / (P.Nx * 16)) * (16 / (int)sizeof(T));
 }
-template <class T, bool TO_RG> static void convert_layout(PlanT<T>& P, int G, const T* in, T* out, int C, cmblStream_t st) {
+template <class T, bool TO_RG> void convert_layout(PlanT<T>& P, int G, const T* in, T* out, int C, cmblStream_t st) {
     typedef LayoutBody<T, TO_RG> B;
     B b{P.Ny, P.Nx, G, in, out};
     launch(b, C * (P.Nx / B::TX) * (P.Ny / B::TY), B::SMEM, st);
 }
 
 template <class T, bool ADJ>
-static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
-                       T ca, T cb, cmblStream_t st) {
+void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
+                T ca, T cb, cmblStream_t st, T* dx_out, T* dy_out) {
     PlanT<T>& P = *F.P;
     T* tmp = reinterpret_cast<T*>(F.tmp.p); T* nline = reinterpret_cast<T*>(F.nline.p); T* jn = reinterpret_cast<T*>(F.jn.p);
     const bool fast = flow_rg_rows(P) > 0;
@@ -155,11 +160,12 @@ static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, c
     }
     if (fast) {
         switch (P.Ny) {
-            case 256: fast_cols<T, 8, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st); break;
-            case 512: fast_cols<T, 9, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st); break;
-            default: fast_cols<T, 10, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st); break;
+            case 256: fast_cols<T, 8, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
+            case 512: fast_cols<T, 9, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
+            default: fast_cols<T, 10, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
         }
     } else {
+        CMBL_REQUIRE(!dx_out, "derivative export needs the fast stage kernels");
         FlowColBody<T, ADJ> b;
         b.fy = P.ay.fft; b.mult_d = P.ay.mult_deriv;
         b.Ny = P.Ny; b.Nx = P.Nx; b.L = col_lines<T>(P.ay.fft, P.Nx); b.logNyv = ilog2(P.Ny / Vec<T>::N); b.tiles_per_plane = P.Nx / (2 * b.L);
@@ -171,7 +177,7 @@ static void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, c
 }
 
 // working buffers of the integrator, sized for all F.C planes
-template <class T> static void flow_reserve(FlowT<T>& F, cmblStream_t st) {
+template <class T> void flow_reserve(FlowT<T>& F, cmblStream_t st) {
     PlanT<T>& P = *F.P;
     const size_t nmap = P.map_elems();
     if (flow_rg_rows(P)) F.yrg.reserve(sizeof(T) * nmap * F.C);
@@ -245,9 +251,17 @@ template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* ou
         return;
     }
     // adjoint flows: Fourier state integrated in map space (see flow.cuh)
-    const C2<T>* Y0 = reinterpret_cast<const C2<T>*>(in);
-    C2<T>* Yout = reinterpret_cast<C2<T>*>(out);
     T* y = reinterpret_cast<T*>(F.ybuf.reserve(sizeof(T) * nmap * F.C));
+    flow_adj_prepare<T>(F, reinterpret_cast<const C2<T>*>(in), y, st);
+    if (op == CMBL_OP_LH) flow_integrate<T>(F, true, y, 2 * n, 0, st);
+    else flow_integrate<T>(F, true, y, 0, 2 * n, st);
+    flow_adj_finish<T>(F, y, reinterpret_cast<C2<T>*>(out), st);
+    (void)nf;
+}
+
+// Fourier state Y0 of an adjoint flow -> its map y = irfft2(Y0), with the ky ∈ {0, Ny/2} rows saved and the Nyquist accumulators cleared
+template <class T> void flow_adj_prepare(FlowT<T>& F, const C2<T>* Y0, T* y, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
     C2<T>* rows0 = reinterpret_cast<C2<T>*>(F.rows0.reserve(sizeof(C2<T>) * 2 * (size_t)P.Nx * F.C));
     T* nacc = reinterpret_cast<T*>(F.nacc.reserve(sizeof(T) * (size_t)P.Ny * F.C));
     T* macc = reinterpret_cast<T*>(F.macc.reserve(sizeof(T) * (size_t)P.Nx * F.C));
@@ -258,17 +272,16 @@ template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* ou
     dev_zero(nacc, sizeof(T) * (size_t)P.Ny * F.C, st);
     dev_zero(macc, sizeof(T) * (size_t)P.Nx * F.C, st);
     irfft2<T>(P, Y0, y, F.C, st);
-    if (op == CMBL_OP_LH) flow_integrate<T>(F, true, y, 2 * n, 0, st);
-    else flow_integrate<T>(F, true, y, 0, 2 * n, st);
+}
+// integrated map y -> Fourier result: rfft2(y) plus what a map cannot carry (saved rows, Nyquist accumulators)
+template <class T> void flow_adj_finish(FlowT<T>& F, const T* y, C2<T>* Yout, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
     rfft2<T>(P, y, Yout, F.C, st);
-    {
-        AdjFixBody<T> b;
-        b.fx = P.ax.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh; b.lxN = P.ax.ell_nyq; b.lyN = P.ay.ell_nyq;
-        b.rows0 = rows0; b.nacc = nacc; b.macc = macc; b.out = Yout;
-        size_t smem = sizeof(C2<T>) * Tile<T, false>::pitch_for(P.Nx, P.ax.fft.sk) + sizeof(T) * 2 * b.NT;
-        launch(b, F.C, smem, st);
-    }
-    (void)nf;
+    AdjFixBody<T> b;
+    b.fx = P.ax.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh; b.lxN = P.ax.ell_nyq; b.lyN = P.ay.ell_nyq;
+    b.rows0 = reinterpret_cast<C2<T>*>(F.rows0.p); b.nacc = reinterpret_cast<T*>(F.nacc.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.out = Yout;
+    size_t smem = sizeof(C2<T>) * Tile<T, false>::pitch_for(P.Nx, P.ax.fft.sk) + sizeof(T) * 2 * b.NT;
+    launch(b, F.C, smem, st);
 }
 
 template <class T> void max_lensing_step(PlanT<T>& P, const void* phi, int phi_basis, const void* eta, int eta_basis, int Nb, double* out_host, cmblStream_t st) {
@@ -313,6 +326,14 @@ template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_rg_rows(*F.P)
     template void flow_integrate_range<T>(FlowT<T>&, bool, T*, int, int, int, int, cmblStream_t);      \
     template void flow_apply<T>(FlowT<T>&, int, const void*, void*, cmblStream_t);                     \
     template int flow_kernel_path<T>(FlowT<T>&);                                                       \
+    template int flow_rg_rows<T>(const PlanT<T>&);                                                     \
+    template void flow_reserve<T>(FlowT<T>&, cmblStream_t);                                            \
+    template void flow_adj_prepare<T>(FlowT<T>&, const C2<T>*, T*, cmblStream_t);                      \
+    template void flow_adj_finish<T>(FlowT<T>&, const T*, C2<T>*, cmblStream_t);                       \
+    template void convert_layout<T, true>(PlanT<T>&, int, const T*, T*, int, cmblStream_t);            \
+    template void convert_layout<T, false>(PlanT<T>&, int, const T*, T*, int, cmblStream_t);           \
+    template void flow_stage<T, false>(FlowT<T>&, int, int, const T*, int, T, const T*, const T*, T*, T*, T, T, cmblStream_t, T*, T*);  \
+    template void flow_stage<T, true>(FlowT<T>&, int, int, const T*, int, T, const T*, const T*, T*, T*, T, T, cmblStream_t, T*, T*);   \
     template void max_lensing_step<T>(PlanT<T>&, const void*, int, const void*, int, int, double*, cmblStream_t);
 INST(float)
 INST(double)

@@ -375,6 +375,7 @@ template <class T> struct FlowT : FlowBase {
     int pcache_G = 0;                    // layout of pcache / minv: 0 = reference layout, else rows per row group
     DevBuf yrg;                          // row-grouped copy of the ODE state
     DevBuf g_yf, g_yd, g_yp, g_uf, g_ud, g_up, g_af, g_ad, g_ap, g_kf, g_kd, g_kp, g_ldf, g_gxy, g_a12, g_six, g_spec, g_spec2;   // δ-flow scratch (flow_grad.cu)
+    DevBuf gq_f[3], gq_d[3], gq_ref, gq_gx, gq_gy, gq_A, gq_Aref, gq_spec;      // fused δ-flow (flow_grad.cu): (y, acc, u) of the f and δf legs, derivative maps, δϕ integrand accumulators
     DevBuf jnblk;                        // per-block private J[N] line of the fast column kernel (fallback when the shared line is not published)
     DevBuf jnflag; int jn_epoch = 0;     // per-plane publication flags of the shared J[N] lines (value = launch epoch)
     DevBuf pcache, minv, ybuf, acc, ubuf, tmp, nline, jn, counter, nacc, macc, rows0, spec, gh;
@@ -383,6 +384,15 @@ template <class T> struct FlowT : FlowBase {
 };
 
 template <class T> void flow_precompute(FlowT<T>& F, const void* phi, int phi_basis, bool with_minv, cmblStream_t st);
+// building blocks shared with the transpose-δ flow (flow_grad.cu)
+template <class T> int flow_rg_rows(const PlanT<T>& P);                       // rows per group of the internal row-grouped layout (0: generic kernels)
+template <class T> void flow_reserve(FlowT<T>& F, cmblStream_t st);
+template <class T, bool TO_RG> void convert_layout(PlanT<T>& P, int G, const T* in, T* out, int C, cmblStream_t st);
+// one RK stage (row kernel + column kernel) on planes [c0, c0+nC); dx_out/dy_out (fast forward kernels only): also export ∂ₓu, ∂ᵧu
+template <class T, bool ADJ> void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
+                                             T ca, T cb, cmblStream_t st, T* dx_out = nullptr, T* dy_out = nullptr);
+template <class T> void flow_adj_prepare(FlowT<T>& F, const C2<T>* Y0, T* y, cmblStream_t st);
+template <class T> void flow_adj_finish(FlowT<T>& F, const T* y, C2<T>* Yout, cmblStream_t st);
 // integrate the map-space flow in place on y from stage index k0 to k1 (0 or 2n)
 template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st);
 template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* y, int k0, int k1, int c0, int nC, cmblStream_t st);

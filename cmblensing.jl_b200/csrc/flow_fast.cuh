@@ -263,8 +263,11 @@ template <class T, bool TO_RG> struct LayoutBody {
 #ifndef CMBL_COL_UNR
 #define CMBL_COL_UNR 2
 #endif
-template <class T, int LOGN, bool ADJ> struct FastColBody {
-    static constexpr int NT = 128, MINB = ADJ ? 2 : CMBL_COL_MINB;
+// DMODE (forward kernel only): the epilogue also stores the two derivative maps it has in registers — ∂ₓu = tmp ± jn and ∂ᵧu — for
+// the δϕ integrand of the transpose-δ flow (flow_grad.cu); a separate instantiation, so the plain kernel's register budget is untouched.
+template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
+    static_assert(!(ADJ && DMODE), "derivative export exists for the forward kernel only");
+    static constexpr int NT = 128, MINB = (ADJ || DMODE) ? 2 : CMBL_COL_MINB;
     static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), CH = N / V;       // CH chunks per column
     static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
     static constexpr int S1 = N / R1, N2 = N / R1;                                   // pass-2 stride is 16
@@ -287,6 +290,7 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
     const T* ybase; const T* acc_in; T* acc_out; T* u_out; T ca, cb;
+    T* dx_out = nullptr; T* dy_out = nullptr;        // DMODE: ∂ₓu, ∂ᵧu (row-grouped layout, like every other map of the launch)
 
     template <int R> struct Tw { Vec<T> r[R], i[R]; };
 
@@ -439,21 +443,23 @@ template <class T, int LOGN, bool ADJ> struct FastColBody {
             for (int k = 0; k < UNR; ++k) {
                 int p, ch; size_t g; unit_of(tid + (it + k) * NT, x0, p, ch, g);
                 const T sgn = (p & 1) ? (T)-1 : (T)1;                  // x0 is even: + for even x, − for odd x
-                Vec<T> a0[2], u0[2];
+                Vec<T> a0[2], u0[2], dxv[2], dyv[2];
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2) {
                     const Vec<T> z = vload(buf + p * N + swzp(ch + s2, p) * V);
 #pragma unroll
                     for (int q = 0; q < V; ++q) {
-                        const T kk = ADJ ? ta[k][s2].v[q] + sgn * jv[k][s2].v[q] + z.v[q]
-                                         : p1a[k][s2].v[q] * (ta[k][s2].v[q] + sgn * jv[k][s2].v[q]) + p2a[k][s2].v[q] * z.v[q];
+                        const T gxq = ta[k][s2].v[q] + sgn * jv[k][s2].v[q];
+                        const T kk = ADJ ? gxq + z.v[q] : p1a[k][s2].v[q] * gxq + p2a[k][s2].v[q] * z.v[q];
                         const T y0 = YB ? ya[k][s2].v[q] : (T)0;
                         a0[s2].v[q] = (AI ? aa[k][s2].v[q] : y0) + cb * kk;
                         u0[s2].v[q] = y0 + ca * kk;
+                        if (DMODE) { dxv[s2].v[q] = gxq; dyv[s2].v[q] = z.v[q]; }
                     }
                 }
                 vstore2(acc_out + pbase + g, a0[0], a0[1]);
                 if (UO) vstore2(u_out + pbase + g, u0[0], u0[1]);
+                if (DMODE) { vstore2(dx_out + pbase + g, dxv[0], dxv[1]); vstore2(dy_out + pbase + g, dyv[0], dyv[1]); }
             }
         }
     }

@@ -146,9 +146,148 @@ template <class T> struct RkUpdateBody {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused transpose-δ flow (transform lengths with fast stage kernels).  Three observations turn the 12 two-dimensional transforms of one
+// velocity evaluation into the stage kernels the plain flows already run:
+//   * the f leg IS the forward flow (its velocity p₁∂ₓf + p₂∂ᵧf is what flow_rows + flow_cols compute), and the δf leg IS the adjoint
+//     flow, which is integrated in map space (flow.cuh): Ł(δf) at a stage is simply the δf leg's stage map;
+//   * the column kernel of the f leg has both derivative maps ∂ₓf, ∂ᵧf in registers in its epilogue and exports them (DMODE);
+//   * δϕ never feeds back into the velocity: dδϕ/dt = g(t, f, δf).  RK4 is then a quadrature for it, and because every term of g is a
+//     fixed linear operator applied to a MAP — iℓₓ·rfft2(m₁) + iℓᵧ·rfft2(m₂) + Σ_ij (−iℓ_i)(−iℓ_j)·rfft2(t p_j m_i) — the five maps are
+//     accumulated over the 4n stages with the RK weights and transformed ONCE at the end: 5·Nb transforms per pullback instead of
+//     5·Nb per stage.
+// Per stage: forward stage kernels (f leg, derivative export), one pointwise kernel (w = Σ_pol Łδf·∇f, m = M⁻¹w, the five
+// accumulators), adjoint stage kernels (δf leg).  Same trajectory as the reference's joint RK4 (src/flowops.jl:40-68).
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct DeltaAccBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "delta_acc"; }
+    int Npol, Nb, Nbphi; size_t nmap; bool bug_compat; T t, wgt;
+    const T* ud; const T* gx; const T* gy;           // [Nb][Npol] maps: δf leg stage state, ∂ₓf, ∂ᵧf
+    const T* pk; const T* mk3;                        // p[k]: [Nbphi][2], M⁻¹[k]: [Nbphi][3]  (every map of this kernel in the same layout)
+    T* A;                                             // [Nb][5] accumulators: m1, m2, t p1 m1, t (p2 m1 + p1 m2), t p2 m2
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < nmap * Nb) {
+                const size_t b = e / nmap, r = e - b * nmap;
+                const size_t bp = (Nbphi == 1) ? 0 : b;
+                const T p1 = pk[(bp * 2 + 0) * nmap + r], p2 = pk[(bp * 2 + 1) * nmap + r];
+                const T m11 = mk3[(bp * 3 + 0) * nmap + r], m21 = mk3[(bp * 3 + 1) * nmap + r], m22 = mk3[(bp * 3 + 2) * nmap + r];
+                T w1 = 0, w2 = 0;
+                for (int pol = 0; pol < Npol; ++pol) {
+                    const size_t i = (b * Npol + pol) * nmap + r;
+                    const T l = ud[i];
+                    w1 += l * gx[i]; w2 += l * gy[i];
+                }
+                const T m1 = m11 * w1 + m21 * w2;                                      // M₁₂ ≡ M₂₁
+                const T m2 = bug_compat ? (m21 * m1 + m22 * w2) : (m21 * w1 + m22 * w2);
+                T* a = A + b * 5 * nmap + r;
+                a[0] += wgt * m1; a[nmap] += wgt * m2;
+                a[2 * nmap] += wgt * (t * p1 * m1); a[3 * nmap] += wgt * (t * p2 * m1 + t * p1 * m2); a[4 * nmap] += wgt * (t * p2 * m2);
+            }
+        }
+    }
+};
+
+// δϕ = iℓₓ·S0 + iℓᵧ·S1 + (−iℓₓ)²·S2 + (−iℓₓ)(−iℓᵧ)·S3 + (−iℓᵧ)²·S4 with S = rfft2 of the five accumulators
+template <class T> struct DeltaPhiSpecBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "delta_phi_spec"; }
+    int Nx, Nyh, Nb; const T* lx; const T* ly; const C2<T>* S; C2<T>* dphi;
+    DEV void operator()(int blk, unsigned char*) const {
+        const size_t nf = (size_t)Nx * Nyh;
+        CMBL_FOR_THREADS(tid, NT) {
+            size_t e = (size_t)blk * NT + tid;
+            if (e < nf * (size_t)Nb) {
+                const size_t b = e / nf, r = e - b * nf;
+                const int kx = (int)(r / Nyh), ky = (int)(r - (size_t)kx * Nyh);
+                const C2<T> d1 = mk<T>((T)0, lx[kx]), d2 = mk<T>((T)0, ly[ky]), n1 = mk<T>((T)0, -lx[kx]), n2 = mk<T>((T)0, -ly[ky]);
+                const C2<T>* s = S + b * 5 * nf + r;
+                C2<T> v = cmul(d1, s[0]) + cmul(d2, s[nf]);
+                v = v + cmul(n1, cmul(n1, s[2 * nf]));
+                v = v + cmul(n1, cmul(n2, s[3 * nf]));
+                v = v + cmul(n2, cmul(n2, s[4 * nf]));
+                dphi[e] = v;
+            }
+        }
+    }
+};
+
+template <class T> static void flow_grad_fused(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,
+                                               bool bug_compat, cmblStream_t st) {
+    PlanT<T>& P = *F.P;
+    const size_t nmap = P.map_elems(), nf = P.four_elems();
+    const int C = F.C, Nb = F.Nb, n = F.nsteps, G = flow_rg_rows(P);
+    const size_t mC = nmap * C;
+    CMBL_REQUIRE(G > 0 && G == F.pcache_G, "fused transpose-δ flow needs the row-grouped caches");
+    flow_reserve(F, st);
+    T* f3[3]; T* d3[3];                               // (y, acc, u) of the two legs, row-grouped
+    for (int i = 0; i < 3; ++i) { f3[i] = (T*)F.gq_f[i].reserve(sizeof(T) * mC); d3[i] = (T*)F.gq_d[i].reserve(sizeof(T) * mC); }
+    T* ref = (T*)F.gq_ref.reserve(sizeof(T) * mC);                                    // a reference-layout map (C planes) for the conversions
+    T* gx = (T*)F.gq_gx.reserve(sizeof(T) * mC); T* gy = (T*)F.gq_gy.reserve(sizeof(T) * mC);
+    T* A = (T*)F.gq_A.reserve(sizeof(T) * 5 * nmap * Nb); T* Aref = (T*)F.gq_Aref.reserve(sizeof(T) * 5 * nmap * Nb);
+    C2<T>* spec = (C2<T>*)F.gq_spec.reserve(sizeof(C2<T>) * 5 * nf * Nb);
+    // initial state: f leg = the forward result, δf leg = irfft2(Δ) (+ what a map cannot carry, flow.cuh), δϕ integrand accumulators = 0
+    convert_layout<T, true>(P, G, fout, f3[0], C, st);
+    flow_adj_prepare<T>(F, delta, ref, st);
+    convert_layout<T, true>(P, G, ref, d3[0], C, st);
+    dev_zero(A, sizeof(T) * 5 * nmap * Nb, st);
+    const int k0 = (op == CMBL_OP_L) ? 2 * n : 0, k1 = (op == CMBL_OP_L) ? 0 : 2 * n;
+    const int sgn = k1 > k0 ? 1 : -1;
+    const double h = (double)sgn / n;
+    const T h2 = (T)(h / 2), h1 = (T)h, h6 = (T)(h / 6), h3 = (T)(h / 3);
+    const T* mk3 = reinterpret_cast<const T*>(F.minv.p);
+    int kk = k0;
+    for (int step = 0; step < n; ++step) {
+        for (int s = 0; s < 4; ++s) {
+            const int kq = kk + (s == 0 ? 0 : (s < 3 ? sgn : 2 * sgn));
+            const T ca = (s < 2) ? h2 : h1, cb = (s == 0 || s == 3) ? h6 : h3;
+            auto stage = [&](T** L3, bool adj, T* dxo, T* dyo) {
+                T* y = L3[0]; T* acc = L3[1]; T* ub = L3[2];
+                const T* u = (s == 0) ? y : ub; const T* ybase = (s == 3) ? nullptr : y; const T* acc_in = (s == 0) ? nullptr : acc;
+                T* acc_out = (s == 3) ? y : acc; T* u_out = (s == 3) ? nullptr : ub;
+                if (adj) flow_stage<T, true>(F, 0, C, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st);
+                else flow_stage<T, false>(F, 0, C, u, kq, cb, ybase, acc_in, acc_out, u_out, ca, cb, st, dxo, dyo);
+            };
+            const T* ud = (s == 0) ? d3[0] : d3[2];                                   // δf leg's stage state, read BEFORE that leg advances
+            stage(f3, false, gx, gy);
+            {
+                DeltaAccBody<T> b;
+                b.Npol = F.Npol; b.Nb = Nb; b.Nbphi = F.Nbphi; b.nmap = nmap; b.bug_compat = bug_compat;
+                b.t = (T)((double)kq / (double)(2 * n)); b.wgt = cb;
+                b.ud = ud; b.gx = gx; b.gy = gy; b.pk = F.pk(kq); b.mk3 = mk3 + (size_t)kq * F.Nbphi * 3 * nmap; b.A = A;
+                launch(b, (int)((nmap * Nb + b.NT - 1) / b.NT), 0, st);
+            }
+            stage(d3, true, nullptr, nullptr);
+        }
+        kk += 2 * sgn;
+    }
+    // δf: back to the reference layout, rfft2, restore the rows / Nyquist terms a map cannot carry
+    convert_layout<T, false>(P, G, d3[0], ref, C, st);
+    flow_adj_finish<T>(F, ref, dfield, st);
+    // δϕ: the five accumulated maps, transformed once
+    convert_layout<T, false>(P, G, A, Aref, 5 * Nb, st);
+    rfft2<T>(P, Aref, spec, 5 * Nb, st);
+    DeltaPhiSpecBody<T> b{P.Nx, P.Nyh, Nb, P.lx, P.ly, spec, dphi};
+    launch(b, (int)((nf * (size_t)Nb + b.NT - 1) / b.NT), 0, st);
+}
+
+static bool grad_fused_enabled() { static const bool v = [] { const char* e = getenv("CMBL_GRAD_FUSED"); return !e || atoi(e) != 0; }(); return v; }
+
+template <class T> static void flow_grad_general(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,
+                                                 bool bug_compat, cmblStream_t st);
+
 template <class T> void flow_grad(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,
                                   bool bug_compat, cmblStream_t st) {
     CMBL_REQUIRE(F.have_p && F.have_minv, "cmbl_lenseflow_grad needs cmbl_lenseflow_precompute(..., with_minv = 1)");
+    if (grad_fused_enabled() && flow_rg_rows(*F.P) > 0 && F.pcache_G > 0) flow_grad_fused<T>(F, op, fout, delta, dfield, dphi, bug_compat, st);
+    else flow_grad_general<T>(F, op, fout, delta, dfield, dphi, bug_compat, st);
+}
+
+// general path (any power-of-two size): one velocity evaluation = 12 batched 2-D transforms + three pointwise kernels
+template <class T> static void flow_grad_general(FlowT<T>& F, int op, const T* fout, const C2<T>* delta, C2<T>* dfield, C2<T>* dphi,
+                                                 bool bug_compat, cmblStream_t st) {
     PlanT<T>& P = *F.P;
     const size_t nmap = P.map_elems(), nf = P.four_elems();
     const int C = F.C, Nb = F.Nb, n = F.nsteps;

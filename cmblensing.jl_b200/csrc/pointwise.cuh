@@ -14,6 +14,35 @@ template <class T> HD C2<T> nan2zero(C2<T> v) {                                 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Cℓ_to_2D / Cℓ_to_Cov (src/proj_lambert.jl:173-175,361-364): out[kx][ky] = nan2zero(Cℓ(ℓmag)) / units with Cℓ the linear
+// interpolation of the table (ell[n] ascending, cl[n]; NaN outside it, src/numerical_algorithms.jl:148-177) and ℓmag = √(ℓx²+ℓy²) in T.
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct ClTo2DBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "cl_to_2d"; }
+    int Nx, Nyh, n; const T* lx; const T* ly; const double* ell; const double* cl; T units; T* out;
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            const size_t e = (size_t)blk * NT + tid;
+            if (e < (size_t)Nx * Nyh) {
+                const int kx = (int)(e / Nyh), ky = (int)(e - (size_t)kx * Nyh);
+                const T lm = sqrt(lx[kx] * lx[kx] + ly[ky] * ly[ky]);
+                const double x = (double)lm;
+                double v = 0;                                                  // outside the table: NaN -> nan2zero -> 0
+                if (x >= ell[0] && x <= ell[n - 1]) {
+                    int lo = 0, hi = n - 1;                                    // last i with ell[i] <= x
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ell[mid] <= x) lo = mid; else hi = mid; }
+                    if (lo == n - 1 || ell[lo] == x) v = cl[lo];
+                    else v = (cl[lo + 1] - cl[lo]) / (ell[lo + 1] - ell[lo]) * (x - ell[lo]) + cl[lo];
+                    if (!(v - v == 0)) v = 0;
+                }
+                out[e] = (T)v / units;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // DiagOp * f , DiagOp \ f
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool CPLX> struct DiagMulBody {

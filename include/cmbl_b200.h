@@ -61,6 +61,11 @@ int cmbl_plan_destroy(cmbl_plan* plan);
  * {Δx, Δℓx, Δℓy, Ωpix, nyquist} */
 int cmbl_plan_grids(cmbl_plan* plan, void* lx, void* ly, void* lam_rfft, void* sin2phi, void* cos2phi, double* scalars);
 
+/* Cℓ_to_Cov(:I, proj, Cℓ; units) (src/proj_lambert.jl:173-175,361-364): out = nan2zero(Cℓ(ℓmag)) / units as ONE real half-plane (Ny/2+1, Nx) of the
+ * plan's dtype on the device; Cℓ = linear interpolation of the HOST table (ell ascending), NaN -> 0 outside it.  units = 0 means Ωpix.
+ * (:P / :IP operators are stacks of such planes: EE, BB / TT, TE, EE, BB.)  Synchronises. */
+int cmbl_cl_to_cov(cmbl_plan* plan, const double* ell_host, const double* cl_host, int n, double units, void* out, void* stream);
+
 /* ---- batched 2-D real FFT: m_rfft! / m_irfft! (src/util_fft.jl:26-27; call sites src/proj_lambert.jl:245-300) ---- */
 int cmbl_rfft2(cmbl_plan* plan, const void* map, void* four, int C, void* stream);        /* unnormalised            */
 int cmbl_irfft2(cmbl_plan* plan, const void* four, void* map, int C, void* stream);       /* 1/(Ny Nx); input intact */
