@@ -48,6 +48,8 @@ SIGNATURES = {
     "cmbl_lenseflow_precompute": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cmbl_lenseflow_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "cmbl_lenseflow_apply_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "cmbl_lenseflow_apply_host_async": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "cmbl_lenseflow_host_sync": (c_int, []),
     "cmbl_lenseflow_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cmbl_max_lensing_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, POINTER(c_double), c_void_p]),
     "cmbl_lenseflow_kernel_path": (c_int, [c_void_p]),

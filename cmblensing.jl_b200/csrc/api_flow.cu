@@ -57,12 +57,20 @@ struct HostPipe {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_start = nullptr, ev_fin = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
+    // asynchronous calls: two staging slots used alternately; slot_free[s] = the D2H of the call that used slot s last has finished
+    cmbl::DevBuf slot[2]; cudaEvent_t slot_free[2] = {nullptr, nullptr}, a_in[2] = {nullptr, nullptr}, a_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false}; unsigned ncalls = 0;
     void ensure(int n) {
         if (!s_in) {
             CMBL_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
             CMBL_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
             CMBL_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
             CMBL_CUDA(cudaEventCreateWithFlags(&ev_fin, cudaEventDisableTiming));
+            for (int i = 0; i < 2; ++i) {
+                CMBL_CUDA(cudaEventCreateWithFlags(&slot_free[i], cudaEventDisableTiming));
+                CMBL_CUDA(cudaEventCreateWithFlags(&a_in[i], cudaEventDisableTiming));
+                CMBL_CUDA(cudaEventCreateWithFlags(&a_done[i], cudaEventDisableTiming));
+            }
         }
         while ((int)ev_in.size() < n) {
             cudaEvent_t a, b;
@@ -72,6 +80,7 @@ struct HostPipe {
         }
     }
 };
+HostPipe& host_pipe() { static thread_local HostPipe hp; return hp; }
 int host_chunks() { static const int v = [] { const char* e = getenv("CMBL_HOST_CHUNKS"); return e ? atoi(e) : 3; }(); return v; }
 }  // namespace
 #endif
@@ -102,7 +111,7 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
             // Map-space flows (L*f, L\f): batch items are independent, so the batch moves through a three-stage pipeline —
             // H2D of items i+1.. on one copy stream, the integration of item group i on the caller's stream, D2H of finished
             // groups on a second copy stream (PCIe is full duplex) — instead of copy-in, compute, copy-out back to back.
-            static thread_local HostPipe hp;
+            HostPipe& hp = host_pipe();
             // group sizes: the first and the last group are the exposed transfers, so they are small (a quarter of the batch);
             // the middle of the batch moves in larger groups that keep the persistent stage kernels filled
             std::vector<int> sizes;
@@ -120,10 +129,7 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
             const char* hin = static_cast<const char*>(in_host); char* hout = static_cast<char*>(out_host); char* dd = static_cast<char*>(d);
             CMBL_CUDA(cudaEventRecord(hp.ev_start, st));                       // the staging buffer is free once earlier work on `st` is done
             CMBL_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_start, 0));
-            // All groups integrate on the caller's stream, one after another.  (Integrating consecutive groups on two streams was
-            // measured and rejected: the persistent column kernel's blocks wait on flags published by other blocks of the same
-            // launch, which is only safe while every block of a launch is resident — two concurrent launches break that and
-            // were seen to stall for seconds.)
+            // All groups integrate on the caller's stream, one after another: they share the handle's work buffers.
             for (int i = 0, b0 = 0; i < ng; b0 += sizes[i], ++i) {
                 const size_t off = plane_b * (size_t)b0 * F.Npol, cb = plane_b * (size_t)sizes[i] * F.Npol;
                 CMBL_CUDA(cudaMemcpyAsync(dd + off, hin + off, cb, cudaMemcpyHostToDevice, hp.s_in));
@@ -145,6 +151,59 @@ int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void
         }
 #endif
     });
+    CMBL_API_END
+}
+
+// Asynchronous variant for a caller that streams many fields through one operator: returns as soon as the work is queued.  Successive
+// calls overlap — the H2D copy of call i+1 runs during the integration of call i, whose D2H copy runs during the integration of call
+// i+1 (two device staging slots, two copy streams) — so the steady-state cost of a call is max(integration, one-way transfer) instead of
+// their sum.  in_host must stay unchanged and out_host is valid only after cmbl_lenseflow_host_sync().
+int cmbl_lenseflow_apply_host_async(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(flow && flow->f && in_host && out_host, "NULL argument");
+    CMBL_REQUIRE(op >= 0 && op <= 3, "LenseFlow op must be 0..3");
+    CMBL_DISPATCH(flow->f->plan, {
+        auto& F = *static_cast<cmbl::FlowT<T>*>(flow->f.get());
+        const bool four = (op == CMBL_OP_LH || op == CMBL_OP_LHINV);
+        const size_t bytes = (four ? sizeof(cmbl::C2<T>) * P.four_elems() : sizeof(T) * P.map_elems()) * (size_t)F.C;
+#ifdef CMBL_EMU
+        static thread_local cmbl::DevBuf io;
+        void* d = io.reserve(bytes);
+        memcpy(d, in_host, bytes);
+        cmbl::flow_apply<T>(F, op, d, d, as_stream(stream));
+        cmbl::dev_download(out_host, d, bytes, as_stream(stream));
+#else
+        cudaStream_t st = as_stream(stream);
+        HostPipe& hp = host_pipe();
+        hp.ensure(1);
+        const int s = (int)(hp.ncalls++ & 1);
+        if (hp.slot[s].cap < bytes) {                                          // (re)allocation: drain everything that may still use the slot
+            CMBL_CUDA(cudaStreamSynchronize(hp.s_in)); CMBL_CUDA(cudaStreamSynchronize(hp.s_out)); CMBL_CUDA(cudaStreamSynchronize(st));
+            hp.slot_used[s] = false;
+        }
+        void* d = hp.slot[s].reserve(bytes);
+        if (hp.slot_used[s]) CMBL_CUDA(cudaStreamWaitEvent(hp.s_in, hp.slot_free[s], 0));         // the slot's previous result has left the device
+        CMBL_CUDA(cudaMemcpyAsync(d, in_host, bytes, cudaMemcpyHostToDevice, hp.s_in));
+        CMBL_CUDA(cudaEventRecord(hp.a_in[s], hp.s_in));
+        CMBL_CUDA(cudaStreamWaitEvent(st, hp.a_in[s], 0));
+        cmbl::flow_apply<T>(F, op, d, d, st);
+        CMBL_CUDA(cudaEventRecord(hp.a_done[s], st));
+        CMBL_CUDA(cudaStreamWaitEvent(hp.s_out, hp.a_done[s], 0));
+        CMBL_CUDA(cudaMemcpyAsync(out_host, d, bytes, cudaMemcpyDeviceToHost, hp.s_out));
+        CMBL_CUDA(cudaEventRecord(hp.slot_free[s], hp.s_out));
+        hp.slot_used[s] = true;
+#endif
+    });
+    CMBL_API_END
+}
+
+// waits until every cmbl_lenseflow_apply_host_async call of this host thread has delivered its out_host
+int cmbl_lenseflow_host_sync(void) {
+    CMBL_API_BEGIN
+#ifndef CMBL_EMU
+    HostPipe& hp = host_pipe();
+    if (hp.s_out) { CMBL_CUDA(cudaStreamSynchronize(hp.s_in)); CMBL_CUDA(cudaStreamSynchronize(hp.s_out)); }
+#endif
     CMBL_API_END
 }
 

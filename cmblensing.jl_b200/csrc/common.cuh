@@ -24,6 +24,7 @@
 #ifdef CMBL_EMU
 #define HD inline
 #define DEV inline
+#define DEV_NOINLINE inline
 typedef void* cmblStream_t;
 #define CMBL_FOR_THREADS(tid, NT) for (int tid = 0; tid < (NT); ++tid)
 #define CMBL_FOR_GROUP(tid, NG, goff) for (int tid = 0; tid < (NG); ++tid)
@@ -33,6 +34,7 @@ typedef void* cmblStream_t;
 #include <cuda_runtime.h>
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
+#define DEV_NOINLINE __device__ __noinline__
 typedef cudaStream_t cmblStream_t;
 #define CMBL_FOR_THREADS(tid, NT) for (int tid = threadIdx.x, _once = 1; _once; _once = 0)
 // a thread GROUP of a warp-specialised block: NG consecutive threads starting at thread `goff` (tid counts from 0 inside the group)

@@ -45,8 +45,6 @@ static int device_sms() {
     return v;
 #endif
 }
-// tile order of the fast column kernel: 0 = round-robin (default), 1 = contiguous tile range per block (see FastColBody)
-static int fast_cols_contig() { static const int v = [] { const char* e = getenv("CMBL_COL_CONTIG"); return e ? atoi(e) : 0; }(); return v; }
 // blocks that compute and publish each J[N] plane pair at launch start (0 = none: every block computes private copies — test knob)
 static int fast_cols_jn_red() { static const int v = [] { const char* e = getenv("CMBL_COL_JN_RED"); return e ? atoi(e) : 3; }(); return v; }
 static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
@@ -101,7 +99,7 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
     b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = nullptr;
     b.jn_pub = reinterpret_cast<T*>(F.jn.p);
-    b.jn_blk = reinterpret_cast<T*>(F.jnblk.reserve(sizeof(T) * (size_t)b.nblocks * private_lines * B::N)); b.contig = fast_cols_contig(); b.jn_red = fast_cols_jn_red();
+    b.jn_blk = reinterpret_cast<T*>(F.jnblk.reserve(sizeof(T) * (size_t)b.nblocks * private_lines * B::N)); b.jn_red = fast_cols_jn_red();
     if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
     b.jn_flag = reinterpret_cast<int*>(F.jnflag.p); b.epoch = ++F.jn_epoch;
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;

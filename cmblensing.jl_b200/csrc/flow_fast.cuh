@@ -285,7 +285,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
     const T* tw1; const T* tw2; const T* mult_d; const T* mult_sign; T cN;     // mult_sign, cN: the Nyquist line operator J (flow.cuh)
     const T* nline;                                  // N(y) per plane (row kernel of this stage)
     T* jn_pub; int* jn_flag; int epoch;              // launch-wide J[N] lines [plane][N]; jn_flag[plane] == epoch <=> this launch's line is published
-    T* jn_blk; int contig, jn_red;                   // per-block private J[N] line [block][N] (fallback); tile order knob; publishers per plane pair
+    T* jn_blk; int jn_red;                           // per-block private J[N] line [block][N] (fallback); publishers per plane pair
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
@@ -525,11 +525,18 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
         jn_pair(ws, ca, cb, jn_pub + (size_t)ca * N, cb >= 0 ? jn_pub + (size_t)cb * N : nullptr, w1, w2, goff, bar);
         CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) { flag_publish(jn_flag + ca, epoch); if (cb >= 0) flag_publish(jn_flag + cb, epoch); } }
     }
-    // the J[N] line of plane c: the published one, or a private copy computed from the same plane pair (identical bits) in `ws`
-    DEV const T* jn_resolve(int published, int c, int nC, T* ws, T* mine, Tw<R1>& w1, Tw<R2>& w2, int goff = 0, int bar = 0) const {
-        if (published) return jn_pub + (size_t)c * N;
+    // RARE path of the column kernel (the publishers of plane c's J[N] line are not resident): a private copy computed from the same plane
+    // pair (identical bits).  The work space is the tile buffer `ws` in which the next tile is landing: let it arrive, use the buffer, request
+    // the tile again.  Deliberately NOT inlined: its registers and its code stay out of the hot loop.
+    DEV_NOINLINE const T* jn_private(int c, int blk, T* ws, const T* next_src, int next_x0) const {
+        Tw<R1> w1; Tw<R2> w2;
+        CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
+        CMBL_SYNC();
+        T* const mine = jn_blk + (size_t)blk * N;
+        const int nC = ntiles / tiles_per_plane;
         const int pr = (c - cbase) / 2, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
-        jn_pair(ws, ca, cb, c == ca ? mine : nullptr, c == cb ? mine : nullptr, w1, w2, goff, bar);
+        jn_pair(ws, ca, cb, c == ca ? mine : nullptr, c == cb ? mine : nullptr, w1, w2);
+        if (next_src) { CMBL_FOR_THREADS(tid, NT) { issue_tile(next_src, next_x0, ws, tid); cp_async_commit(); } }
         return mine;
     }
 
@@ -545,7 +552,6 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
         // moment the launch works on a window of neighbouring column tiles (their 128/256-byte runs share DRAM pages and the window's
         // pages fit the TLB reach; contiguous per-block ranges spread the blocks over the whole 0.7 GB working set and were measured
         // 25 % slower) and the Q and U (I, Q, U) tiles of the same columns are in flight together and share the p maps.
-        //   contig != 0 (experiment knob): block b owns the contiguous tile range [b·ntiles/nblocks, (b+1)·ntiles/nblocks).
         // J[N] lines: NO block ever waits for another block.  At launch start a few blocks (jn_red per plane pair; blocks of the first
         // wave that own one tile less than the others) compute the lines of one plane pair each into the launch-wide array jn[plane][N]
         // and publish a per-plane flag — while their first tile is in flight.  Before a block's first epilogue on a plane it LOOKS at
@@ -553,16 +559,11 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
         // microseconds into the launch) -> it reads the shared line; not published (the producers are not resident: another stream
         // owns the SMs, MPS, ...) -> it computes a private copy of the same plane pair (identical bits) and goes on.  Correct and
         // deterministic under any residency.
-        T* const jmine = jn_blk + (size_t)blk * N;
-        const int nC = (ntiles / tiles_per_plane);                     // planes of this launch
         auto item_of = [&](int t) { return (t / Npol) / tiles_per_plane; };
         auto x0_of = [&](int t) { return ((t / Npol) % tiles_per_plane) * M; };
-        const int tstep = contig ? 1 : nblocks;
-        const int tend = contig ? (int)((long long)(blk + 1) * ntiles / nblocks) : ntiles;
-        int tile = contig ? (int)((long long)blk * ntiles / nblocks) : blk;
-        int cur = 0, cj = -1;
+        int tile = blk, cur = 0, cj = -1;
         const T* jline = nullptr;
-        if (tile < tend) {
+        if (tile < ntiles) {
             const int c = cbase + item_of(tile) * Npol + tile % Npol, x0 = x0_of(tile);
             CMBL_FOR_THREADS(tid, NT) {
                 issue_tile(u + (size_t)c * nmap, x0, sbase, tid);
@@ -570,23 +571,23 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
                 cp_async_commit();
             }
         }
-        jn_publish(blk, nC, sbase + TILE, w1, w2);                     // (publisher blocks only) first tile in flight
+        jn_publish(blk, ntiles / tiles_per_plane, sbase + TILE, w1, w2);          // (publisher blocks only) first tile in flight
         CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
-        for (; tile < tend; tile += tstep, cur ^= 1) {
+        for (; tile < ntiles; tile += nblocks, cur ^= 1) {
             T* const buf = sbase + cur * TILE;
             T* const nbuf = sbase + (cur ^ 1) * TILE;
-            const int c = cbase + item_of(tile) * Npol + tile % Npol, x0 = x0_of(tile), next = tile + tstep;
+            const int c = cbase + item_of(tile) * Npol + tile % Npol, x0 = x0_of(tile), next = tile + nblocks;
             const int cn = cbase + item_of(next) * Npol + next % Npol, x0n = x0_of(next);
             const T* const p1 = p_plane(pk, c, Npol, Nbphi, 0, nmap);
             const T* const p2 = p_plane(pk, c, Npol, Nbphi, 1, nmap);
             CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
             CMBL_SYNC();
-            if (next < tend) {                                         // the next tile lands while this one is transformed (DRAM is idle then)
+            if (next < ntiles) {                                       // the next tile lands while this one is transformed (DRAM is idle then)
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
-            if (ADJ && next < tend) {
+            if (ADJ && next < ntiles) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0n, pbuf, tid); cp_async_commit(); }
             }
             CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
@@ -597,22 +598,12 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
             CMBL_SYNC();
             int fl = 1;
             CMBL_FOR_THREADS(tid, NT) {
-                if (tid == 0 && c != cj) fl = (flag_look(jn_flag + c) == epoch);      // is this plane's J[N] line published?  (the answer rides on the barrier)
                 if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1);
+                if (tid == 0 && c != cj) fl = (flag_look(jn_flag + c) == epoch);      // is this plane's J[N] line published?  (the answer rides on the barrier)
             }
             fl = block_and(fl);
             if (c != cj) {
-                if (fl) jline = jn_pub + (size_t)c * N;
-                else {
-                    // RARE (the publishers are not resident: another stream owns the SMs, MPS, ...): compute a private copy of the line.
-                    // The work space is the other tile buffer: let the tile that is landing there arrive, use the buffer, request the tile again.
-                    CMBL_FOR_THREADS(tid, NT) { cp_async_wait_all(); }
-                    CMBL_SYNC();
-                    jline = jn_resolve(0, c, nC, nbuf, jmine, w1, w2);
-                    if (next < tend) {
-                        CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
-                    }
-                }
+                jline = fl ? jn_pub + (size_t)c * N : jn_private(c, blk, nbuf, next < ntiles ? u + (size_t)cn * nmap : nullptr, x0n);
                 cj = c;
             }
             CMBL_FOR_THREADS(tid, NT) {

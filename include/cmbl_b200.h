@@ -102,6 +102,12 @@ int cmbl_lenseflow_apply(cmbl_flow* flow, int op, const void* in, void* out, voi
  * of groups, default 3 = a quarter / half / quarter of the batch: the first and last group are the exposed transfers, the
  * middle one keeps the persistent stage kernels filled; 1 = copy-in / compute / copy-out back to back). */
 int cmbl_lenseflow_apply_host(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream);
+/* the same for a caller that streams many fields through one operator: returns once the work is queued; successive calls overlap (H2D of
+ * call i+1 and D2H of call i-1 run during the integration of call i: two staging slots, two copy streams), so a call costs
+ * max(integration, one-way transfer) instead of their sum.  in_host must stay unchanged, and out_host is valid only, after
+ * cmbl_lenseflow_host_sync() (which waits for every asynchronous call of the calling host thread). */
+int cmbl_lenseflow_apply_host_async(cmbl_flow* flow, int op, const void* in_host, void* out_host, void* stream);
+int cmbl_lenseflow_host_sync(void);
 /* pullback through Lϕ*f (op 0) or Lϕ\f (op 2): negδvelocityᴴ transpose flow (src/lenseflow.jl:176-214, src/flowops.jl:40-68).
  * f_out_map = the forward result (Map), delta = cotangent (Fourier). Outputs: dfield (Fourier, C planes), dphi (Fourier,
  * Nb_f planes: one per batch item, also when a single ϕ is shared by the batch — sum them for the gradient w.r.t. the

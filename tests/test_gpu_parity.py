@@ -490,6 +490,13 @@ def test_host_pipeline_matches_device_path(cuda_pkg, nb):
             lib.call("cmbl_lenseflow_apply_host", cache.handle, op, P(hin), P(hout), st)
             torch.cuda.synchronize()
             assert torch.equal(hout.to(DEV), dev_out)
+        # asynchronous variant: three calls in flight over two staging slots, results valid after cmbl_lenseflow_host_sync
+        houts = [torch.zeros(x.shape, dtype=x.dtype).pin_memory() for _ in range(3)]
+        for ho in houts:
+            lib.call("cmbl_lenseflow_apply_host_async", cache.handle, op, P(hin), P(ho), st)
+        lib.call("cmbl_lenseflow_host_sync")
+        for ho in houts:
+            assert torch.equal(ho.to(DEV), dev_out)
 
 
 def test_2048_fp32_roundtrip(cuda_pkg):
