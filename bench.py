@@ -119,6 +119,21 @@ class ClockSampler:
                 "source": "NVML poll (5 ms) inside the timed region"}
 
 
+def numa_interleave():
+    """Spread this process's future page allocations (the pinned host buffers of the e2e leg) over all NUMA nodes: at 8 ranks the host side
+    of the e2e path moves ~300 GB/s, more than one socket's DRAM delivers.  set_mempolicy(MPOL_INTERLEAVE); returns the node count or None."""
+    try:
+        nodes = [int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if len(nodes) < 2:
+            return len(nodes)
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2))      # SYS_set_mempolicy (x86-64), MPOL_INTERLEAVE
+        return len(nodes) if rc == 0 else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -338,6 +353,7 @@ def main():
                 clocks = fut.result()
 
     # ---- end-to-end: HOST buffers through the C ABI, copies inside the timed region ---------------------------------
+    numa = numa_interleave() if (world >= 4 and os.environ.get("CMBL_BENCH_NUMA", "interleave") == "interleave") else None
     hin = torch.empty(fmap.arr.shape, dtype=tT).pin_memory(); hin.copy_(fmap.arr)
     hout = torch.empty(fmap.arr.shape, dtype=tT).pin_memory()
 
@@ -546,11 +562,15 @@ def main():
                        "l2": "working set (4 state buffers 4x%.0f MB + p-cache %.1f GB) exceeds the 126 MB L2" % (nbytes / 1e6, 15 * NB * 2 * AB["pass_bytes"] / 1e9),
                        "map_applies_per_sec": world * NB * 1e3 / ms_step},
             "clocks": clocks,
-            "e2e": {"value": world * 1e3 / ms_e2e, "unit": "applies/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e,
-                    "api": "cmbl_lenseflow_apply_host (pinned host buffers, H2D + apply + D2H)",
+            "e2e": {"value": world * 1e3 / ms_e2e_stream, "unit": "applies/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e_stream,
+                    "api": "cmbl_lenseflow_apply_host_async + cmbl_lenseflow_host_sync (pinned host buffers; every step copies its own input H2D and its own result D2H; "
+                           "the copies of step i overlap the integrations of steps i-1 / i+1 through two staging slots and two copy streams)",
+                    "timer": "host wall clock around the K queued calls and the final cmbl_lenseflow_host_sync, bracketed by device synchronisation; max over ranks "
+                             "(the D2H tail runs on the library's copy stream, which CUDA events on the caller's stream do not see)",
+                    "synchronous": {"value": world * 1e3 / ms_e2e, "unit": "applies/s", "ms_per_step": ms_e2e,
+                                    "api": "cmbl_lenseflow_apply_host (returns when out_host is valid: H2D + apply + D2H of ONE call, item groups pipelined inside the call)"},
                     "copies_alone_ms_per_step": ms_copy, "device_apply_ms_per_step": ms_step,
-                    "streaming": {"value": world * 1e3 / ms_e2e_stream, "unit": "applies/s", "ms_per_step": ms_e2e_stream, "timer": "host wall clock around K queued calls + cmbl_lenseflow_host_sync (max over ranks)",
-                                  "api": "cmbl_lenseflow_apply_host_async: same per-step H2D and D2H bytes, overlapped with the neighbouring steps' integrations (two staging slots)"}},
+                    "host_memory_policy": (f"MPOL_INTERLEAVE over {numa} NUMA nodes (ranks >= 4)" if numa else "default (first touch)")},
             "gpu_launches": launches,
             "roofline": roofline,
             "roofline_apply": {"bound": "hbm", "achieved": apply_gbs, "peak": peak, "unit": "GB/s", "frac": apply_gbs / peak, "frac_of_8TBs_nominal": apply_gbs / 8000.0,

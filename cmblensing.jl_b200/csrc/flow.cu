@@ -47,6 +47,8 @@ static int device_sms() {
 }
 // blocks that compute and publish each J[N] plane pair at launch start (0 = none: every block computes private copies — test knob)
 static int fast_cols_jn_red() { static const int v = [] { const char* e = getenv("CMBL_COL_JN_RED"); return e ? atoi(e) : 3; }(); return v; }
+// bounded patience of a flag look: polls of ~0.15 us each (default ~15 us in total; 0 = look once)
+static int fast_cols_jn_polls() { static const int v = [] { const char* e = getenv("CMBL_COL_JN_POLLS"); return e ? atoi(e) : 100; }(); return v; }
 static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
     static const int v = [] { const char* e = getenv("CMBL_FLOW_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     return v > 0 ? std::min(full, v * device_sms()) : full;
@@ -94,12 +96,15 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     b.dx_out = dx_out; b.dy_out = dy_out;
     b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv; b.mult_sign = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
     b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / B::M; b.ntiles = nC * b.tiles_per_plane;
-    b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
+    // every block that can be resident; a launch with fewer tiles than that gets a few extra blocks that own no tile and only compute and
+    // publish the J[N] lines, so that no tile-owning block of a one-wave launch is delayed by them
+    b.jn_red = fast_cols_jn_red();
+    b.nblocks = std::min(b.ntiles + b.jn_red * ((nC + 1) / 2), fast_block_cap(persistent_blocks<B>(B::SMEM)));
     b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T), adj); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
     b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = nullptr;
     b.jn_pub = reinterpret_cast<T*>(F.jn.p);
-    b.jn_blk = reinterpret_cast<T*>(F.jnblk.reserve(sizeof(T) * (size_t)b.nblocks * private_lines * B::N)); b.jn_red = fast_cols_jn_red();
+    b.jn_blk = reinterpret_cast<T*>(F.jnblk.reserve(sizeof(T) * (size_t)b.nblocks * private_lines * B::N)); b.jn_polls = fast_cols_jn_polls();
     if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
     b.jn_flag = reinterpret_cast<int*>(F.jnflag.p); b.epoch = ++F.jn_epoch;
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;

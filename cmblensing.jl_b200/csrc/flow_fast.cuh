@@ -159,6 +159,20 @@ DEV int flag_look(const int* p) {
     return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 #endif
 }
+// patient look: poll the flag for a BOUNDED time (a few microseconds more than a publisher needs after launch) before giving up.  The bound
+// keeps the forward-progress guarantee — a block whose publishers are not resident stops waiting and computes its own copy — while a block
+// that merely arrives a microsecond early does not pay for a private copy.
+DEV int flag_look_patient(const int* p, int want, int polls) {
+#ifdef __CUDA_ARCH__
+    for (int i = 0; i < polls; ++i) {
+        if (flag_look(p) == want) return 1;
+        __nanosleep(128);
+    }
+    return flag_look(p) == want;
+#else
+    (void)polls; return flag_look(p) == want;
+#endif
+}
 // block-wide OR of a per-thread predicate (includes a barrier); the host emulator runs the threads of a block one after another in
 // one host thread, so the value set by "thread 0" is already what every thread sees
 DEV int block_or(int v) {
@@ -285,7 +299,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
     const T* tw1; const T* tw2; const T* mult_d; const T* mult_sign; T cN;     // mult_sign, cN: the Nyquist line operator J (flow.cuh)
     const T* nline;                                  // N(y) per plane (row kernel of this stage)
     T* jn_pub; int* jn_flag; int epoch;              // launch-wide J[N] lines [plane][N]; jn_flag[plane] == epoch <=> this launch's line is published
-    T* jn_blk; int jn_red;                           // per-block private J[N] line [block][N] (fallback); publishers per plane pair
+    T* jn_blk; int jn_red, jn_polls;                 // per-block private J[N] line [block][N] (fallback); publishers per plane pair; bounded polls of a flag
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
@@ -517,10 +531,15 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
 
     // publisher blocks: compute the lines of one plane pair into jn_pub and raise the flags (the block's first tile is in flight)
     DEV void jn_publish(int blk, int nC, T* ws, Tw<R1>& w1, Tw<R2>& w2, int goff = 0, int bar = 0) const {
-        const int npairs = (nC + 1) / 2, np = jn_red * npairs;
-        int b0 = ntiles % nblocks;                                     // round-robin: blocks b0.. own one tile less than blocks 0..b0-1
-        if (b0 + np > nblocks) b0 = 0;
-        if (blk < b0 || blk >= b0 + np || blk >= nblocks) return;
+        const int npairs = (nC + 1) / 2;
+        int b0, np;
+        if (nblocks > ntiles) { b0 = ntiles; np = nblocks - ntiles; }  // small launch: the grid carries extra blocks that own no tile and only publish
+        else {
+            np = jn_red * npairs;
+            b0 = ntiles % nblocks;                                     // round-robin: blocks b0.. own one tile less than blocks 0..b0-1
+            if (b0 + np > nblocks) b0 = 0;
+        }
+        if (blk < b0 || blk >= b0 + np) return;
         const int pr = (blk - b0) % npairs, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
         jn_pair(ws, ca, cb, jn_pub + (size_t)ca * N, cb >= 0 ? jn_pub + (size_t)cb * N : nullptr, w1, w2, goff, bar);
         CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) { flag_publish(jn_flag + ca, epoch); if (cb >= 0) flag_publish(jn_flag + cb, epoch); } }
@@ -599,7 +618,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
             int fl = 1;
             CMBL_FOR_THREADS(tid, NT) {
                 if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1);
-                if (tid == 0 && c != cj) fl = (flag_look(jn_flag + c) == epoch);      // is this plane's J[N] line published?  (the answer rides on the barrier)
+                if (tid == 0 && c != cj) fl = flag_look_patient(jn_flag + c, epoch, jn_polls);   // is this plane's J[N] line published?  (the answer rides on the barrier)
             }
             fl = block_and(fl);
             if (c != cj) {
