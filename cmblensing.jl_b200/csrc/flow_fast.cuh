@@ -152,6 +152,17 @@ DEV void flag_publish(int* p, int v) {
     __atomic_store_n(p, v, __ATOMIC_RELEASE);
 #endif
 }
+// two flags behind ONE release fence (fence + relaxed stores is a release sequence; each st.release would pay its own MEMBAR)
+DEV void flag_publish2(int* p, int* q, int v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    if (q) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(q), "r"(v) : "memory");
+#else
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+    if (q) __atomic_store_n(q, v, __ATOMIC_RELEASE);
+#endif
+}
 DEV int flag_look(const int* p) {
 #ifdef __CUDA_ARCH__
     int got; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p) : "memory"); return got;
@@ -164,8 +175,11 @@ DEV int flag_look(const int* p) {
 // that merely arrives a microsecond early does not pay for a private copy.
 DEV int flag_look_patient(const int* p, int want, int polls) {
 #ifdef __CUDA_ARCH__
+    // polls are relaxed loads (served by L2, no side effect on this SM's L1); ONE acquire load — whose L1 invalidation is what makes the
+    // published line visible to the plain loads that follow — once the flag has been seen or the patience is used up
     for (int i = 0; i < polls; ++i) {
-        if (flag_look(p) == want) return 1;
+        int got; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p) : "memory");
+        if (got == want) break;
         __nanosleep(128);
     }
     return flag_look(p) == want;
@@ -542,7 +556,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
         if (blk < b0 || blk >= b0 + np) return;
         const int pr = (blk - b0) % npairs, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
         jn_pair(ws, ca, cb, jn_pub + (size_t)ca * N, cb >= 0 ? jn_pub + (size_t)cb * N : nullptr, w1, w2, goff, bar);
-        CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) { flag_publish(jn_flag + ca, epoch); if (cb >= 0) flag_publish(jn_flag + cb, epoch); } }
+        CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) flag_publish2(jn_flag + ca, cb >= 0 ? jn_flag + cb : nullptr, epoch); }
     }
     // RARE path of the column kernel (the publishers of plane c's J[N] line are not resident): a private copy computed from the same plane
     // pair (identical bits).  The work space is the tile buffer `ws` in which the next tile is landing: let it arrive, use the buffer, request

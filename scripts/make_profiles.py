@@ -1,0 +1,33 @@
+"""Turns the ncu captures of a GPU pass (gpurun_out/r02_ncu_*.ncu-rep + gpurun_out/binary_sha16.txt) into the tracked summaries under
+profiles/: one text summary per capture (key metrics per launch + stall reasons + hottest SASS locations) and profiles/traffic.json
+(DRAM bytes per launch of the two stage kernels, keyed by dtype, with the sha256 of the libcmbl_b200.so the capture was taken from — bench.py
+reports `roofline.traffic` only when that hash matches the library it has loaded).
+usage: python scripts/make_profiles.py [tag]"""
+import csv, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+CMD = {"flow_f64": "ncu --set full --clock-control none --import-source on -s 38 -c 2  python scripts/ncu_target.py f64 fwd   (Nside=1024 QU batch 8; one flow_rows + one flow_cols launch of the first RK step)",
+       "flow_f32": "ncu --set full --clock-control none --import-source on -s 38 -c 2  python scripts/ncu_target.py f32 fwd",
+       "adj_f64": "ncu --set full --clock-control none --import-source on -s 12 -c 2  python scripts/ncu_target.py f64 adj   (adjoint stage kernels)",
+       "fft_f64": "ncu --set full --clock-control none --import-source on -s 2 -c 3  python scripts/ncu_target.py f64 adj   (general 2-D transform kernels of the irfft2 that opens L'*f)"}
+sha = open(os.path.join(G, "binary_sha16.txt")).read().strip() if os.path.exists(os.path.join(G, "binary_sha16.txt")) else None
+traffic = {"binary_sha16": sha, "source": f"profiles/{tag}_ncu_flow_{{f64,f32}}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
+for key, cmd in CMD.items():
+    rep = os.path.join(G, f"{tag}_ncu_{key}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    s1 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    s2 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_hot.py"), rep, "12"], capture_output=True, text=True).stdout
+    open(os.path.join(P, f"{tag}_ncu_{key}.txt"), "w").write(cmd + f"\nlibcmbl_b200.so sha256[:16] = {sha}\n" + s1 + s2)
+    rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+    hdr = rows[0]; kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    for r in rows[2:]:
+        nm = "flow_rows" if "RowBody" in r[kn] and "C2C" not in r[kn] else ("flow_cols" if "ColBody" in r[kn] and "R2C" not in r[kn] and "C2R" not in r[kn] else None)
+        if nm and key.startswith("flow_"):
+            b = float(r[rd]) * unit[rows[1][rd]] + float(r[wr]) * unit[rows[1][wr]]
+            traffic.setdefault(key[5:], {})[nm] = b
+    print("wrote", f"profiles/{tag}_ncu_{key}.txt")
+json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+print(json.dumps(traffic))
