@@ -291,6 +291,9 @@ template <class T, bool TO_RG> struct LayoutBody {
 #ifndef CMBL_COL_UNR
 #define CMBL_COL_UNR 2
 #endif
+#ifndef CMBL_COL_UNR_ADJ
+#define CMBL_COL_UNR_ADJ (sizeof(T) == 8 ? 4 : CMBL_COL_UNR)   // adjoint kernel (3 operands per unit, 2 blocks/SM): 4 units in flight in fp64
+#endif                                                          // (L'*f 7.81 -> 7.71 ms; neutral in fp32; profiles/r02_col_epilogue_unroll.log)
 // DMODE (forward kernel only): the epilogue also stores the two derivative maps it has in registers — ∂ₓu = tmp ± jn and ∂ᵧu — for
 // the δϕ integrand of the transpose-δ flow (flow_grad.cu); a separate instantiation, so the plain kernel's register budget is untouched.
 template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
@@ -450,7 +453,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
     }
     template <int KIND> DEV void epilogue(const T* buf, int tid, size_t pbase, int x0, const T* jc, const T* p1, const T* p2) const {
         constexpr bool YB = KIND != 2, AI = KIND != 0, UO = KIND != 2;
-        constexpr int ITER = M * CH / 2 / NT, UNR = (ITER % CMBL_COL_UNR == 0) ? CMBL_COL_UNR : 2;
+        constexpr int ITER = M * CH / 2 / NT, UNRW = ADJ ? CMBL_COL_UNR_ADJ : CMBL_COL_UNR, UNR = (ITER % UNRW == 0) ? UNRW : 2;
         static_assert(ITER % UNR == 0, "epilogue unroll");
         const T* tc = tmp + pbase;
         const T* yb = YB ? ybase + pbase : nullptr;
