@@ -14,6 +14,8 @@ cap r02_ncu_flow_f64 38 2 python scripts/ncu_target.py f64 fwd
 cap r02_ncu_flow_f32 38 2 python scripts/ncu_target.py f32 fwd
 cap r02_ncu_adj_f64 12 2 python scripts/ncu_target.py f64 adj
 cap r02_ncu_fft_f64 2 3 python scripts/ncu_target.py f64 adj
+python scripts/make_profiles.py r02 gpurun_out/profiles_out > gpurun_out/make_profiles.log 2>&1; tail -2 gpurun_out/make_profiles.log
+rm -f gpurun_out/r02_ncu_flow_f32.ncu-rep gpurun_out/r02_ncu_adj_f64.ncu-rep gpurun_out/r02_ncu_fft_f64.ncu-rep      # keep one .ncu-rep (64 MiB limit on what travels back)
 python - <<'PY'
 import json
 for n in ("ref", "f64", "f32"):

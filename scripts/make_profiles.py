@@ -2,11 +2,12 @@
 profiles/: one text summary per capture (key metrics per launch + stall reasons + hottest SASS locations) and profiles/traffic.json
 (DRAM bytes per launch of the two stage kernels, keyed by dtype, with the sha256 of the libcmbl_b200.so the capture was taken from — bench.py
 reports `roofline.traffic` only when that hash matches the library it has loaded).
-usage: python scripts/make_profiles.py [tag]"""
+usage: python scripts/make_profiles.py [tag] [outdir]   (run on the GPU box right after the captures — the .ncu-rep files are too big to travel)"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
-G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+G = os.path.join(ROOT, "gpurun_out"); P = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")     # (on the GPU box: write next to the captures)
+os.makedirs(P, exist_ok=True)
 CMD = {"flow_f64": "ncu --set full --clock-control none --import-source on -s 38 -c 2  python scripts/ncu_target.py f64 fwd   (Nside=1024 QU batch 8; one flow_rows + one flow_cols launch of the first RK step)",
        "flow_f32": "ncu --set full --clock-control none --import-source on -s 38 -c 2  python scripts/ncu_target.py f32 fwd",
        "adj_f64": "ncu --set full --clock-control none --import-source on -s 12 -c 2  python scripts/ncu_target.py f64 adj   (adjoint stage kernels)",
