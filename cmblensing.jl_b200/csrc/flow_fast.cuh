@@ -157,10 +157,10 @@ DEV void flag_publish2(int* p, int* q, int v) {
 #ifdef __CUDA_ARCH__
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-    if (q) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(q), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(q), "r"(v) : "memory");       // q == p when there is only one flag
 #else
     __atomic_store_n(p, v, __ATOMIC_RELEASE);
-    if (q) __atomic_store_n(q, v, __ATOMIC_RELEASE);
+    __atomic_store_n(q, v, __ATOMIC_RELEASE);
 #endif
 }
 DEV int flag_look(const int* p) {
@@ -559,7 +559,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
         if (blk < b0 || blk >= b0 + np) return;
         const int pr = (blk - b0) % npairs, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
         jn_pair(ws, ca, cb, jn_pub + (size_t)ca * N, cb >= 0 ? jn_pub + (size_t)cb * N : nullptr, w1, w2, goff, bar);
-        CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) flag_publish2(jn_flag + ca, cb >= 0 ? jn_flag + cb : nullptr, epoch); }
+        CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) flag_publish2(jn_flag + ca, jn_flag + (cb >= 0 ? cb : ca), epoch); }
     }
     // RARE path of the column kernel (the publishers of plane c's J[N] line are not resident): a private copy computed from the same plane
     // pair (identical bits).  The work space is the tile buffer `ws` in which the next tile is landing: let it arrive, use the buffer, request
