@@ -170,14 +170,17 @@ def reference_arm(args, rank, world):
             t_be[be] = float("inf")
     best = min(t_be, key=t_be.get)
     O.set_fft_backend(best); O.set_workers(cores)
-    est_item = t_be[best] * NSTEPS_RK                               # one item, n = 7
+    # the warm-up step is timed: if K steps of the whole batch would not end within ~4 minutes, halve the number of items and say so
     W = 1
     nit = NB
-    while nit > 1 and est_item * nit * (args.steps + W) > 240.0:    # keep the whole run within ~4 minutes
-        nit //= 2
-    L = O.precompute(proj, phi[:nit], NSTEPS_RK, phi_is_fourier=True)
-    for _ in range(W):
+    while True:
+        L = O.precompute(proj, phi[:nit], NSTEPS_RK, phi_is_fourier=True)
+        t0 = time.perf_counter()
         O.lenseflow_apply(L, O.OP_L, f[:nit])
+        t_w = time.perf_counter() - t0
+        if nit == 1 or t_w * args.steps <= 240.0:
+            break
+        nit //= 2
     t0 = time.perf_counter()
     for _ in range(args.steps):
         O.lenseflow_apply(L, O.OP_L, f[:nit])

@@ -151,13 +151,48 @@ class Field:
             o = torch.as_tensor(o, device=self.arr.device, dtype=self.proj.T).reshape(-1, 1, 1, 1)
         return self._like(fn(self.arr, o))
 
-    def __add__(self, o): return self._bin(o, torch.add)
-    def __sub__(self, o): return self._bin(o, torch.sub)
-    def __mul__(self, o): return self._bin(o, torch.mul)
+    def _axpby(self, a, y=None, b=1.0):
+        """out = a .* self + b .* y with per-batch scalars (cmbl_field_axpby): the linear combinations of the callers (leap-frog, RK and
+        line-search updates, `x + α*Δ`) run on the library's kernel, not on eager tensor ops.  None if the case is not covered."""
+        if self.Nbatch > 64:
+            return None
+        av = np.atleast_1d(np.asarray(a, dtype=np.float64)).ravel(); bv = np.atleast_1d(np.asarray(b, dtype=np.float64)).ravel()
+        if y is not None:
+            self._check(y)
+            if y.basis != self.basis:
+                y = convert(y, self.basis)
+            if y.arr.shape != self.arr.shape:
+                return None                                         # broadcasting batches: generic path
+        if av.size not in (1, self.Nbatch) or bv.size not in (1, self.Nbatch):
+            return None
+        out = torch.empty_like(self.arr)
+        A = (c_double * av.size)(*av); B = (c_double * bv.size)(*bv)
+        self.proj.lib.call("cmbl_field_axpby", self.proj.handle, FOURIER if self.is_fourier else MAP, A, int(av.size), _ptr(self.arr), B, int(bv.size),
+                           _ptr(y.arr) if y is not None else c_void_p(0), _ptr(out), self.Npol, self.Nbatch, _stream(out))
+        return self._like(out)
+
+    @staticmethod
+    def _is_scalars(o):
+        return isinstance(o, (int, float, np.floating, np.integer)) or (isinstance(o, (list, tuple, np.ndarray)) and np.ndim(o) <= 1)
+
+    def __add__(self, o):
+        r = self._axpby(1.0, o, 1.0) if isinstance(o, Field) else None
+        return r if r is not None else self._bin(o, torch.add)
+
+    def __sub__(self, o):
+        r = self._axpby(1.0, o, -1.0) if isinstance(o, Field) else None
+        return r if r is not None else self._bin(o, torch.sub)
+
+    def __mul__(self, o):
+        r = self._axpby(o) if self._is_scalars(o) else None
+        return r if r is not None else self._bin(o, torch.mul)
+
     def __truediv__(self, o): return self._bin(o, torch.div)
     __radd__ = __add__
     __rmul__ = __mul__
-    def __neg__(self): return self._like(-self.arr)
+    def __neg__(self):
+        r = self._axpby(-1.0)
+        return r if r is not None else self._like(-self.arr)
     def __rsub__(self, o): return (-self) + o
     def zero(self): return self._like(torch.zeros_like(self.arr))
     def copy(self): return self._like(self.arr.clone())

@@ -40,6 +40,7 @@ SIGNATURES = {
     "cmbl_rfft2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cmbl_irfft2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cmbl_diag_mul": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "cmbl_field_axpby": (c_int, [c_void_p, c_int, POINTER(c_double), c_int, c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cmbl_qu_eb": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cmbl_blockdiag_ieb": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cmbl_dot": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, POINTER(c_double), c_void_p]),

@@ -17,6 +17,24 @@ int cmbl_diag_mul(cmbl_plan* plan, int basis, const void* diag, int Cd, const vo
     CMBL_API_END
 }
 
+int cmbl_field_axpby(cmbl_plan* plan, int basis, const double* a_host, int na, const void* x, const double* b_host, int nb, const void* y_or_null,
+                     void* out, int Npol, int Nb, void* stream) {
+    CMBL_API_BEGIN
+    CMBL_REQUIRE(plan && plan->p && a_host && x && out, "NULL argument");
+    CMBL_REQUIRE(basis == CMBL_MAP || basis == CMBL_FOURIER, "basis must be Map or Fourier");
+    CMBL_REQUIRE(Nb >= 1 && Nb <= cmbl::AXPBY_MAX_NB && Npol >= 1, "cmbl_field_axpby handles 1..64 batch items");
+    CMBL_REQUIRE((na == 1 || na == Nb) && (!y_or_null || (b_host && (nb == 1 || nb == Nb))), "scalars must have length 1 or Nb (batch sizes must broadcast)");
+    CMBL_DISPATCH(plan->p.get(), {
+        cmbl::AxpbyBody<T> k;
+        k.per_batch = (basis == CMBL_MAP ? P.map_elems() : 2 * P.four_elems()) * (size_t)Npol;
+        k.total = k.per_batch * (size_t)Nb; k.x = (const T*)x; k.y = (const T*)y_or_null; k.out = (T*)out; k.na = na; k.nb = y_or_null ? nb : 1;
+        for (int i = 0; i < na; ++i) k.a[i] = a_host[i];
+        if (y_or_null) for (int i = 0; i < nb; ++i) k.b[i] = b_host[i];
+        cmbl::launch(k, (int)((k.total + k.NT - 1) / k.NT), 0, as_stream(stream));
+    });
+    CMBL_API_END
+}
+
 int cmbl_qu_eb(cmbl_plan* plan, int dir, const void* in, void* out, int Nb, int pair_stride_planes, int first_plane, void* stream) {
     CMBL_API_BEGIN
     CMBL_REQUIRE(plan && plan->p && in && out, "NULL argument");

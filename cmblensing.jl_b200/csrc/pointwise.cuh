@@ -43,6 +43,30 @@ template <class T> struct ClTo2DBody {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// out = a ⊙ x + b ⊙ y on fields, a and b per-batch scalars (BatchedReal broadcasts of the reference: `@. x + α*Δ`, the RK / leap-frog
+// axpys of the callers, src/batching.jl:9-45).  Arrays are addressed as reals (a complex field is 2·n reals); y may be NULL (b ignored).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AXPBY_MAX_NB = 64;
+template <class T> struct AxpbyBody {
+    static constexpr int NT = 256;
+    static const char* name() { return "field_axpby"; }
+    size_t per_batch, total; const T* x; const T* y; T* out; int na, nb;
+    double a[AXPBY_MAX_NB], b[AXPBY_MAX_NB];
+    DEV void operator()(int blk, unsigned char*) const {
+        CMBL_FOR_THREADS(tid, NT) {
+            const size_t e = (size_t)blk * NT + tid;
+            if (e < total) {
+                const size_t bi = e / per_batch;
+                const T aa = (T)a[na == 1 ? 0 : bi];
+                T v = aa * x[e];
+                if (y) v += (T)b[nb == 1 ? 0 : bi] * y[e];
+                out[e] = v;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // DiagOp * f , DiagOp \ f
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, bool CPLX> struct DiagMulBody {

@@ -75,6 +75,11 @@ int cmbl_irfft2(cmbl_plan* plan, const void* four, void* map, int C, void* strea
  * basis selects the element type of in/out (Map: real, Fourier: complex); diag is REAL with Cd planes, Cd == C or
  * Cd == Npol_d (broadcast over the batch: plane c uses diag plane c % Cd). in may alias out. */
 int cmbl_diag_mul(cmbl_plan* plan, int basis, const void* diag, int Cd, const void* in, void* out, int C, int ldiv, void* stream);
+/* Field broadcasts with per-batch scalars (BatchedReal, src/batching.jl:9-45): out = a .* x .+ b .* y, e.g. `x + α*Δ`, the leap-frog and
+ * line-search updates of the callers.  a_host[na], b_host[nb]: HOST doubles, length 1 or Nb; y may be NULL (out = a .* x).  x, y, out:
+ * fields of Npol*Nb planes in `basis` (out may alias x or y).  Nb <= 64. */
+int cmbl_field_axpby(cmbl_plan* plan, int basis, const double* a_host, int na, const void* x, const double* b_host, int nb, const void* y_or_null,
+                     void* out, int Npol, int Nb, void* stream);
 /* QU<->EB rotation in Fourier space (src/proj_lambert.jl:253-271). dir 0: EB->QU, 1: QU->EB.  The two planes of each of
  * the Nb pairs are consecutive; pair_stride_planes = Npol of the array (2 for QU, 3 for IQU with first_plane = 1). */
 int cmbl_qu_eb(cmbl_plan* plan, int dir, const void* in, void* out, int Nb, int pair_stride_planes, int first_plane, void* stream);
