@@ -182,7 +182,9 @@ template <class Body> __global__ void __launch_bounds__(Body::NT, MinBlocks<Body
 }
 #endif
 
-template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStream_t st) {
+// cluster > 1: the blocks of the grid are launched as thread-block clusters of that many consecutive blocks (co-scheduled by the hardware,
+// so a cluster barrier between them can never wait for a block that is not resident)
+template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStream_t st, int cluster = 1) {
     if (grid <= 0) return;
     ++g_launch_count;
 #ifdef CMBL_EMU
@@ -207,7 +209,15 @@ template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStre
         configured = true;
     }
     if (g_profiling) prof_before(Body::name(), st);
-    if (UsesPdl<Body>::value && pdl_enabled() && !g_profiling) {
+    if (cluster > 1) {
+        CMBL_REQUIRE(grid % cluster == 0, "grid must be a multiple of the cluster size");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Body::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CMBL_CUDA(cudaLaunchKernelEx(&cfg, kern<Body>, b));
+    } else if (UsesPdl<Body>::value && pdl_enabled() && !g_profiling) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Body::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];
@@ -238,6 +248,34 @@ template <class Body> int persistent_blocks(size_t smem) {
         cached = per_sm * sms;
     }
     return cached;
+#endif
+}
+
+// blocks of a persistent kernel launched in clusters of `cluster` blocks that can be resident at once
+template <class Body> int persistent_blocks_clustered(size_t smem, int cluster) {
+#ifdef CMBL_EMU
+    const int n = persistent_blocks<Body>(smem); return n - n % cluster;
+#else
+    static thread_local int cached = 0, cached_for = 0;
+    if (!cached || cached_for != cluster) {
+        CMBL_CUDA(cudaFuncSetAttribute(kern<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(cluster * 1024)); cfg.blockDim = dim3((unsigned)Body::NT); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        CMBL_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, kern<Body>, &cfg));
+        CMBL_REQUIRE(nclusters >= 1, "persistent kernel does not fit on the device in clusters");
+        cached = nclusters * cluster; cached_for = cluster;
+    }
+    return cached;
+#endif
+}
+// barrier over the blocks of this block's cluster (a no-op for an unclustered launch: the implicit cluster is the block itself)
+DEV void cluster_sync() {
+#ifdef __CUDA_ARCH__
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 #endif
 }
 

@@ -49,6 +49,10 @@ static int device_sms() {
 static int fast_cols_jn_red() { static const int v = [] { const char* e = getenv("CMBL_COL_JN_RED"); return e ? atoi(e) : 3; }(); return v; }
 // bounded patience of a flag look: polls of ~0.15 us each (default ~15 us in total; 0 = look once)
 static int fast_cols_jn_polls() { static const int v = [] { const char* e = getenv("CMBL_COL_JN_POLLS"); return e ? atoi(e) : 100; }(); return v; }
+// opt-in experiment (CMBL_COL_PAIR=1): the Q and U tile of the same columns run as a 2-block cluster whose epilogues start together (cluster
+// barrier), hoping that the p maps both read come from DRAM once.  Measured (profiles/r02_col_cluster_pair.log): DRAM reads unchanged
+// (683 vs 679 MB per launch) and +4 % time, so it is off by default.
+static int fast_cols_pair() { static const int v = [] { const char* e = getenv("CMBL_COL_PAIR"); return e ? atoi(e) : 0; }(); return v; }
 static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
     static const int v = [] { const char* e = getenv("CMBL_FLOW_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     return v > 0 ? std::min(full, v * device_sms()) : full;
@@ -99,7 +103,11 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     // every block that can be resident; a launch with fewer tiles than that gets a few extra blocks that own no tile and only compute and
     // publish the J[N] lines, so that no tile-owning block of a one-wave launch is delayed by them
     b.jn_red = fast_cols_jn_red();
-    b.nblocks = std::min(b.ntiles + b.jn_red * ((nC + 1) / 2), fast_block_cap(persistent_blocks<B>(B::SMEM)));
+    // (experiment knob) forward kernel on QU fields: clusters of two blocks (Q tile, U tile of the same columns) with aligned epilogues
+    const int cluster = (!adj && F.Npol == 2 && fast_cols_pair() && b.ntiles >= 4) ? 2 : 1;
+    const int cap = cluster == 2 ? fast_block_cap(persistent_blocks_clustered<B>(B::SMEM, 2)) & ~1 : fast_block_cap(persistent_blocks<B>(B::SMEM));
+    b.nblocks = std::min(b.ntiles + b.jn_red * ((nC + 1) / 2), cap);
+    if (cluster == 2) { b.nblocks &= ~1; b.csync = 1; }
     b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.pf = fast_pf(sizeof(T), adj); b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.wgt = wgt;
     b.nline = reinterpret_cast<T*>(F.nline.p); b.jn = nullptr;
@@ -108,7 +116,7 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
     b.jn_flag = reinterpret_cast<int*>(F.jnflag.p); b.epoch = ++F.jn_epoch;
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
-    launch(b, b.nblocks, B::SMEM, st);
+    launch(b, b.nblocks, B::SMEM, st, cluster);
 }
 template <class T, int LOGN, bool ADJ>
 static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb, cmblStream_t st,

@@ -317,6 +317,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
     const T* nline;                                  // N(y) per plane (row kernel of this stage)
     T* jn_pub; int* jn_flag; int epoch;              // launch-wide J[N] lines [plane][N]; jn_flag[plane] == epoch <=> this launch's line is published
     T* jn_blk; int jn_red, jn_polls;                 // per-block private J[N] line [block][N] (fallback); publishers per plane pair; bounded polls of a flag
+    int csync = 0;                                   // launched in clusters of 2 blocks that synchronise before every epilogue
     int Nx, G, lgGV, tiles_per_plane, ntiles, nblocks, Npol, Nbphi, cbase, pf;     // G rows per row group, 2^lgGV = G / V
     int sms; unsigned stagger_ns;
     const T* u; const T* pk; const T* tmp; const T* jn; T* macc; T wgt;
@@ -642,6 +643,9 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
                 jline = fl ? jn_pub + (size_t)c * N : jn_private(c, blk, nbuf, next < ntiles ? u + (size_t)cn * nmap : nullptr, x0n);
                 cj = c;
             }
+            // (opt-in experiment, CMBL_COL_PAIR=1) blocks 2i and 2i+1 form a cluster and hold the Q and the U tile of the same columns; they
+            // start their epilogues together.  A cluster barrier cannot deadlock: the hardware co-schedules the blocks of a cluster.
+            if (csync) cluster_sync();
             CMBL_FOR_THREADS(tid, NT) {
                 if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
                 else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
