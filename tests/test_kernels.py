@@ -150,6 +150,27 @@ def test_precompute_p_cache(pkg, be, Ny, Nx):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_field_broadcasts(pkg, be, dtype):
+    """Field arithmetic with per-batch scalars (BatchedReal broadcasts, src/batching.jl:9-45) on cmbl_field_axpby: x ± y, x·α with α a scalar or
+    one value per batch item, −x, in the Map and the Fourier basis; mismatched batch sizes and metadata are refused like the reference does."""
+    pr = make_problem(pkg, 32, 16, "P", dtype, nb=3, lib=be.lib, device=be.device)
+    npT, _ = T_of(dtype)
+    f = pr["f"]; m = pkg.QUMap(f)
+    rng = np.random.default_rng(4)
+    g = pr["F"]((rng.standard_normal(f.arr.shape) + 1j * rng.standard_normal(f.arr.shape)).astype(pr["oproj"].cT), "EBFourier")
+    fa, ga, ma = f.cpu_numpy(), g.cpu_numpy(), m.cpu_numpy()
+    α = np.array([0.5, -2.0, 3.25])
+    tol = 1e-15 if dtype == "f64" else 1e-6
+    assert relerr((f + g).cpu_numpy(), fa + ga) < tol and relerr((f - g).cpu_numpy(), fa - ga) < tol
+    assert relerr((f * 1.5).cpu_numpy(), fa * npT(1.5)) < tol and relerr((-m).cpu_numpy(), -ma) < tol
+    assert relerr((m * α).cpu_numpy(), ma * α.astype(npT)[:, None, None, None]) < tol
+    assert relerr((f + g * α).cpu_numpy(), fa + ga * α.astype(npT)[:, None, None, None]) < tol
+    assert relerr((m + pkg.QUMap(g)).cpu_numpy(), ma + pkg.QUMap(g).cpu_numpy()) < tol          # converted to the left operand's basis
+    with pytest.raises(Exception):
+        m * np.array([1.0, 2.0])                                                                 # batch 3 vs 2 cannot broadcast
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
 def test_get_max_lensing_step(pkg, be, dtype):
     """get_max_lensing_step(ϕ, η) (src/lenseflow.jl:242-256) against the oracle, per batch item and as the reference's single minimum;
     the defining property: det(𝕀 + ∇∇(ϕ + α η)) keeps its sign for α < αmax and has changed it somewhere just above αmax."""
