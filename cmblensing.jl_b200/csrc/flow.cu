@@ -70,10 +70,10 @@ template <class T, int LOGN, bool ADJ>
 static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cmblStream_t st) {
     PlanT<T>& P = *F.P;
     static const bool use_tma = [] { const char* e = getenv("CMBL_ROW_TMA"); return !e || atoi(e) != 0; }();
-    if (use_tma) {
+    if (use_tma || LOGN > 10) {
         typedef TmaRowBody<T, LOGN, ADJ> B;
         B b;
-        b.fx = P.ax.fft; b.mult = P.ax.mult_deriv;
+        b.fx = P.ax.fft; b.mult = P.ax.fmult_deriv;
         b.Ny = P.Ny; b.tiles_per_plane = P.Ny / B::ROWS; b.ntiles = nC * b.tiles_per_plane;
         b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
         b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
@@ -82,15 +82,17 @@ static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cm
         launch(b, b.nblocks, B::SMEM, st);
         return;
     }
+    if constexpr (LOGN <= 10) {
     typedef FastRowBody<T, LOGN, ADJ> B;
     B b;
-    b.fx = P.ax.fft; b.mult = P.ax.mult_deriv;
+    b.fx = P.ax.fft; b.mult = P.ax.fmult_deriv;
     b.Ny = P.Ny; b.tiles_per_plane = P.Ny / B::ROWS; b.ntiles = nC * b.tiles_per_plane;
     b.nblocks = std::min(b.ntiles, fast_block_cap(persistent_blocks<B>(B::SMEM)));
     b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0; b.sms = device_sms(); b.stagger_ns = fast_stagger_ns();
     b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.nline = reinterpret_cast<T*>(F.nline.p);
     b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
     launch(b, b.nblocks, B::SMEM, st);
+    }
 }
 template <class T, class B>
 static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb,
@@ -98,7 +100,7 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     PlanT<T>& P = *F.P;
     B b;
     b.dx_out = dx_out; b.dy_out = dy_out;
-    b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.mult_deriv; b.mult_sign = P.ay.mult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
+    b.tw1 = P.ay.ftw1; b.tw2 = P.ay.ftw2; b.mult_d = P.ay.fmult_deriv; b.mult_sign = P.ay.fmult_sign; b.cN = P.ax.ell_nyq / (T)P.Nx;
     b.Nx = P.Nx; b.G = flow_rg_rows(P); b.lgGV = ilog2(b.G / B::V); b.tiles_per_plane = P.Nx / B::M; b.ntiles = nC * b.tiles_per_plane;
     // every block that can be resident; a launch with fewer tiles than that gets a few extra blocks that own no tile and only compute and
     // publish the J[N] lines, so that no tile-owning block of a one-wave launch is delayed by them
@@ -128,19 +130,19 @@ static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, co
 }
 template <class T> static bool fast_rows_ok(const PlanT<T>& P) {
     if (!fast_enabled() || !fast_len_ok(P.Nx) || !P.ax.ftw1) return false;
-    const int rows = (FAST_TILE_BYTES / (P.Nx * 16)) * (16 / (int)sizeof(T));
-    return P.Ny % rows == 0 && Tile<T, false>::bytes(P.Ny, 1, P.ay.fft.sk) <= (size_t)FAST_TILE_BYTES;
+    const int rows = (fast_tile_bytes(P.Nx) / (P.Nx * 16)) * (16 / (int)sizeof(T));
+    return P.Ny % rows == 0;
 }
 template <class T> static bool fast_cols_ok(const PlanT<T>& P) {
     if (!fast_enabled() || !fast_len_ok(P.Ny) || !P.ay.ftw1) return false;
-    const int cols = FAST_TILE_BYTES / (int)sizeof(T) / P.Ny;
+    const int cols = fast_tile_bytes(P.Ny) / (int)sizeof(T) / P.Ny;
     return P.Nx % cols == 0;
 }
 
 // rows per group of the row-grouped internal layout (flow_fast.cuh), 0 = the generic kernels on the reference layout
 template <class T> int flow_rg_rows(const PlanT<T>& P) {
     if (!fast_rows_ok(P) || !fast_cols_ok(P) || P.Ny % 64 != 0 || P.Nx % 32 != 0) return 0;
-    return (FAST_TILE_BYTES / (P.Nx * 16)) * (16 / (int)sizeof(T));
+    return (fast_tile_bytes(P.Nx) / (P.Nx * 16)) * (16 / (int)sizeof(T));
 }
 template <class T, bool TO_RG> void convert_layout(PlanT<T>& P, int G, const T* in, T* out, int C, cmblStream_t st) {
     typedef LayoutBody<T, TO_RG> B;
@@ -158,7 +160,8 @@ void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T*
         switch (P.Nx) {
             case 256: fast_rows<T, 8, ADJ>(F, c0, nC, u, kq, wgt, st); break;
             case 512: fast_rows<T, 9, ADJ>(F, c0, nC, u, kq, wgt, st); break;
-            default: fast_rows<T, 10, ADJ>(F, c0, nC, u, kq, wgt, st); break;
+            case 1024: fast_rows<T, 10, ADJ>(F, c0, nC, u, kq, wgt, st); break;
+            default: fast_rows<T, 11, ADJ>(F, c0, nC, u, kq, wgt, st); break;
         }
     } else {
         FlowRowBody<T, ADJ> b;
@@ -173,7 +176,8 @@ void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T*
         switch (P.Ny) {
             case 256: fast_cols<T, 8, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
             case 512: fast_cols<T, 9, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
-            default: fast_cols<T, 10, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
+            case 1024: fast_cols<T, 10, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
+            default: fast_cols<T, 11, ADJ>(F, c0, nC, u, kq, wgt, ybase, acc_in, acc_out, u_out, ca, cb, st, dx_out, dy_out); break;
         }
     } else {
         CMBL_REQUIRE(!dx_out, "derivative export needs the fast stage kernels");

@@ -230,10 +230,14 @@ template <class T> DEV Vec<T> vload_ldg(const T* p) {        // cached read-only
 template <int LOGN> struct FastSched {
     static constexpr int LOGR1 = (LOGN == 8) ? 2 : 3, LOGR2 = LOGN - 4 - LOGR1;
     static constexpr int R1 = 1 << LOGR1, R2 = 1 << LOGR2;
-    static_assert(LOGN >= 8 && LOGN <= 10, "fast path covers N = 256, 512, 1024");
+    static_assert(LOGN >= 8 && LOGN <= 11, "fast path covers N = 256, 512, 1024, 2048");      // 2048 = 8 · 16 · 16
 };
-inline bool fast_len_ok(int N) { return N == 256 || N == 512 || N == 1024; }
-constexpr int FAST_TILE_BYTES = 32768;
+inline bool fast_len_ok(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048; }
+// tile bytes and threads per block of the stage kernels for transform length N: 32 KB / 128 threads up to 1024, 64 KB / 256 threads at 2048
+// (with 32 KB a column tile would be two columns wide and a row group two rows high: 32-byte runs in the row-grouped layout; the bigger tile
+// keeps the runs at 128 B fp64 / 256 B fp32 and the bigger block keeps one butterfly task per thread and sweep)
+constexpr int fast_tile_bytes(int N) { return N > 1024 ? 65536 : 32768; }
+constexpr int fast_threads(int N) { return N > 1024 ? 256 : 128; }
 
 HD int swz8(int ch) { return ch ^ ((ch >> 3) & 7); }        // column kernel: chunk index within a plane
 HD int swzx(int x) { return x ^ ((x >> 4) & 7); }           // row kernel: x index within a chunk-row
@@ -298,15 +302,15 @@ template <class T, bool TO_RG> struct LayoutBody {
 // the δϕ integrand of the transpose-δ flow (flow_grad.cu); a separate instantiation, so the plain kernel's register budget is untouched.
 template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
     static_assert(!(ADJ && DMODE), "derivative export exists for the forward kernel only");
-    static constexpr int NT = 128, MINB = (ADJ || DMODE) ? 2 : CMBL_COL_MINB;
     static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), CH = N / V;       // CH chunks per column
+    static constexpr int TB = fast_tile_bytes(N), NT = fast_threads(N), MINB = (N > 1024) ? 1 : (ADJ || DMODE) ? 2 : CMBL_COL_MINB;
     static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
     static constexpr int S1 = N / R1, N2 = N / R1;                                   // pass-2 stride is 16
-    static constexpr int TILE = FAST_TILE_BYTES / (int)sizeof(T);                   // reals per tile buffer
+    static constexpr int TILE = TB / (int)sizeof(T);                                // reals per tile buffer
     static constexpr int L = TILE / (2 * N);                                         // complex lines (column pairs) per tile
     static constexpr int NB1 = S1 / V, NB2 = N / (R2 * V);                           // bundles per line in pass 1 / pass 2
     static constexpr int NBUF = ADJ ? 3 : 2;
-    static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * NBUF;
+    static constexpr size_t SMEM = (size_t)TB * NBUF;
     static constexpr bool PDL = true;
     static const char* name() { return "flow_cols"; }
 
@@ -349,7 +353,8 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
         for (int q = 1; q < R; ++q) { w.r[q] = vload_ldg(tw + ((q - 1) * 2) * tws + toff); w.i[q] = vload_ldg(tw + ((q - 1) * 2 + 1) * tws + toff); }
     }
     DEV void load_tw1(Tw<R1>& w, int task) const { load_tw<R1>(w, tw1, S1, V * (task % NB1)); }
-    DEV void load_tw2(Tw<R2>& w, int task) const { load_tw<R2>(w, tw2, 16, (V * (task % NB2)) & 15); }
+    static constexpr bool HALF2 = (R2 == 16);       // second sweep in half bundles (pass2_half): its twiddles are not kept across barriers
+    DEV void load_tw2(Tw<R2>& w, int task) const { if constexpr (!HALF2) load_tw<R2>(w, tw2, 16, (V * (task % NB2)) & 15); }
 
     // ---- twiddled pass on V adjacent butterflies: chunk index of element m = c0 + m*cs --------------------------
     template <int R, bool INV> DEV void bundle_pass(T* re, T* im, int xr_, int xi_, int c0, int cs, const Tw<R>& w, const T* pre, const T* pim) const {
@@ -396,7 +401,49 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
             bundle_pass<R1, INV>(re, im, pxor(2 * l), pxor(2 * l + 1), b, S1 / V, w, pre, pre ? pre + N : nullptr);
         }
     }
+    // R2 = 16 (N = 2048): a V-wide bundle would hold 2·16·V data values plus 2·15·V twiddles per thread.  Half bundles — V/2 adjacent
+    // butterflies, 8-byte shared-memory accesses — stay in registers and give each of the 256 threads one task per line pair.
+    struct alignas(8) HalfVec { T v[V / 2]; };
+    template <bool INV> DEV void pass2_half(T* buf, int tid, int nl) const {
+        constexpr int VB = V / 2, NBH = 2 * NB2, R = R2;
+        for (int task = tid; task < nl * NBH; task += NT) {
+            const int l = task / NBH, bh = task % NBH, b = bh >> 1, e0 = (bh & 1) * VB;
+            const int j0 = V * b, jj0 = j0 & 15, a = j0 >> 4, c0 = (a * N2 + jj0) / V, cs = 16 / V;
+            T* re = buf + (2 * l) * N; T* im = re + N;
+            const int xr_ = pxor(2 * l), xi_ = pxor(2 * l + 1);
+            HalfVec xr[R], xi[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const int o = swz8(c0 + m * cs);
+                xr[m] = *reinterpret_cast<const HalfVec*>(re + (o ^ xr_) * V + e0); xi[m] = *reinterpret_cast<const HalfVec*>(im + (o ^ xi_) * V + e0);
+            }
+#pragma unroll
+            for (int e = 0; e < VB; ++e) {
+                C2<T> v[R];
+#pragma unroll
+                for (int m = 0; m < R; ++m) v[m] = mk<T>(xr[m].v[e], xi[m].v[e]);
+                const T* tw = tw2 + jj0 + e0 + e;                         // ftw2[(q-1)][re|im][jj]
+                if (!INV) {
+                    dftR<T, R, false>(v);
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[q] = cmul(v[q], mk<T>(CMBL_LDG(tw + ((q - 1) * 2) * 16), CMBL_LDG(tw + ((q - 1) * 2 + 1) * 16)));
+                } else {
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], mk<T>(CMBL_LDG(tw + ((q - 1) * 2) * 16), CMBL_LDG(tw + ((q - 1) * 2 + 1) * 16)));
+                    dftR<T, R, true>(v);
+                }
+#pragma unroll
+                for (int m = 0; m < R; ++m) { xr[m].v[e] = v[m].x; xi[m].v[e] = v[m].y; }
+            }
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const int o = swz8(c0 + m * cs);
+                *reinterpret_cast<HalfVec*>(re + (o ^ xr_) * V + e0) = xr[m]; *reinterpret_cast<HalfVec*>(im + (o ^ xi_) * V + e0) = xi[m];
+            }
+        }
+    }
     template <bool INV> DEV void pass2(T* buf, int tid, Tw<R2>& w, int nl = L) const {
+        if constexpr (HALF2) { pass2_half<INV>(buf, tid, nl); return; }
         for (int task = tid; task < nl * NB2; task += NT) {
             const int l = task / NB2, b = task % NB2;
             if (task != tid) load_tw2(w, task);
@@ -513,7 +560,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
     // so plane ca's N(y) rides in the real part and plane cb's (cb < 0: none) in the imaginary part — done in a tile buffer that is
     // not in use.  Results go to dst_a / dst_b (global memory).  Ends with a barrier.
     DEV void jn_pair(T* ws, int ca, int cb, T* dst_a, T* dst_b, Tw<R1>& w1, Tw<R2>& w2, int goff = 0, int bar = 0) const {
-        CMBL_FOR_GROUP(tid, 128, goff) {
+        CMBL_FOR_GROUP(tid, NT, goff) {
             for (int i = tid; i < 2 * CH; i += NT) {
                 const int pl = i / CH, ch = i % CH, c = pl ? cb : ca;
                 Vec<T> z; for (int e = 0; e < V; ++e) z.v[e] = 0;
@@ -522,18 +569,18 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
             }
             load_tw1(w1, tid);
         }
-        group_sync(bar, 128);
-        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(ws, nullptr, tid, w1, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
-        group_sync(bar, 128);
-        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(ws, tid, w2, 1); }
-        group_sync(bar, 128);
-        CMBL_FOR_GROUP(tid, 128, goff) { middle(ws, tid, nullptr, 0, mult_sign, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
-        group_sync(bar, 128);
-        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(ws, tid, w2, 1); CMBL_PRE_END(load_tw1(w1, tid)); }
-        group_sync(bar, 128);
-        CMBL_FOR_GROUP(tid, 128, goff) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(ws, nullptr, tid, w1, 1); }
-        group_sync(bar, 128);
-        CMBL_FOR_GROUP(tid, 128, goff) {
+        group_sync(bar, NT);
+        CMBL_FOR_GROUP(tid, NT, goff) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(ws, nullptr, tid, w1, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        group_sync(bar, NT);
+        CMBL_FOR_GROUP(tid, NT, goff) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(ws, tid, w2, 1); }
+        group_sync(bar, NT);
+        CMBL_FOR_GROUP(tid, NT, goff) { middle(ws, tid, nullptr, 0, mult_sign, 1); CMBL_PRE_END(load_tw2(w2, tid)); }
+        group_sync(bar, NT);
+        CMBL_FOR_GROUP(tid, NT, goff) { CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(ws, tid, w2, 1); CMBL_PRE_END(load_tw1(w1, tid)); }
+        group_sync(bar, NT);
+        CMBL_FOR_GROUP(tid, NT, goff) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(ws, nullptr, tid, w1, 1); }
+        group_sync(bar, NT);
+        CMBL_FOR_GROUP(tid, NT, goff) {
             for (int i = tid; i < 2 * CH; i += NT) {
                 const int pl = i / CH, ch = i % CH;
                 T* dst = pl ? dst_b : dst_a;
@@ -544,7 +591,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
                 }
             }
         }
-        group_sync(bar, 128);
+        group_sync(bar, NT);
     }
 
     // publisher blocks: compute the lines of one plane pair into jn_pub and raise the flags (the block's first tile is in flight)
@@ -560,7 +607,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
         if (blk < b0 || blk >= b0 + np) return;
         const int pr = (blk - b0) % npairs, ca = cbase + 2 * pr, cb = (2 * pr + 1 < nC) ? ca + 1 : -1;
         jn_pair(ws, ca, cb, jn_pub + (size_t)ca * N, cb >= 0 ? jn_pub + (size_t)cb * N : nullptr, w1, w2, goff, bar);
-        CMBL_FOR_GROUP(tid, 128, goff) { if (tid == 0) flag_publish2(jn_flag + ca, jn_flag + (cb >= 0 ? cb : ca), epoch); }
+        CMBL_FOR_GROUP(tid, NT, goff) { if (tid == 0) flag_publish2(jn_flag + ca, jn_flag + (cb >= 0 ? cb : ca), epoch); }
     }
     // RARE path of the column kernel (the publishers of plane c's J[N] line are not resident): a private copy computed from the same plane
     // pair (identical bits).  The work space is the tile buffer `ws` in which the next tile is landing: let it arrive, use the buffer, request
@@ -677,6 +724,8 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
 template <class T, int LOGN, bool ADJ> struct FastRowBody {
     static constexpr int NT = 128, MINB = ADJ ? 2 : (sizeof(T) == 8 ? CMBL_ROW_F64_MINB : 3);
     static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), H = V / 2;          // H complex lines per chunk
+    static constexpr int FAST_TILE_BYTES = 32768;
+    static_assert(LOGN <= 10, "the cp.async row kernel is kept for lengths up to 1024 (CMBL_ROW_TMA=0); 2048 runs on TmaRowBody only");
     static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
     static constexpr int S1 = N / R1, N2 = N / R1, NB2 = N / R2, NBM = N / 16;
     static constexpr int CPX = FAST_TILE_BYTES / (N * 16);                            // 16-byte chunks per x (even)
@@ -963,15 +1012,20 @@ DEV void fence_proxy_async() {                  // make this thread's shared-mem
 // in the other, which is also where tile t-1's result is read from by its outgoing copy.
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, int LOGN, bool ADJ> struct TmaRowBody {
-    static constexpr int NT = 128, MINB = ADJ ? 2 : (sizeof(T) == 8 ? CMBL_ROW_F64_MINB : 3);
     static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), H = V / 2;
+    static constexpr int FAST_TILE_BYTES = fast_tile_bytes(N), NT = fast_threads(N);
+    static constexpr int MINB = (N > 1024) ? 1 : ADJ ? 2 : (sizeof(T) == 8 ? CMBL_ROW_F64_MINB : 3);
     static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
     static constexpr int S1 = N / R1, N2 = N / R1, NB2 = N / R2, NBM = N / 16;
     static constexpr int CPX = FAST_TILE_BYTES / (N * 16);
     static constexpr int ROWS = CPX * V;
     static constexpr int TILE = FAST_TILE_BYTES / (int)sizeof(T);
-    static constexpr int NP1 = (CPX / 2) / (NT / S1), NP2 = (CPX / 2) / (NT / NB2);      // chunk-row pairs per thread and sweep
+    // chunk rows a thread takes together in a sweep (PW: 2 = adjacent pairs, always in the first / last sweep whose global side moves 256 bits;
+    // 1 where the pairs would not give every thread a task: the radix-16 second sweep at N = 2048) and tasks per thread and sweep
+    static constexpr int PW2 = ((CPX / 2) % (NT / NB2) == 0) ? 2 : 1;
+    static constexpr int NP1 = (CPX / 2) / (NT / S1), NP2 = (CPX / PW2) / (NT / NB2);
     static_assert(NT % S1 == 0 && NT % NB2 == 0 && NT % NBM == 0 && CPX % 2 == 0 && NP1 >= 1 && NP2 >= 1, "thread/butterfly mapping");
+    static_assert((CPX / 2) % (NT / S1) == 0 && (CPX / PW2) % (NT / NB2) == 0 && CPX % (NT / NBM) == 0, "chunk-row mapping");
 #ifdef CMBL_EMU
     static constexpr size_t SMEM = (size_t)FAST_TILE_BYTES * (ADJ ? 3 : 2) + 64 + FAST_TILE_BYTES;   // + snapshot for the serial emulation
 #else
@@ -1014,14 +1068,14 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
     // the eight 128-bit accesses of a quarter-warp hit eight different 16-byte bank groups.  (The work layout is unaffected: a row
     // is a multiple of 4 KB there.)
     static DEV int lane_par(int tid) { return CPX == 2 ? ((tid >> 2) & 1) : CPX == 4 ? ((tid >> 1) & 3) : (tid & 7); }
-    template <int R, int NP, bool LIN> DEV void sw_load(const T* buf, const T* pbuf, int g0, int gs, int x0, int xs, Chunk (&x)[NP][2][R], int par = 0) const {
+    template <int R, int NP, bool LIN, int PW = 2> DEV void sw_load(const T* buf, const T* pbuf, int g0, int gs, int x0, int xs, Chunk (&x)[NP][PW][R], int par = 0) const {
 #pragma unroll
         for (int i = 0; i < NP; ++i)
 #pragma unroll
             for (int m = 0; m < R; ++m)
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int o = off<LIN>((2 * (g0 + i * gs) + s) ^ par, x0 + m * xs);
+                for (int s = 0; s < PW; ++s) {
+                    const int o = off<LIN>((PW * (g0 + i * gs) + s) ^ par, x0 + m * xs);
                     x[i][s][m] = ld(buf + o);
                     if (pbuf) {
                         Vec<T> p = vload(pbuf + o), a; memcpy(&a, &x[i][s][m], 16);
@@ -1031,11 +1085,11 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
                     }
                 }
     }
-    template <int R, int NP, bool INV> DEV void sw_compute(Chunk (&x)[NP][2][R], const C2<T>* w) const {
+    template <int R, int NP, bool INV, int PW = 2> DEV void sw_compute(Chunk (&x)[NP][PW][R], const C2<T>* w) const {
 #pragma unroll
         for (int i = 0; i < NP; ++i)
 #pragma unroll
-            for (int s = 0; s < 2; ++s)
+            for (int s = 0; s < PW; ++s)
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
                     C2<T> v[R];
@@ -1054,13 +1108,13 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
                     for (int m = 0; m < R; ++m) x[i][s][m].c[h] = v[m];
                 }
     }
-    template <int R, int NP, bool LIN> DEV void sw_store(T* buf, int g0, int gs, int x0, int xs, const Chunk (&x)[NP][2][R], int par = 0) const {
+    template <int R, int NP, bool LIN, int PW = 2> DEV void sw_store(T* buf, int g0, int gs, int x0, int xs, const Chunk (&x)[NP][PW][R], int par = 0) const {
 #pragma unroll
         for (int i = 0; i < NP; ++i)
 #pragma unroll
             for (int m = 0; m < R; ++m)
 #pragma unroll
-                for (int s = 0; s < 2; ++s) st(buf + off<LIN>((2 * (g0 + i * gs) + s) ^ par, x0 + m * xs), x[i][s][m]);
+                for (int s = 0; s < PW; ++s) st(buf + off<LIN>((PW * (g0 + i * gs) + s) ^ par, x0 + m * xs), x[i][s][m]);
     }
     DEV void middle(T* buf, int tid, const T* mlt, T* nline_c, T* nacc_c, int y0) const {
         const int j = tid % NBM;
@@ -1158,10 +1212,10 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
             CMBL_FOR_THREADS(tid, NT) {
                 CMBL_PRE_START(load_w2(tid, w2));
                 const int j = tid % NB2;
-                Chunk x[NP2][2][R2];
-                sw_load<R2, NP2, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
-                sw_compute<R2, NP2, false>(x, w2);
-                sw_store<R2, NP2, false>(buf, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+                Chunk x[NP2][PW2][R2];
+                sw_load<R2, NP2, false, PW2>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+                sw_compute<R2, NP2, false, PW2>(x, w2);
+                sw_store<R2, NP2, false, PW2>(buf, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
             }
             CMBL_SYNC();
             CMBL_FOR_THREADS(tid, NT) {
@@ -1172,10 +1226,10 @@ template <class T, int LOGN, bool ADJ> struct TmaRowBody {
             CMBL_FOR_THREADS(tid, NT) {
                 CMBL_PRE_START(load_w2(tid, w2));
                 const int j = tid % NB2;
-                Chunk x[NP2][2][R2];
-                sw_load<R2, NP2, false>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
-                sw_compute<R2, NP2, true>(x, w2);
-                sw_store<R2, NP2, false>(buf, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+                Chunk x[NP2][PW2][R2];
+                sw_load<R2, NP2, false, PW2>(buf, nullptr, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
+                sw_compute<R2, NP2, true, PW2>(x, w2);
+                sw_store<R2, NP2, false, PW2>(buf, tid / NB2, NT / NB2, (j >> 4) * N2 + (j & 15), 16, x);
             }
             CMBL_SYNC();
             // ---- last sweep: swizzled work layout -> linear order, in place; then one outgoing bulk copy ----------------

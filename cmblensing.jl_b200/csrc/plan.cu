@@ -109,8 +109,13 @@ static void build_axis(std::vector<void*>& owned, AxisTables<T>& a, int N, T dl)
     a.mult_sign = upload_vec(owned, ms);
     a.ell_nyq = (T)(-(N / 2)) * dl;
     a.nyq_pos = pos[N / 2];
-    if (f.npass == 3 && f.radix[2] == 16) {
-        const int R1 = f.radix[0], R2 = f.radix[1], S1 = N / R1;
+    // fast-path schedule and tables (plan.cuh)
+    int fr[MAX_PASSES] = {0, 0, 0, 0, 0, 0};
+    bool fast = false;
+    if (f.npass == 3 && f.radix[2] == 16) { fast = true; for (int i = 0; i < 3; ++i) fr[i] = f.radix[i]; }
+    else if (N == 2048) { fast = true; fr[0] = 8; fr[1] = 16; fr[2] = 16; }
+    if (fast) {
+        const int R1 = fr[0], R2 = fr[1], S1 = N / R1;
         std::vector<T> t1((size_t)(R1 - 1) * 2 * S1), t2((size_t)(R2 - 1) * 2 * 16);
         for (int q = 1; q < R1; ++q)
             for (int j = 0; j < S1; ++j) { t1[((size_t)(q - 1) * 2) * S1 + j] = W[j * q].x; t1[((size_t)(q - 1) * 2 + 1) * S1 + j] = W[j * q].y; }
@@ -118,6 +123,15 @@ static void build_axis(std::vector<void*>& owned, AxisTables<T>& a, int N, T dl)
             for (int jj = 0; jj < 16; ++jj) { t2[((size_t)(q - 1) * 2) * 16 + jj] = W[jj * q * R1].x; t2[((size_t)(q - 1) * 2 + 1) * 16 + jj] = W[jj * q * R1].y; }
         a.ftw1 = upload_vec(owned, t1);
         a.ftw2 = upload_vec(owned, t2);
+        a.fmult_deriv = a.mult_deriv; a.fmult_sign = a.mult_sign;
+        if (fr[1] != f.radix[1]) {                             // its own tile order
+            std::vector<int> fpos = fft_positions(N, 3, fr);
+            CMBL_REQUIRE(fpos[N / 2] == 8, "the fast kernels read the Nyquist coefficient at tile position 8");
+            std::vector<T> fmd(N), fms(N);
+            for (int k = 0; k < N; ++k) { fmd[fpos[k]] = md[pos[k]]; fms[fpos[k]] = ms[pos[k]]; }
+            a.fmult_deriv = upload_vec(owned, fmd);
+            a.fmult_sign = upload_vec(owned, fms);
+        }
     }
 }
 

@@ -16,10 +16,13 @@ template <class T> struct AxisTables {
     const T* mult_sign = nullptr;    // [N] tile order: sign(k(p)) / N      (DC and Nyquist 0)
     T ell_nyq = 0;                   // ℓ of the Nyquist frequency (negative, src/proj_lambert.jl:63-64)
     int nyq_pos = 0;                 // tile position of the Nyquist frequency after the forward passes
-    // fast path (flow_fast.cuh), only when the schedule is exactly [R1, R2, 16]: planar twiddle tables
+    // fast path (flow_fast.cuh): a three-sweep schedule [R1, R2, 16] — the generic schedule up to N = 1024, [8, 16, 16] at N = 2048 (where
+    // the generic kernels run four sweeps) — with planar twiddle tables
     //   ftw1[(q-1)][re|im][j]  = W_N^(j q),        j < N/R1, q = 1..R1-1     (first forward / last inverse pass)
     //   ftw2[(q-1)][re|im][jj] = W_{N/R1}^(jj q),  jj < 16,  q = 1..R2-1     (second forward / first inverse pass)
+    // and the multiplier tables in ITS tile order (the same arrays as mult_deriv / mult_sign when the schedules coincide)
     const T* ftw1 = nullptr; const T* ftw2 = nullptr;
+    const T* fmult_deriv = nullptr; const T* fmult_sign = nullptr;
 };
 
 struct PlanBase {

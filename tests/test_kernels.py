@@ -109,9 +109,10 @@ def test_lenseflow_all_ops(pkg, be, Ny, Nx, pol, nb, nbphi, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi,path", [(256, 256, "P", 2, 2, 3), (512, 256, "I", 1, 1, 3), (256, 1024, "I", 2, 1, 3),
-                                                      (1024, 512, "I", 1, 1, 3), (256, 256, "IP", 2, 2, 3), (64, 256, "I", 1, 1, 0), (256, 32, "P", 1, 1, 0), (512, 64, "I", 1, 1, 0), (128, 64, "P", 1, 1, 0)])
+                                                      (1024, 512, "I", 1, 1, 3), (256, 256, "IP", 2, 2, 3), (2048, 256, "P", 1, 1, 3), (256, 2048, "I", 2, 1, 3), (64, 256, "I", 1, 1, 0), (256, 32, "P", 1, 1, 0), (512, 64, "I", 1, 1, 0), (128, 64, "P", 1, 1, 0)])
 def test_lenseflow_fast_path(pkg, be, Ny, Nx, pol, nb, nbphi, path, dtype):
-    """The persistent cp.async kernels of csrc/flow_fast.cuh (lengths 256/512/1024), all four ops, against the oracle;
+    """The persistent stage kernels of csrc/flow_fast.cuh (lengths 256/512/1024, and 2048 with its 64 KB tiles, 256 threads and [8,16,16]
+    schedule, as column and as row length), all four ops, against the oracle;
     `path` = 3 when the pair of fast kernels (row-grouped internal layout) must have been used, 0 for the generic pair."""
     pr = make_problem(pkg, Ny, Nx, pol, dtype, nb=nb, nbphi=nbphi, nsteps=2, mask=False, seed=11, lib=be.lib, device=be.device)
     L = pkg.LenseFlow(pr["phi"], 2)
@@ -208,7 +209,7 @@ def test_lenseflow_adjoint_identity(pkg, be, pol, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-@pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(16, 32, "I", 1, 1), (32, 16, "P", 2, 2), (256, 256, "P", 1, 1)])
+@pytest.mark.parametrize("Ny,Nx,pol,nb,nbphi", [(16, 32, "I", 1, 1), (32, 16, "P", 2, 2), (256, 256, "P", 1, 1), (2048, 256, "I", 1, 1)])
 def test_lenseflow_pullback(pkg, be, Ny, Nx, pol, nb, nbphi, dtype):
     """negδvelocityᴴ transpose flow (src/lenseflow.jl:176-214) against the oracle, reference-compatible (aliased) and exact."""
     nst = 3 if Ny < 256 else 1
