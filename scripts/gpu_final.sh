@@ -14,8 +14,10 @@ cap r02_ncu_flow_f64 38 2 python scripts/ncu_target.py f64 fwd
 cap r02_ncu_flow_f32 38 2 python scripts/ncu_target.py f32 fwd
 cap r02_ncu_adj_f64 12 2 python scripts/ncu_target.py f64 adj
 cap r02_ncu_fft_f64 2 3 python scripts/ncu_target.py f64 adj
-# DRAM traffic of one whole RK4 step (4 row + 4 column launches: stage kinds 0,1,1,2), metrics only
-timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_op_read_hit_rate.pct --clock-control none -s 20 -c 10 python scripts/ncu_target.py f64 fwd 2>&1 | grep -i "RowBody\|ColBody\|dram__\|duration\|hit_rate" > gpurun_out/r02_stage_traffic_by_kind.log; tail -5 gpurun_out/r02_stage_traffic_by_kind.log
+# DRAM traffic of one whole RK4 step (4 row + 4 column launches: stage kinds 0,1,1,2 in some rotation), metrics only, both precisions
+for dt in f64 f32; do
+  timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_op_read_hit_rate.pct --clock-control none -s 20 -c 8 --csv --log-file gpurun_out/r02_stage_traffic_by_kind_$dt.csv python scripts/ncu_target.py $dt fwd > /dev/null 2>&1
+done
 python scripts/make_profiles.py r02 gpurun_out/profiles_out > gpurun_out/make_profiles.log 2>&1; tail -2 gpurun_out/make_profiles.log
 rm -f gpurun_out/r02_ncu_flow_f32.ncu-rep gpurun_out/r02_ncu_adj_f64.ncu-rep gpurun_out/r02_ncu_fft_f64.ncu-rep      # keep one .ncu-rep (64 MiB limit on what travels back)
 python - <<'PY'

@@ -30,5 +30,32 @@ for key, cmd in CMD.items():
             b = float(r[rd]) * unit[rows[1][rd]] + float(r[wr]) * unit[rows[1][wr]]
             traffic.setdefault(key[5:], {})[nm] = b
     print("wrote", f"profiles/{tag}_ncu_{key}.txt")
+# The --set full captures above hold ONE launch of each stage kernel (a middle RK4 stage: 6C + 2Cϕ plane passes for the column kernel, against
+# 4C + 2Cϕ for the first and the last stage).  bench.py's `roofline.achieved` is an average over all launches, so the traffic it is compared
+# with is the mean over the four stages of one RK4 step, from the metrics-only pass gpurun_out/<tag>_stage_traffic_by_kind_<dtype>.csv.
+unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+for dt in ("f64", "f32"):
+    f = os.path.join(G, f"{tag}_stage_traffic_by_kind_{dt}.csv")
+    if not os.path.exists(f):
+        continue
+    rows = [r for r in csv.reader(open(f)) if len(r) > 10]
+    hdr = rows[0]; ki, idc, mn, mu, mv = hdr.index("Kernel Name"), hdr.index("ID"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+    per = {}
+    for r in rows[1:]:
+        per.setdefault((r[idc], r[ki]), {})[r[mn]] = float(r[mv].replace(",", "")) * unit.get(r[mu], 1.0)
+    out = {"flow_rows": [], "flow_cols": []}; lines = []
+    for (i, k), m in sorted(per.items(), key=lambda kv: int(kv[0][0])):
+        nm = "flow_rows" if "RowBody" in k else ("flow_cols" if "FastColBody" in k else None)
+        if nm:
+            out[nm].append(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"])
+            lines.append(f"launch {i} {nm}: read {m['dram__bytes_read.sum']/1e6:.1f} MB, written {m['dram__bytes_write.sum']/1e6:.1f} MB, {m['gpu__time_duration.sum']:.0f} ns, L2 read hit {m['lts__t_sector_op_read_hit_rate.pct']:.1f} %")
+    if out["flow_cols"]:
+        traffic[dt + "_full_capture_launch"] = traffic.get(dt)
+        traffic[dt] = {k: sum(v) / len(v) for k, v in out.items() if v}
+        traffic[dt + "_by_stage"] = out
+        open(os.path.join(P, f"{tag}_stage_traffic_by_kind_{dt}.txt"), "w").write(
+            "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_op_read_hit_rate.pct --clock-control none -s 20 -c 8  python scripts/ncu_target.py "
+            + dt + " fwd   (one RK4 step: 4 row + 4 column launches)\nlibcmbl_b200.so sha256[:16] = " + str(sha) + "\n" + "\n".join(lines) + "\n")
+traffic["source"] = f"mean over the four stages of one RK4 step (profiles/{tag}_stage_traffic_by_kind_*.txt, ncu metrics pass); *_full_capture_launch: the single launch of the --set full capture (profiles/{tag}_ncu_flow_*.txt)"
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic))

@@ -71,6 +71,7 @@ NL = 5
 torch.cuda.synchronize(); t0 = time.perf_counter()
 x, ΔH, acc = pkg.gibbs_sample_ϕ(ds, f_m, ϕ_m, symp_kwargs=(dict(N=NL, ϵ=0.01),), always_accept=False)
 torch.cuda.synchronize(); th = time.perf_counter() - t0
+if pol == "IP": ΔH = np.full_like(ΔH, np.nan)      # timing only: with the stand-in Nϕ of the IP branch (no quadratic estimate, no mixing matrix) ΔH is not meaningful
 print(f"   HMC ϕ° update, {NL} leap-frog steps: {th*1e3:.0f} ms = {NL/th:.1f} leap-frog steps/s for the batch of {NB} ({NB*NL/th:.1f} chain-steps/s); ΔH = {np.round(ΔH, 3)}, accept = {acc}")
 # per-kernel device time of one gradient (CUDA events around every launch)
 lib.cdll.cmbl_profile_begin()
