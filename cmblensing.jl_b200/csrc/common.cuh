@@ -175,7 +175,9 @@ template <class Body, class = void> struct MinBlocks { static constexpr int valu
 template <class Body> struct MinBlocks<Body, decltype((void)Body::MINB)> { static constexpr int value = Body::MINB; };
 template <class Body, class = void> struct UsesPdl { static constexpr bool value = false; };
 template <class Body> struct UsesPdl<Body, decltype((void)Body::PDL)> { static constexpr bool value = Body::PDL; };
-inline bool pdl_enabled() { static const bool v = [] { const char* e = getenv("CMBL_PDL"); return e && atoi(e) != 0; }(); return v; }
+// programmatic dependent launch of a kernel that supports it (Body::PDL): CMBL_PDL=0/1 forces it off/on, otherwise the launcher's hint decides
+inline int pdl_env() { static const int v = [] { const char* e = getenv("CMBL_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }(); return v; }
+inline bool pdl_enabled(int hint) { const int e = pdl_env(); return e >= 0 ? e == 1 : hint > 0; }
 template <class Body> __global__ void __launch_bounds__(Body::NT, MinBlocks<Body>::value) kern(const Body b) {
     extern __shared__ __align__(1024) unsigned char cmbl_smem[];   // 1024: tensor-map copies with the 128-byte swizzle
     b((int)blockIdx.x, cmbl_smem);
@@ -184,11 +186,11 @@ template <class Body> __global__ void __launch_bounds__(Body::NT, MinBlocks<Body
 
 // cluster > 1: the blocks of the grid are launched as thread-block clusters of that many consecutive blocks (co-scheduled by the hardware,
 // so a cluster barrier between them can never wait for a block that is not resident)
-template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStream_t st, int cluster = 1) {
+template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStream_t st, int cluster = 1, int pdl_hint = 0) {
     if (grid <= 0) return;
     ++g_launch_count;
 #ifdef CMBL_EMU
-    (void)st;
+    (void)st; (void)cluster; (void)pdl_hint;
     int nthr = (int)std::thread::hardware_concurrency(); if (nthr < 1) nthr = 1; if (nthr > grid) nthr = grid;
     if (const char* e = getenv("CMBL_EMU_THREADS")) { nthr = atoi(e); if (nthr < 1) nthr = 1; }
     if (grid <= 64) nthr = grid;       // small (persistent) grids: every block gets its own host thread — blocks of a persistent
@@ -217,7 +219,7 @@ template <class Body> void launch(const Body& b, int grid, size_t smem, cmblStre
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         CMBL_CUDA(cudaLaunchKernelEx(&cfg, kern<Body>, b));
-    } else if (UsesPdl<Body>::value && pdl_enabled() && !g_profiling) {
+    } else if (UsesPdl<Body>::value && pdl_enabled(pdl_hint) && !g_profiling) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)Body::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];

@@ -1,6 +1,35 @@
 #include "fft2d.cuh"
+#include "fft2d_fast.cuh"
+#include <algorithm>
 
 namespace cmbl {
+
+// column passes on the persistent tile kernels of fft2d_fast.cuh (Ny = 256 … 2048); CMBL_FFT_FAST=0 keeps the generic ones (A/B, tests)
+static bool fft_fast_enabled() { static const bool v = [] { const char* e = getenv("CMBL_FFT_FAST"); return !e || atoi(e) != 0; }(); return v; }
+template <class T> static bool fft_cols_fast_ok(const PlanT<T>& P) {
+    if (!fft_fast_enabled() || !fast_len_ok(P.Ny) || !P.ay.ftw1) return false;
+    return P.Nx % (fast_tile_bytes(P.Ny) / (int)sizeof(T) / P.Ny) == 0;
+}
+template <class T, class B> static void fft_cols_fast_setup(PlanT<T>& P, B& b, int nC) {
+    b.fc.tw1 = P.ay.ftw1; b.fc.tw2 = P.ay.ftw2;
+    b.fc.Nx = P.Nx; b.fc.G = P.Ny; b.fc.lgGV = ilog2(P.Ny / B::V);             // the reference layout is the row-grouped layout with a single group
+    b.tiles_per_plane = P.Nx / B::M; b.ntiles = nC * b.tiles_per_plane;
+    b.nblocks = std::min(b.ntiles, persistent_blocks<B>(B::SMEM));
+}
+template <class T, int LOGN> static void rfft2_cols_fast(PlanT<T>& P, const T* in, C2<T>* out, int nC, cmblStream_t st) {
+    typedef FastR2CColBody<T, LOGN> B;
+    B b{};
+    fft_cols_fast_setup<T, B>(P, b, nC);
+    b.Nyh = P.Nyh; b.in = in; b.out = out;
+    launch(b, b.nblocks, B::SMEM, st);
+}
+template <class T, int LOGN> static void irfft2_cols_fast(PlanT<T>& P, const C2<T>* in, T* out, int nC, const T* post_diag, int post_planes, cmblStream_t st) {
+    typedef FastC2RColBody<T, LOGN> B;
+    B b{};
+    fft_cols_fast_setup<T, B>(P, b, nC);
+    b.scale = (T)1 / ((T)P.Ny * (T)P.Nx); b.in = in; b.out = out; b.post_diag = post_diag; b.post_planes = post_planes;
+    launch(b, b.nblocks, B::SMEM, st);
+}
 
 // Planes per pass pair.  The two 1-D passes of a 2-D transform exchange a half-plane spectrum per plane; transforming a few
 // planes at a time keeps that intermediate (and, for irfft2, a scratch buffer reused by every group) inside the 126 MB L2.
@@ -23,7 +52,14 @@ template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmb
         const int nC = (C - c0 < chunk) ? C - c0 : chunk;
         const T* in = map + (size_t)c0 * P.map_elems();
         C2<T>* out = four + (size_t)c0 * P.four_elems();
-        {
+        if (fft_cols_fast_ok(P)) {
+            switch (P.Ny) {
+                case 256: rfft2_cols_fast<T, 8>(P, in, out, nC, st); break;
+                case 512: rfft2_cols_fast<T, 9>(P, in, out, nC, st); break;
+                case 1024: rfft2_cols_fast<T, 10>(P, in, out, nC, st); break;
+                default: rfft2_cols_fast<T, 11>(P, in, out, nC, st); break;
+            }
+        } else {
             R2CColBody<T> b;
             b.fy = P.ay.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh;
             b.L = col_lines<T>(P.ay.fft, P.Nx); b.tiles_per_plane = P.Nx / (2 * b.L);
@@ -53,13 +89,21 @@ template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cm
             b.in = four + (size_t)c0 * P.four_elems(); b.out = scratch;
             launch(b, nC * b.tiles_per_plane, Tile<T, true>::bytes(P.Nx, b.L, 0), st);
         }
-        {
+        CMBL_REQUIRE(!post_diag || (c0 % post_planes == 0), "plane groups must start on a diagonal period");
+        if (fft_cols_fast_ok(P)) {
+            T* out = map + (size_t)c0 * P.map_elems();
+            switch (P.Ny) {
+                case 256: irfft2_cols_fast<T, 8>(P, scratch, out, nC, post_diag, post_planes, st); break;
+                case 512: irfft2_cols_fast<T, 9>(P, scratch, out, nC, post_diag, post_planes, st); break;
+                case 1024: irfft2_cols_fast<T, 10>(P, scratch, out, nC, post_diag, post_planes, st); break;
+                default: irfft2_cols_fast<T, 11>(P, scratch, out, nC, post_diag, post_planes, st); break;
+            }
+        } else {
             C2RColBody<T> b;
             b.fy = P.ay.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh;
             b.L = col_lines<T>(P.ay.fft, P.Nx); b.tiles_per_plane = P.Nx / (2 * b.L);
             b.scale = (T)1 / ((T)P.Ny * (T)P.Nx);
             b.in = scratch; b.out = map + (size_t)c0 * P.map_elems();
-            CMBL_REQUIRE(!post_diag || (c0 % post_planes == 0), "plane groups must start on a diagonal period");
             b.post_diag = post_diag; b.post_planes = post_planes;
             launch(b, nC * b.tiles_per_plane, Tile<T, false>::bytes(P.Ny, b.L, P.ay.fft.sk), st);
         }

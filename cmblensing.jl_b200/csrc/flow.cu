@@ -53,6 +53,11 @@ static int fast_cols_jn_polls() { static const int v = [] { const char* e = gete
 // barrier), hoping that the p maps both read come from DRAM once.  Measured (profiles/r02_col_cluster_pair.log): DRAM reads unchanged
 // (683 vs 679 MB per launch) and +4 % time, so it is off by default.
 static int fast_cols_pair() { static const int v = [] { const char* e = getenv("CMBL_COL_PAIR"); return e ? atoi(e) : 0; }(); return v; }
+// Programmatic dependent launch between the stage kernels (the next kernel's blocks are scheduled and load their tables while the previous one
+// drains; griddepcontrol.wait orders the data).  Measured by shape (profiles/r02_pdl_by_shape.log): fp64 gains everywhere (0.3-2.5 % on the
+// machine-filling launches, 13-21 % on small ones, 15 % on the adjoint flow of Nside=1024 batch 1), fp32 gains only on launches of a few tiles
+// (13-25 % at 256², but +2..+12 % on the larger ones) — so: on for fp64, on for fp32 launches with fewer tiles than half the SMs.  CMBL_PDL=0/1 overrides.
+template <class T> static int fast_pdl_hint(int ntiles) { return (sizeof(T) == 8 || 2 * ntiles <= device_sms()) ? 1 : 0; }
 static int fast_block_cap(int full) {     // experiment knob: cap the persistent grid at N blocks per SM
     static const int v = [] { const char* e = getenv("CMBL_FLOW_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     return v > 0 ? std::min(full, v * device_sms()) : full;
@@ -79,7 +84,7 @@ static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cm
         b.Npol = F.Npol; b.Nbphi = F.Nbphi; b.cbase = c0;
         b.u = u; b.pk = F.pk(kq); b.tmp = reinterpret_cast<T*>(F.tmp.p); b.nline = reinterpret_cast<T*>(F.nline.p);
         b.nacc = reinterpret_cast<T*>(F.nacc.p); b.wgt = wgt;
-        launch(b, b.nblocks, B::SMEM, st);
+        launch(b, b.nblocks, B::SMEM, st, 1, fast_pdl_hint<T>(b.ntiles));
         return;
     }
     if constexpr (LOGN <= 10) {
@@ -118,7 +123,7 @@ static void fast_cols_launch(FlowT<T>& F, int c0, int nC, const T* u, int kq, T 
     if (F.jnflag.cap < sizeof(int) * (size_t)F.C) { F.jnflag.reserve(sizeof(int) * (size_t)F.C); dev_zero(F.jnflag.p, sizeof(int) * (size_t)F.C, st); }
     b.jn_flag = reinterpret_cast<int*>(F.jnflag.p); b.epoch = ++F.jn_epoch;
     b.ybase = ybase; b.acc_in = acc_in; b.acc_out = acc_out; b.u_out = u_out; b.ca = ca; b.cb = cb;
-    launch(b, b.nblocks, B::SMEM, st, cluster);
+    launch(b, b.nblocks, B::SMEM, st, cluster, fast_pdl_hint<T>(b.ntiles));
 }
 template <class T, int LOGN, bool ADJ>
 static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out, T ca, T cb, cmblStream_t st,

@@ -36,7 +36,7 @@ def test_no_cpu_fallback(pkg):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-@pytest.mark.parametrize("Ny,Nx", SIZES + [(256, 256), (512, 8), (8, 2048)])
+@pytest.mark.parametrize("Ny,Nx", SIZES + [(256, 256), (512, 8), (8, 2048), (1024, 16), (2048, 8), (512, 64)])
 def test_rfft2_irfft2(pkg, be, Ny, Nx, dtype):
     npT, tT = T_of(dtype)
     rng = np.random.default_rng(0)
