@@ -18,8 +18,13 @@
 #ifndef CMBL_FFT_MINB
 #define CMBL_FFT_MINB 2
 #endif
+#ifndef CMBL_FFT_ROW_UNR
+#define CMBL_FFT_ROW_UNR 4          // strided loads of the row pass kept in flight per thread (the tile's runs are L·sizeof(C2) = 64 bytes)
+#endif
 
 namespace cmbl {
+
+constexpr int FFT_ROW_UNR = CMBL_FFT_ROW_UNR;
 
 inline int tile_budget_bytes() {
     static int v = [] { const char* e = getenv("CMBL_TILE_KB"); int kb = e ? atoi(e) : 70; if (kb < 8) kb = 8; if (kb > 200) kb = 200; return kb * 1024; }();
@@ -39,7 +44,7 @@ template <class T> int col_lines(const Fft1D<T>& f, int Nother, int extra = 0) {
 }
 // lines per tile for row kernels (interleaved tile)
 template <class T> int row_lines(int N, int maxL) {
-    size_t per = sizeof(C2<T>) * (size_t)N;
+    size_t per = Tile<T, true>::bytes(N, 1, 0);
     int L = (int)(tile_budget_bytes() / per);
     if (L < 1) L = 1;
     L = pow2_floor(L);
@@ -98,6 +103,7 @@ template <class T, bool INV> struct C2CRowBody {
         C2<T>* dst = out + (size_t)c * Nx * Nyh;
         const int logL = ilog2(L);                                              // L is a power of two
         CMBL_FOR_THREADS(tid, NT) {
+#pragma unroll FFT_ROW_UNR
             for (int e = tid; e < L * Nx; e += NT) {
                 const int x = e >> logL, l = e & (L - 1);
                 C2<T> v = (k0 + l < Nyh) ? src[(size_t)x * Nyh + k0 + l] : mk<T>(0, 0);

@@ -22,16 +22,19 @@ template <class T> struct Fft1D {
 };
 
 // Shared-memory tile of L complex lines of length N.
-//   LFAST = true : element (l, i) at i*L + l   (lines interleaved; used when lines are strided in global memory)
+//   LFAST = true : element (l, i) at (i + (i >> 4))*L + l   (lines interleaved; used when lines are strided in global memory).  One
+//                  padding slot per 16 elements: in the twiddle-free radix-16 pass the lanes of a warp hold neighbouring butterflies
+//                  whose elements are 16·L slots apart — a multiple of the 128-byte bank width for the usual L·sizeof(C2) = 64 B —
+//                  and the skew spreads them over both halves (27-45 % of the row pass's shared-memory wavefronts were conflicts).
 //   LFAST = false: element (l, i) at l*pitch + i + (i >> sk)   (line-major; sk = log2 of the LAST radix of the schedule,
 //                  so that the stride-R accesses of the fused middle pass are bank-conflict free)
 template <class T, bool LFAST> struct Tile {
     C2<T>* s; int L; int pitch; int sk;
     HD int phys(int i) const { return i + (i >> sk); }
-    HD C2<T>& at(int l, int i) const { return LFAST ? s[i * L + l] : s[l * pitch + i + (i >> sk)]; }
+    HD C2<T>& at(int l, int i) const { return LFAST ? s[(i + (i >> 4)) * L + l] : s[l * pitch + i + (i >> sk)]; }
     // pitch ≡ 2 (mod 16) elements: transposing tile loads (lines fastest across threads) stay conflict free
     static HD int pitch_for(int N, int sk) { int p = N + (N >> sk); return p + ((18 - (p & 15)) & 15); }
-    static HD size_t bytes(int N, int L, int sk) { return sizeof(C2<T>) * (size_t)(LFAST ? N * L : pitch_for(N, sk) * L); }
+    static HD size_t bytes(int N, int L, int sk) { return sizeof(C2<T>) * (size_t)(LFAST ? (N + (N >> 4)) * L : pitch_for(N, sk) * L); }
 };
 template <class T> HD Tile<T, false> line_tile(unsigned char* smem, int L, const Fft1D<T>& f) {
     Tile<T, false> t; t.s = reinterpret_cast<C2<T>*>(smem); t.L = L; t.pitch = Tile<T, false>::pitch_for(f.N, f.sk); t.sk = f.sk; return t;
