@@ -100,9 +100,16 @@ template <class T> void cg_gradientf(CgT<T>& G, const C2<T>* f, const C2<T>* d, 
     const T* const icn2 = G.Npol == 3 ? G.Mf : nullptr;
     // Ł(f): EB→QU, irfft2 ; Lϕ* in map space
     chain<T>(G, f, none, cnone, false, none, 1, none, none, cnone, w1, st);
-    irfft2<T>(P, w1, m1, C, st);
-    flow_integrate<T>(F, false, m1, 0, 2 * n, st);
-    rfft2<T>(P, m1, w1, C, st);
+    if (const int Gd = flow_rg_direct(F)) {         // the two transforms hand the integrator's row-grouped buffer over directly
+        T* yrg = reinterpret_cast<T*>(F.yrg.reserve(sizeof(T) * P.map_elems() * F.C));
+        irfft2<T>(P, w1, yrg, C, st, nullptr, 1, Gd);
+        flow_integrate<T>(F, false, yrg, 0, 2 * n, st, true);
+        rfft2<T>(P, yrg, w1, C, st, Gd);
+    } else {
+        irfft2<T>(P, w1, m1, C, st);
+        flow_integrate<T>(F, false, m1, 0, 2 * n, st);
+        rfft2<T>(P, m1, w1, C, st);
+    }
     if (G.mask) {
         // B then M = Mf∘Mpix:   QU→EB, ×B, EB→QU (one pass) | irfft2 with ×Mpix on its store | rfft2 | QU→EB ×Mf
         chain<T>(G, w1, none, cnone, false, none, 2, G.B, none, cnone, w2, st, none, 1);

@@ -10,23 +10,24 @@ template <class T> static bool fft_cols_fast_ok(const PlanT<T>& P) {
     if (!fft_fast_enabled() || !fast_len_ok(P.Ny) || !P.ay.ftw1) return false;
     return P.Nx % (fast_tile_bytes(P.Ny) / (int)sizeof(T) / P.Ny) == 0;
 }
-template <class T, class B> static void fft_cols_fast_setup(PlanT<T>& P, B& b, int nC) {
+template <class T> bool fft_rg_io_ok(const PlanT<T>& P) { return fft_cols_fast_ok(P); }
+template <class T, class B> static void fft_cols_fast_setup(PlanT<T>& P, B& b, int nC, int G) {
     b.fc.tw1 = P.ay.ftw1; b.fc.tw2 = P.ay.ftw2;
-    b.fc.Nx = P.Nx; b.fc.G = P.Ny; b.fc.lgGV = ilog2(P.Ny / B::V);             // the reference layout is the row-grouped layout with a single group
+    b.fc.Nx = P.Nx; b.fc.G = G ? G : P.Ny; b.fc.lgGV = ilog2(b.fc.G / B::V);   // the reference layout is the row-grouped layout with a single group
     b.tiles_per_plane = P.Nx / B::M; b.ntiles = nC * b.tiles_per_plane;
     b.nblocks = std::min(b.ntiles, persistent_blocks<B>(B::SMEM));
 }
-template <class T, int LOGN> static void rfft2_cols_fast(PlanT<T>& P, const T* in, C2<T>* out, int nC, cmblStream_t st) {
+template <class T, int LOGN> static void rfft2_cols_fast(PlanT<T>& P, const T* in, C2<T>* out, int nC, cmblStream_t st, int G) {
     typedef FastR2CColBody<T, LOGN> B;
     B b{};
-    fft_cols_fast_setup<T, B>(P, b, nC);
+    fft_cols_fast_setup<T, B>(P, b, nC, G);
     b.Nyh = P.Nyh; b.in = in; b.out = out;
     launch(b, b.nblocks, B::SMEM, st);
 }
-template <class T, int LOGN> static void irfft2_cols_fast(PlanT<T>& P, const C2<T>* in, T* out, int nC, const T* post_diag, int post_planes, cmblStream_t st) {
+template <class T, int LOGN> static void irfft2_cols_fast(PlanT<T>& P, const C2<T>* in, T* out, int nC, const T* post_diag, int post_planes, cmblStream_t st, int G) {
     typedef FastC2RColBody<T, LOGN> B;
     B b{};
-    fft_cols_fast_setup<T, B>(P, b, nC);
+    fft_cols_fast_setup<T, B>(P, b, nC, G);
     b.scale = (T)1 / ((T)P.Ny * (T)P.Nx); b.in = in; b.out = out; b.post_diag = post_diag; b.post_planes = post_planes;
     launch(b, b.nblocks, B::SMEM, st);
 }
@@ -45,8 +46,9 @@ template <class T> static int fft_chunk_planes(const PlanT<T>& P, int C) {
     return n < C ? n : C;
 }
 
-template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmblStream_t st) {
+template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmblStream_t st, int G) {
     if (C <= 0) return;
+    CMBL_REQUIRE(!G || fft_cols_fast_ok(P), "row-grouped map input needs the persistent column kernels");
     const int chunk = fft_chunk_planes(P, C);
     for (int c0 = 0; c0 < C; c0 += chunk) {
         const int nC = (C - c0 < chunk) ? C - c0 : chunk;
@@ -54,10 +56,10 @@ template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmb
         C2<T>* out = four + (size_t)c0 * P.four_elems();
         if (fft_cols_fast_ok(P)) {
             switch (P.Ny) {
-                case 256: rfft2_cols_fast<T, 8>(P, in, out, nC, st); break;
-                case 512: rfft2_cols_fast<T, 9>(P, in, out, nC, st); break;
-                case 1024: rfft2_cols_fast<T, 10>(P, in, out, nC, st); break;
-                default: rfft2_cols_fast<T, 11>(P, in, out, nC, st); break;
+                case 256: rfft2_cols_fast<T, 8>(P, in, out, nC, st, G); break;
+                case 512: rfft2_cols_fast<T, 9>(P, in, out, nC, st, G); break;
+                case 1024: rfft2_cols_fast<T, 10>(P, in, out, nC, st, G); break;
+                default: rfft2_cols_fast<T, 11>(P, in, out, nC, st, G); break;
             }
         } else {
             R2CColBody<T> b;
@@ -76,8 +78,9 @@ template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmb
     }
 }
 
-template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st, const T* post_diag, int post_planes) {
+template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st, const T* post_diag, int post_planes, int G) {
     if (C <= 0) return;
+    CMBL_REQUIRE(!G || (fft_cols_fast_ok(P) && !post_diag), "row-grouped map output needs the persistent column kernels and no Map-basis diagonal");
     const int chunk = fft_chunk_planes(P, C);
     C2<T>* scratch = reinterpret_cast<C2<T>*>(P.scratch_four.reserve(sizeof(C2<T>) * P.four_elems() * (size_t)chunk));   // reused by every group
     for (int c0 = 0; c0 < C; c0 += chunk) {
@@ -93,10 +96,10 @@ template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cm
         if (fft_cols_fast_ok(P)) {
             T* out = map + (size_t)c0 * P.map_elems();
             switch (P.Ny) {
-                case 256: irfft2_cols_fast<T, 8>(P, scratch, out, nC, post_diag, post_planes, st); break;
-                case 512: irfft2_cols_fast<T, 9>(P, scratch, out, nC, post_diag, post_planes, st); break;
-                case 1024: irfft2_cols_fast<T, 10>(P, scratch, out, nC, post_diag, post_planes, st); break;
-                default: irfft2_cols_fast<T, 11>(P, scratch, out, nC, post_diag, post_planes, st); break;
+                case 256: irfft2_cols_fast<T, 8>(P, scratch, out, nC, post_diag, post_planes, st, G); break;
+                case 512: irfft2_cols_fast<T, 9>(P, scratch, out, nC, post_diag, post_planes, st, G); break;
+                case 1024: irfft2_cols_fast<T, 10>(P, scratch, out, nC, post_diag, post_planes, st, G); break;
+                default: irfft2_cols_fast<T, 11>(P, scratch, out, nC, post_diag, post_planes, st, G); break;
             }
         } else {
             C2RColBody<T> b;
@@ -110,9 +113,11 @@ template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cm
     }
 }
 
-template void rfft2<float>(PlanT<float>&, const float*, C2<float>*, int, cmblStream_t);
-template void rfft2<double>(PlanT<double>&, const double*, C2<double>*, int, cmblStream_t);
-template void irfft2<float>(PlanT<float>&, const C2<float>*, float*, int, cmblStream_t, const float*, int);
-template void irfft2<double>(PlanT<double>&, const C2<double>*, double*, int, cmblStream_t, const double*, int);
+template void rfft2<float>(PlanT<float>&, const float*, C2<float>*, int, cmblStream_t, int);
+template void rfft2<double>(PlanT<double>&, const double*, C2<double>*, int, cmblStream_t, int);
+template void irfft2<float>(PlanT<float>&, const C2<float>*, float*, int, cmblStream_t, const float*, int, int);
+template void irfft2<double>(PlanT<double>&, const C2<double>*, double*, int, cmblStream_t, const double*, int, int);
+template bool fft_rg_io_ok<float>(const PlanT<float>&);
+template bool fft_rg_io_ok<double>(const PlanT<double>&);
 
 }  // namespace cmbl

@@ -19,7 +19,8 @@
 #define CMBL_FFT_MINB 2
 #endif
 #ifndef CMBL_FFT_ROW_UNR
-#define CMBL_FFT_ROW_UNR 4          // strided loads of the row pass kept in flight per thread (the tile's runs are L·sizeof(C2) = 64 bytes)
+#define CMBL_FFT_ROW_UNR 16         // strided loads of the row pass kept in flight per thread (the tile's runs are L·sizeof(C2) = 64 bytes):
+                                    // all 16 of a thread instead of 4 — fft2_rows 118 -> 111 us fp64, 81 -> 72 us fp32 (profiles/r02_fft_row_unroll.log)
 #endif
 
 namespace cmbl {
@@ -164,9 +165,13 @@ template <class T> struct C2RColBody {
     }
 };
 
-template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmblStream_t st);
+// G > 0 (both directions): the MAP side is in the row-grouped layout of the fast stage kernels with G rows per group (flow_fast.cuh) instead
+// of the reference layout — the transforms that open and close a flow then hand over the integrator's own buffer and the two layout
+// conversions disappear.  Only where fft_rg_io_ok(P) (the persistent column kernels of fft2d_fast.cuh address either layout).
+template <class T> bool fft_rg_io_ok(const PlanT<T>& P);
+template <class T> void rfft2(PlanT<T>& P, const T* map, C2<T>* four, int C, cmblStream_t st, int G = 0);
 // post_diag: optional REAL Map-basis diagonal (post_planes planes, broadcast over the batch) multiplied into the result — the
 // pixel mask of M = Mfourier·Mpix rides on the transform's store instead of a separate pass over the maps
-template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st, const T* post_diag = nullptr, int post_planes = 1);
+template <class T> void irfft2(PlanT<T>& P, const C2<T>* four, T* map, int C, cmblStream_t st, const T* post_diag = nullptr, int post_planes = 1, int G = 0);
 
 }  // namespace cmbl

@@ -212,7 +212,7 @@ template <class T> void flow_reserve(FlowT<T>& F, cmblStream_t st) {
 // RK4 over stages k0 → k1 for the planes [c0, c0 + nC) of the caller's state `ycaller` (reference layout, F.C planes).
 // Planes of different batch items are independent, so a caller may integrate plane ranges one after another (the pipelined
 // host path below overlaps their transfers with the integration of their neighbours).
-template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* ycaller, int k0, int k1, int c0, int nC, cmblStream_t st) {
+template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* ycaller, int k0, int k1, int c0, int nC, cmblStream_t st, bool rg_state) {
     CMBL_REQUIRE(F.have_p, "LenseFlow used before cmbl_lenseflow_precompute");
     CMBL_REQUIRE(c0 >= 0 && nC >= 1 && c0 + nC <= F.C && c0 % F.Npol == 0 && nC % F.Npol == 0, "plane range must cover whole batch items");
     PlanT<T>& P = *F.P;
@@ -221,8 +221,9 @@ template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* ycaller, 
     const int G = flow_rg_rows(P);
     CMBL_REQUIRE(G == F.pcache_G, "p-cache layout does not match the kernel path");
     flow_reserve(F, st);
+    CMBL_REQUIRE(!rg_state || G, "a row-grouped state needs the fast stage kernels");
     T* y = ycaller;
-    if (G) {                                        // integrate on a row-grouped copy of the state (flow_fast.cuh)
+    if (G && !rg_state) {                           // integrate on a row-grouped copy of the state (flow_fast.cuh)
         y = reinterpret_cast<T*>(F.yrg.p);
         convert_layout<T, true>(P, G, ycaller + (size_t)c0 * nmap, y + (size_t)c0 * nmap, nC, st);
     }
@@ -246,16 +247,21 @@ template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* ycaller, 
         }
         kk += 2 * sgn;
     }
-    if (G) convert_layout<T, false>(P, G, y + (size_t)c0 * nmap, ycaller + (size_t)c0 * nmap, nC, st);
+    if (G && !rg_state) convert_layout<T, false>(P, G, y + (size_t)c0 * nmap, ycaller + (size_t)c0 * nmap, nC, st);
     F.integrated_once = true;
 }
 
-template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st) {
+template <class T> int flow_rg_direct(FlowT<T>& F) {
+    static const bool on = [] { const char* e = getenv("CMBL_RG_DIRECT"); return !e || atoi(e) != 0; }();
+    const int G = flow_rg_rows(*F.P);
+    return (on && G > 0 && fft_rg_io_ok(*F.P)) ? G : 0;
+}
+template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st, bool rg_state) {
     static const int chunk_env = [] { const char* e = getenv("CMBL_FLOW_CHUNK"); return e ? atoi(e) : 0; }();
     int chunk = (chunk_env > 0 && chunk_env < F.C) ? chunk_env : F.C;             // planes integrated together (L2 residency)
     chunk = (chunk + F.Npol - 1) / F.Npol * F.Npol;
     for (int c0 = 0; c0 < F.C; c0 += chunk)
-        flow_integrate_range<T>(F, adj, y, k0, k1, c0, (F.C - c0 < chunk) ? F.C - c0 : chunk, st);
+        flow_integrate_range<T>(F, adj, y, k0, k1, c0, (F.C - c0 < chunk) ? F.C - c0 : chunk, st, rg_state);
 }
 
 template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st) {
@@ -271,16 +277,18 @@ template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* ou
         return;
     }
     // adjoint flows: Fourier state integrated in map space (see flow.cuh)
-    T* y = reinterpret_cast<T*>(F.ybuf.reserve(sizeof(T) * nmap * F.C));
-    flow_adj_prepare<T>(F, reinterpret_cast<const C2<T>*>(in), y, st);
-    if (op == CMBL_OP_LH) flow_integrate<T>(F, true, y, 2 * n, 0, st);
-    else flow_integrate<T>(F, true, y, 0, 2 * n, st);
-    flow_adj_finish<T>(F, y, reinterpret_cast<C2<T>*>(out), st);
+    // the transforms around the flow read / write the integrator's row-grouped buffer directly where they can (no layout conversions)
+    const int Gd = flow_rg_direct(F);
+    T* y = reinterpret_cast<T*>(Gd ? F.yrg.reserve(sizeof(T) * nmap * F.C) : F.ybuf.reserve(sizeof(T) * nmap * F.C));
+    flow_adj_prepare<T>(F, reinterpret_cast<const C2<T>*>(in), y, st, Gd);
+    if (op == CMBL_OP_LH) flow_integrate<T>(F, true, y, 2 * n, 0, st, Gd > 0);
+    else flow_integrate<T>(F, true, y, 0, 2 * n, st, Gd > 0);
+    flow_adj_finish<T>(F, y, reinterpret_cast<C2<T>*>(out), st, Gd);
     (void)nf;
 }
 
 // Fourier state Y0 of an adjoint flow -> its map y = irfft2(Y0), with the ky ∈ {0, Ny/2} rows saved and the Nyquist accumulators cleared
-template <class T> void flow_adj_prepare(FlowT<T>& F, const C2<T>* Y0, T* y, cmblStream_t st) {
+template <class T> void flow_adj_prepare(FlowT<T>& F, const C2<T>* Y0, T* y, cmblStream_t st, int G) {
     PlanT<T>& P = *F.P;
     C2<T>* rows0 = reinterpret_cast<C2<T>*>(F.rows0.reserve(sizeof(C2<T>) * 2 * (size_t)P.Nx * F.C));
     T* nacc = reinterpret_cast<T*>(F.nacc.reserve(sizeof(T) * (size_t)P.Ny * F.C));
@@ -291,12 +299,12 @@ template <class T> void flow_adj_prepare(FlowT<T>& F, const C2<T>* Y0, T* y, cmb
     }
     dev_zero(nacc, sizeof(T) * (size_t)P.Ny * F.C, st);
     dev_zero(macc, sizeof(T) * (size_t)P.Nx * F.C, st);
-    irfft2<T>(P, Y0, y, F.C, st);
+    irfft2<T>(P, Y0, y, F.C, st, nullptr, 1, G);
 }
 // integrated map y -> Fourier result: rfft2(y) plus what a map cannot carry (saved rows, Nyquist accumulators)
-template <class T> void flow_adj_finish(FlowT<T>& F, const T* y, C2<T>* Yout, cmblStream_t st) {
+template <class T> void flow_adj_finish(FlowT<T>& F, const T* y, C2<T>* Yout, cmblStream_t st, int G) {
     PlanT<T>& P = *F.P;
-    rfft2<T>(P, y, Yout, F.C, st);
+    rfft2<T>(P, y, Yout, F.C, st, G);
     AdjFixBody<T> b;
     b.fx = P.ax.fft; b.Ny = P.Ny; b.Nx = P.Nx; b.Nyh = P.Nyh; b.lxN = P.ax.ell_nyq; b.lyN = P.ay.ell_nyq;
     b.rows0 = reinterpret_cast<C2<T>*>(F.rows0.p); b.nacc = reinterpret_cast<T*>(F.nacc.p); b.macc = reinterpret_cast<T*>(F.macc.p); b.out = Yout;
@@ -342,14 +350,15 @@ template <class T> int flow_kernel_path(FlowT<T>& F) { return flow_rg_rows(*F.P)
 
 #define INST(T)                                                                                        \
     template void flow_precompute<T>(FlowT<T>&, const void*, int, bool, cmblStream_t);                 \
-    template void flow_integrate<T>(FlowT<T>&, bool, T*, int, int, cmblStream_t);                      \
-    template void flow_integrate_range<T>(FlowT<T>&, bool, T*, int, int, int, int, cmblStream_t);      \
+    template void flow_integrate<T>(FlowT<T>&, bool, T*, int, int, cmblStream_t, bool);                \
+    template void flow_integrate_range<T>(FlowT<T>&, bool, T*, int, int, int, int, cmblStream_t, bool); \
+    template int flow_rg_direct<T>(FlowT<T>&);                                                         \
     template void flow_apply<T>(FlowT<T>&, int, const void*, void*, cmblStream_t);                     \
     template int flow_kernel_path<T>(FlowT<T>&);                                                       \
     template int flow_rg_rows<T>(const PlanT<T>&);                                                     \
     template void flow_reserve<T>(FlowT<T>&, cmblStream_t);                                            \
-    template void flow_adj_prepare<T>(FlowT<T>&, const C2<T>*, T*, cmblStream_t);                      \
-    template void flow_adj_finish<T>(FlowT<T>&, const T*, C2<T>*, cmblStream_t);                       \
+    template void flow_adj_prepare<T>(FlowT<T>&, const C2<T>*, T*, cmblStream_t, int);                 \
+    template void flow_adj_finish<T>(FlowT<T>&, const T*, C2<T>*, cmblStream_t, int);                  \
     template void convert_layout<T, true>(PlanT<T>&, int, const T*, T*, int, cmblStream_t);            \
     template void convert_layout<T, false>(PlanT<T>&, int, const T*, T*, int, cmblStream_t);           \
     template void flow_stage<T, false>(FlowT<T>&, int, int, const T*, int, T, const T*, const T*, T*, T*, T, T, cmblStream_t, T*, T*);  \

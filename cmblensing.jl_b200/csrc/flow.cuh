@@ -391,11 +391,14 @@ template <class T, bool TO_RG> void convert_layout(PlanT<T>& P, int G, const T* 
 // one RK stage (row kernel + column kernel) on planes [c0, c0+nC); dx_out/dy_out (fast forward kernels only): also export ∂ₓu, ∂ᵧu
 template <class T, bool ADJ> void flow_stage(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, const T* ybase, const T* acc_in, T* acc_out, T* u_out,
                                              T ca, T cb, cmblStream_t st, T* dx_out = nullptr, T* dy_out = nullptr);
-template <class T> void flow_adj_prepare(FlowT<T>& F, const C2<T>* Y0, T* y, cmblStream_t st);
-template <class T> void flow_adj_finish(FlowT<T>& F, const T* y, C2<T>* Yout, cmblStream_t st);
+template <class T> void flow_adj_prepare(FlowT<T>& F, const C2<T>* Y0, T* y, cmblStream_t st, int G = 0);     // G > 0: y in the row-grouped layout (fft2d.cuh)
+template <class T> void flow_adj_finish(FlowT<T>& F, const T* y, C2<T>* Yout, cmblStream_t st, int G = 0);
+// rows per group when the transforms around a flow can hand over the integrator's row-grouped buffer directly (0 = convert layouts)
+template <class T> int flow_rg_direct(FlowT<T>& F);
 // integrate the map-space flow in place on y from stage index k0 to k1 (0 or 2n)
-template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st);
-template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* y, int k0, int k1, int c0, int nC, cmblStream_t st);
+// rg_state: y already is the row-grouped state (all F.C planes) — no layout conversion on entry / exit
+template <class T> void flow_integrate(FlowT<T>& F, bool adj, T* y, int k0, int k1, cmblStream_t st, bool rg_state = false);
+template <class T> void flow_integrate_range(FlowT<T>& F, bool adj, T* y, int k0, int k1, int c0, int nC, cmblStream_t st, bool rg_state = false);
 template <class T> void flow_apply(FlowT<T>& F, int op, const void* in, void* out, cmblStream_t st);
 template <class T> int flow_kernel_path(FlowT<T>& F);
 // smallest positive α per batch item with det(𝕀 + ∇∇(ϕ + α η)) = 0 somewhere (host doubles; +inf if none); synchronises

@@ -224,14 +224,15 @@ template <class T> static void flow_grad_fused(FlowT<T>& F, int op, const T* fou
     flow_reserve(F, st);
     T* f3[3]; T* d3[3];                               // (y, acc, u) of the two legs, row-grouped
     for (int i = 0; i < 3; ++i) { f3[i] = (T*)F.gq_f[i].reserve(sizeof(T) * mC); d3[i] = (T*)F.gq_d[i].reserve(sizeof(T) * mC); }
-    T* ref = (T*)F.gq_ref.reserve(sizeof(T) * mC);                                    // a reference-layout map (C planes) for the conversions
+    const int Gd = flow_rg_direct(F);               // the transforms address the row-grouped buffers directly where they can
+    T* ref = Gd ? nullptr : (T*)F.gq_ref.reserve(sizeof(T) * mC);                     // a reference-layout map (C planes) for the conversions
     T* gx = (T*)F.gq_gx.reserve(sizeof(T) * mC); T* gy = (T*)F.gq_gy.reserve(sizeof(T) * mC);
-    T* A = (T*)F.gq_A.reserve(sizeof(T) * 5 * nmap * Nb); T* Aref = (T*)F.gq_Aref.reserve(sizeof(T) * 5 * nmap * Nb);
+    T* A = (T*)F.gq_A.reserve(sizeof(T) * 5 * nmap * Nb); T* Aref = Gd ? nullptr : (T*)F.gq_Aref.reserve(sizeof(T) * 5 * nmap * Nb);
     C2<T>* spec = (C2<T>*)F.gq_spec.reserve(sizeof(C2<T>) * 5 * nf * Nb);
     // initial state: f leg = the forward result, δf leg = irfft2(Δ) (+ what a map cannot carry, flow.cuh), δϕ integrand accumulators = 0
     convert_layout<T, true>(P, G, fout, f3[0], C, st);
-    flow_adj_prepare<T>(F, delta, ref, st);
-    convert_layout<T, true>(P, G, ref, d3[0], C, st);
+    if (Gd) flow_adj_prepare<T>(F, delta, d3[0], st, Gd);
+    else { flow_adj_prepare<T>(F, delta, ref, st); convert_layout<T, true>(P, G, ref, d3[0], C, st); }
     dev_zero(A, sizeof(T) * 5 * nmap * Nb, st);
     const int k0 = (op == CMBL_OP_L) ? 2 * n : 0, k1 = (op == CMBL_OP_L) ? 0 : 2 * n;
     const int sgn = k1 > k0 ? 1 : -1;
@@ -264,11 +265,11 @@ template <class T> static void flow_grad_fused(FlowT<T>& F, int op, const T* fou
         kk += 2 * sgn;
     }
     // δf: back to the reference layout, rfft2, restore the rows / Nyquist terms a map cannot carry
-    convert_layout<T, false>(P, G, d3[0], ref, C, st);
-    flow_adj_finish<T>(F, ref, dfield, st);
+    if (Gd) flow_adj_finish<T>(F, d3[0], dfield, st, Gd);
+    else { convert_layout<T, false>(P, G, d3[0], ref, C, st); flow_adj_finish<T>(F, ref, dfield, st); }
     // δϕ: the five accumulated maps, transformed once
-    convert_layout<T, false>(P, G, A, Aref, 5 * Nb, st);
-    rfft2<T>(P, Aref, spec, 5 * Nb, st);
+    if (Gd) rfft2<T>(P, A, spec, 5 * Nb, st, Gd);
+    else { convert_layout<T, false>(P, G, A, Aref, 5 * Nb, st); rfft2<T>(P, Aref, spec, 5 * Nb, st); }
     DeltaPhiSpecBody<T> b{P.Nx, P.Nyh, Nb, P.lx, P.ly, spec, dphi};
     launch(b, (int)((nf * (size_t)Nb + b.NT - 1) / b.NT), 0, st);
 }
