@@ -1,4 +1,4 @@
-// Fast path of the two LenseFlow stage kernels (flow.cuh) for transform lengths 256 / 512 / 1024, written for B200:
+// Fast path of the two LenseFlow stage kernels (flow.cuh) for transform lengths 256 / 512 / 1024 / 2048, written for B200:
 //
 //   * persistent blocks (grid = resident blocks of the whole GPU) that walk over tiles blk, blk+G, blk+2G, ...
 //   * every global→shared transfer is asynchronous (cp.async, 16 B per request) into a double-buffered tile, so the
@@ -9,14 +9,16 @@
 //       column kernel: planar tile, plane p = column x0+p, chunk = V consecutive y;  a thread owns V adjacent butterflies
 //       row kernel   : tile [cl][x], chunk = V consecutive rows at one x (= V/2 complex lines); a thread owns one
 //                      butterfly index and keeps its twiddles in registers for the whole launch
-//   * schedule [R1, R2, 16] (same as plan.cu, so the tile-order multiplier tables are shared): forward R1, forward R2,
-//     fused register-resident middle (forward 16 · multiplier · inverse 16), inverse R2, inverse R1.
+//   * schedule [R1, R2, 16] (plan.cu's schedule up to 1024, so the tile-order multiplier tables are shared; [8, 16, 16] with its own
+//     tables at 2048, where tiles are 64 KB and blocks 256 threads): forward R1, forward R2, fused register-resident middle
+//     (forward 16 · multiplier · inverse 16), inverse R2, inverse R1.
 //   * the state of the ODE (y, u, tmp, acc) and the p-cache live in a library-internal ROW-GROUPED layout while the fast
 //     kernels run:  element (x, y) of a plane at  ((y / G)·Nx + x)·G + y % G,  G = rows of one row-kernel tile
 //     (G·sizeof(T) = 32 B at Nx = 1024).  A row tile (all x, G rows) is then ONE contiguous 32 KB run and a column tile
 //     (M columns, all y) is Ny/G runs of M·G·sizeof(T) bytes (128 B fp64 / 256 B fp32) — in the reference's column-major
 //     layout a row tile is 1024 pieces of 32 B at an 8 KB stride, which DRAM serves at < 20 % of its bandwidth
-//     (measured: 1.2 TB/s).  LayoutBody converts caller buffers on entry / exit of flow_integrate.
+//     (measured: 1.2 TB/s).  LayoutBody converts caller buffers on entry / exit of flow_integrate; the transforms that open and close
+//     a flow inside the library (fft2d_fast.cuh) address the row-grouped buffer directly.
 // The arithmetic is the generic kernels' (same butterflies, twiddles and order of operations per element).
 #pragma once
 #include "flow.cuh"

@@ -125,7 +125,7 @@ int cmbl_lenseflow_grad(cmbl_flow* flow, int op, const void* f_out_map, const vo
  * ϕ, η: Nb planes each, Map or Fourier.  Synchronises. */
 int cmbl_max_lensing_step(cmbl_plan* plan, const void* phi, int phi_basis, const void* eta, int eta_basis, int Nb, double* out_host, void* stream);
 /* which stage kernels this flow runs (diagnostic): bit 0 = fast persistent row kernel, bit 1 = fast persistent column kernel
- * (csrc/flow_fast.cuh; transform length 256/512/1024), 0 = generic kernels of csrc/flow.cuh */
+ * (csrc/flow_fast.cuh; transform length 256/512/1024/2048), 0 = generic kernels of csrc/flow.cuh */
 int cmbl_lenseflow_kernel_path(cmbl_flow* flow);
 /* read back one cached p map set for tests: out_host = p[k] as (Ny,Nx,2,Nb_phi) of the plan's dtype */
 int cmbl_lenseflow_get_p(cmbl_flow* flow, int k, void* out_host);
