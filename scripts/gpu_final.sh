@@ -20,6 +20,9 @@ for dt in f64 f32; do
 done
 python scripts/make_profiles.py r02 gpurun_out/profiles_out > gpurun_out/make_profiles.log 2>&1; tail -2 gpurun_out/make_profiles.log
 rm -f gpurun_out/r02_ncu_flow_f32.ncu-rep gpurun_out/r02_ncu_adj_f64.ncu-rep gpurun_out/r02_ncu_fft_f64.ncu-rep      # keep one .ncu-rep (64 MiB limit on what travels back)
+# gradient of logpdf(Mixed) / HMC update at the bench workload, and the standalone transforms
+timeout 600 python scripts/time_map_joint.py f64 1024 P 8 1 2>&1 | tail -5 > gpurun_out/r02_gradient_timing.log; tail -4 gpurun_out/r02_gradient_timing.log | cut -c1-200
+{ for dt in f64 f32; do timeout 300 python scripts/time_fft.py $dt 2>&1 | grep "us"; done; } > gpurun_out/r02_fft_final.log 2>&1
 # compute-sanitizer on the small workload (all kernel families, incl. transform length 2048 and the persistent transform column kernels)
 { echo "compute-sanitizer --tool {memcheck,racecheck,synccheck} python scripts/sanitize_target.py   (256x256 QU + 64x64 IQU generic + 2048x256 I fp64 + 256x2048 QU fp32: all four flow ops, pullback, 3 CG iterations, get_max_lensing_step)"
   echo "libcmbl_b200.so sha256[:16] = $(cat gpurun_out/binary_sha16.txt)"
