@@ -75,7 +75,7 @@ template <class T, int LOGN, bool ADJ>
 static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cmblStream_t st) {
     PlanT<T>& P = *F.P;
     static const bool use_tma = [] { const char* e = getenv("CMBL_ROW_TMA"); return !e || atoi(e) != 0; }();
-    if (use_tma || LOGN > 10) {
+    if (use_tma || fast_row_tile_bytes<T>(1 << LOGN) != 32768) {
         typedef TmaRowBody<T, LOGN, ADJ> B;
         B b;
         b.fx = P.ax.fft; b.mult = P.ax.fmult_deriv;
@@ -87,7 +87,7 @@ static void fast_rows(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, cm
         launch(b, b.nblocks, B::SMEM, st, 1, fast_pdl_hint<T>(b.ntiles));
         return;
     }
-    if constexpr (LOGN <= 10) {
+    if constexpr (fast_row_tile_bytes<T>(1 << LOGN) == 32768) {
     typedef FastRowBody<T, LOGN, ADJ> B;
     B b;
     b.fx = P.ax.fft; b.mult = P.ax.fmult_deriv;
@@ -135,7 +135,7 @@ static void fast_cols(FlowT<T>& F, int c0, int nC, const T* u, int kq, T wgt, co
 }
 template <class T> static bool fast_rows_ok(const PlanT<T>& P) {
     if (!fast_enabled() || !fast_len_ok(P.Nx) || !P.ax.ftw1) return false;
-    const int rows = (fast_tile_bytes(P.Nx) / (P.Nx * 16)) * (16 / (int)sizeof(T));
+    const int rows = (fast_row_tile_bytes<T>(P.Nx) / (P.Nx * 16)) * (16 / (int)sizeof(T));
     return P.Ny % rows == 0;
 }
 template <class T> static bool fast_cols_ok(const PlanT<T>& P) {
@@ -147,7 +147,7 @@ template <class T> static bool fast_cols_ok(const PlanT<T>& P) {
 // rows per group of the row-grouped internal layout (flow_fast.cuh), 0 = the generic kernels on the reference layout
 template <class T> int flow_rg_rows(const PlanT<T>& P) {
     if (!fast_rows_ok(P) || !fast_cols_ok(P) || P.Ny % 64 != 0 || P.Nx % 32 != 0) return 0;
-    return (fast_tile_bytes(P.Nx) / (P.Nx * 16)) * (16 / (int)sizeof(T));
+    return (fast_row_tile_bytes<T>(P.Nx) / (P.Nx * 16)) * (16 / (int)sizeof(T));
 }
 template <class T, bool TO_RG> void convert_layout(PlanT<T>& P, int G, const T* in, T* out, int C, cmblStream_t st) {
     typedef LayoutBody<T, TO_RG> B;

@@ -240,6 +240,15 @@ inline bool fast_len_ok(int N) { return N == 256 || N == 512 || N == 1024 || N =
 // keeps the runs at 128 B fp64 / 256 B fp32 and the bigger block keeps one butterfly task per thread and sweep)
 constexpr int fast_tile_bytes(int N) { return N > 1024 ? 65536 : 32768; }
 constexpr int fast_threads(int N) { return N > 1024 ? 256 : 128; }
+// The ROW kernel's tile also fixes G, the rows per group of the row-grouped layout, and with it the run length of every access of the
+// column kernel: M·G·sizeof(T) bytes.  At Nx = 1024 in fp64 a 32 KB row tile gives G = 4 and 128-byte runs — the one shape where the column
+// kernel's DRAM streams are that short (fp32: 256 B; Nx = 512: 512 B) — so CMBL_ROW_TILE_KB_1024_F64 = 64 trades a row kernel at one
+// 256-thread block per SM (the 2048 shape) for 256-byte runs in the column kernel.
+#ifndef CMBL_ROW_TILE_KB_1024_F64
+#define CMBL_ROW_TILE_KB_1024_F64 32
+#endif
+template <class T> constexpr int fast_row_tile_bytes(int N) { return (N == 1024 && sizeof(T) == 8) ? CMBL_ROW_TILE_KB_1024_F64 * 1024 : fast_tile_bytes(N); }
+template <class T> constexpr int fast_row_threads(int N) { return fast_row_tile_bytes<T>(N) > 32768 ? 256 : 128; }
 
 HD int swz8(int ch) { return ch ^ ((ch >> 3) & 7); }        // column kernel: chunk index within a plane
 HD int swzx(int x) { return x ^ ((x >> 4) & 7); }           // row kernel: x index within a chunk-row
@@ -296,6 +305,9 @@ template <class T, bool TO_RG> struct LayoutBody {
 #endif
 #ifndef CMBL_COL_UNR
 #define CMBL_COL_UNR 2
+#endif
+#ifndef CMBL_COL_ABLATE
+#define CMBL_COL_ABLATE 0        // experiments only (wrong results): 1 = no sweeps (landing + epilogue), 2 = no epilogue (landing + sweeps)
 #endif
 #ifndef CMBL_COL_UNR_ADJ
 #define CMBL_COL_UNR_ADJ (sizeof(T) == 8 ? 4 : CMBL_COL_UNR)   // adjoint kernel (3 operands per unit, 2 blocks/SM): 4 units in flight in fp64
@@ -658,6 +670,7 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
             }
         }
         jn_publish(blk, ntiles / tiles_per_plane, sbase + TILE, w1, w2);          // (publisher blocks only) first tile in flight
+        stagger_start(blk, sms, stagger_ns);                                       // (experiment knob, default 0) de-phase the blocks of an SM
         CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_END(load_tw1(w1, tid)); }
         for (; tile < ntiles; tile += nblocks, cur ^= 1) {
             T* const buf = sbase + cur * TILE;
@@ -671,20 +684,20 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
             if (next < ntiles) {                                       // the next tile lands while this one is transformed (DRAM is idle then)
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(u + (size_t)cn * nmap, x0n, nbuf, tid); cp_async_commit(); }
             }
-            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
+            CMBL_FOR_THREADS(tid, NT) { CMBL_PRE_START(load_tw1(w1, tid)); if (CMBL_COL_ABLATE != 1) pass1<false>(buf, ADJ ? pbuf : nullptr, tid, w1); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
             if (ADJ && next < ntiles) {
                 CMBL_FOR_THREADS(tid, NT) { issue_tile(p_plane(pk, cn, Npol, Nbphi, 1, nmap), x0n, pbuf, tid); cp_async_commit(); }
             }
-            CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<false>(buf, tid, w2); }
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 1) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); if (CMBL_COL_ABLATE != 1) pass2<false>(buf, tid, w2); }
             CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) { if (pf == 2) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); middle(buf, tid, ADJ ? macc + (size_t)c * Nx : nullptr, x0, mult_d); CMBL_PRE_END(load_tw2(w2, tid)); }
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 2) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); if (CMBL_COL_ABLATE != 1) middle(buf, tid, ADJ ? macc + (size_t)c * Nx : nullptr, x0, mult_d); CMBL_PRE_END(load_tw2(w2, tid)); }
             CMBL_SYNC();
-            CMBL_FOR_THREADS(tid, NT) { if (pf == 3) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
+            CMBL_FOR_THREADS(tid, NT) { if (pf == 3) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw2(w2, tid)); if (CMBL_COL_ABLATE != 1) pass2<true>(buf, tid, w2); CMBL_PRE_END(load_tw1(w1, tid)); }
             CMBL_SYNC();
             int fl = 1;
             CMBL_FOR_THREADS(tid, NT) {
-                if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); pass1<true>(buf, pbuf, tid, w1);
+                if (pf == 4) prefetch_epilogue(tid, (size_t)c * nmap, x0, p1, p2); CMBL_PRE_START(load_tw1(w1, tid)); if (CMBL_COL_ABLATE != 1) pass1<true>(buf, pbuf, tid, w1);
                 if (tid == 0 && c != cj) fl = flag_look_patient(jn_flag + c, epoch, jn_polls);   // is this plane's J[N] line published?  (the answer rides on the barrier)
             }
             fl = block_and(fl);
@@ -696,7 +709,8 @@ template <class T, int LOGN, bool ADJ, bool DMODE = false> struct FastColBody {
             // start their epilogues together.  A cluster barrier cannot deadlock: the hardware co-schedules the blocks of a cluster.
             if (csync) cluster_sync();
             CMBL_FOR_THREADS(tid, NT) {
-                if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
+                if (CMBL_COL_ABLATE == 2) { }
+                else if (kind == 0) epilogue<0>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
                 else if (kind == 1) epilogue<1>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
                 else epilogue<2>(buf, tid, (size_t)c * nmap, x0, jline, p1, p2);
                 CMBL_PRE_END(load_tw1(w1, tid));                      // twiddles of the next tile's first sweep
@@ -1015,8 +1029,8 @@ DEV void fence_proxy_async() {                  // make this thread's shared-mem
 // ---------------------------------------------------------------------------------------------------------------
 template <class T, int LOGN, bool ADJ> struct TmaRowBody {
     static constexpr int N = 1 << LOGN, V = 16 / (int)sizeof(T), H = V / 2;
-    static constexpr int FAST_TILE_BYTES = fast_tile_bytes(N), NT = fast_threads(N);
-    static constexpr int MINB = (N > 1024) ? 1 : ADJ ? 2 : (sizeof(T) == 8 ? CMBL_ROW_F64_MINB : 3);
+    static constexpr int FAST_TILE_BYTES = fast_row_tile_bytes<T>(N), NT = fast_row_threads<T>(N);
+    static constexpr int MINB = (FAST_TILE_BYTES > 32768) ? 1 : ADJ ? 2 : (sizeof(T) == 8 ? CMBL_ROW_F64_MINB : 3);
     static constexpr int R1 = FastSched<LOGN>::R1, R2 = FastSched<LOGN>::R2;
     static constexpr int S1 = N / R1, N2 = N / R1, NB2 = N / R2, NBM = N / 16;
     static constexpr int CPX = FAST_TILE_BYTES / (N * 16);
