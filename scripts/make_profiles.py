@@ -11,7 +11,7 @@ os.makedirs(P, exist_ok=True)
 CMD = {"flow_f64": "ncu --set full --clock-control none --import-source on -s 38 -c 2  python scripts/ncu_target.py f64 fwd   (Nside=1024 QU batch 8; one flow_rows + one flow_cols launch of the first RK step)",
        "flow_f32": "ncu --set full --clock-control none --import-source on -s 38 -c 2  python scripts/ncu_target.py f32 fwd",
        "adj_f64": "ncu --set full --clock-control none --import-source on -s 12 -c 2  python scripts/ncu_target.py f64 adj   (adjoint stage kernels)",
-       "fft_f64": "ncu --set full --clock-control none --import-source on -s 2 -c 3  python scripts/ncu_target.py f64 adj   (general 2-D transform kernels of the irfft2 that opens L'*f)"}
+       "fft_f64": "ncu --set full --clock-control none --import-source on -s 2 -c 3  python scripts/ncu_target.py f64 adj   (general 2-D transform kernels of the rfft2 inside precompute: persistent column kernel + row pass)"}
 sha = open(os.path.join(G, "binary_sha16.txt")).read().strip() if os.path.exists(os.path.join(G, "binary_sha16.txt")) else None
 traffic = {"binary_sha16": sha, "source": f"profiles/{tag}_ncu_flow_{{f64,f32}}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
 for key, cmd in CMD.items():
