@@ -119,6 +119,16 @@ class ClockSampler:
                 "source": "NVML poll (5 ms) inside the timed region"}
 
 
+def csrc_sha16():
+    """sha256[:16] over the kernel sources the library is built from (sorted csrc/*.cu, *.cuh and the Makefile)."""
+    import glob, hashlib
+    d = os.path.join(ROOT, "cmblensing.jl_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + [os.path.join(d, "Makefile")]):
+        h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def numa_interleave():
     """Spread this process's future page allocations (the pinned host buffers of the e2e leg) over all NUMA nodes: at 8 ranks the host side
     of the e2e path moves ~300 GB/s, more than one socket's DRAM delivers.  set_mempolicy(MPOL_INTERLEAVE); returns the node count or None."""
@@ -459,16 +469,19 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes,
                 "kernels": {k: {"launches_per_step": v[0] // 2, "avg_ms": v[1] / v[0], "share": v[1] / tot_prof,
                                 "algorithmic_GBs": (kbytes[k] / (v[1] / v[0]) / 1e6 if k in kbytes else None)} for k, v in prof.items()}}
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture — reported only when that capture
-    # was taken from the very binary that is loaded now (sha256 of libcmbl_b200.so recorded next to the numbers), else null
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture — reported only when that capture was taken from the
+    # code that is loaded now: the same library file (sha256 of libcmbl_b200.so) or, because nvcc builds are not bit-reproducible, a library
+    # built from the same kernel sources (sha256 over csrc/*.cu, *.cuh, Makefile recorded next to the numbers); else null
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             import hashlib
             tj = json.load(open(traffic_file))
             sha = hashlib.sha256(open(lib.path, "rb").read()).hexdigest()[:16]
-            roofline["traffic_capture"] = {"binary_sha16": tj.get("binary_sha16"), "loaded_sha16": sha, "source": tj.get("source")}
-            if tj.get("binary_sha16") == sha:
+            src = csrc_sha16()
+            roofline["traffic_capture"] = {"binary_sha16": tj.get("binary_sha16"), "loaded_sha16": sha, "source_sha16": tj.get("source_sha16"),
+                                           "tree_source_sha16": src, "source": tj.get("source")}
+            if tj.get("binary_sha16") == sha or (tj.get("source_sha16") and tj.get("source_sha16") == src):
                 roofline["traffic"] = tj.get(args.dtype, {}).get(dom)
         except Exception:
             pass

@@ -13,7 +13,13 @@ CMD = {"flow_f64": "ncu --set full --clock-control none --import-source on -s 38
        "adj_f64": "ncu --set full --clock-control none --import-source on -s 12 -c 2  python scripts/ncu_target.py f64 adj   (adjoint stage kernels)",
        "fft_f64": "ncu --set full --clock-control none --import-source on -s 2 -c 3  python scripts/ncu_target.py f64 adj   (general 2-D transform kernels of the rfft2 inside precompute: persistent column kernel + row pass)"}
 sha = open(os.path.join(G, "binary_sha16.txt")).read().strip() if os.path.exists(os.path.join(G, "binary_sha16.txt")) else None
-traffic = {"binary_sha16": sha, "source": f"profiles/{tag}_ncu_flow_{{f64,f32}}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
+def csrc_sha16():          # same definition as bench.py
+    import glob, hashlib
+    d = os.path.join(ROOT, "cmblensing.jl_b200", "csrc"); h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + [os.path.join(d, "Makefile")]):
+        h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+traffic = {"binary_sha16": sha, "source_sha16": csrc_sha16(), "source": f"profiles/{tag}_ncu_flow_{{f64,f32}}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
 for key, cmd in CMD.items():
     rep = os.path.join(G, f"{tag}_ncu_{key}.ncu-rep")
     if not os.path.exists(rep):
