@@ -519,6 +519,22 @@ def main():
                  "apply_frac_of_measured_peak": AB2["apply"] / ms2 / 1e6 / peak}
         del c2, out2, f2, ϕ2
 
+    # ---- the batched 2-D transforms on their own (m_rfft! / m_irfft!, src/util_fft.jl:26-27): 16 planes of the headline shape ------------
+    fft_line = None
+    if rank == 0 and world == 1 and "other" not in skip:
+        C16 = NPOL * NB
+        fm16 = fmap.arr.reshape(C16, NSIDE, NSIDE)
+        F16 = torch.empty((C16, NSIDE, NSIDE // 2 + 1), dtype=proj.cT, device=dev); back16 = torch.empty_like(fm16)
+        ms_r, _ = timed(lambda: lib.call("cmbl_rfft2", proj.handle, P(fm16), P(F16), C16, st), 20, 3)
+        ms_i, _ = timed(lambda: lib.call("cmbl_irfft2", proj.handle, P(F16), P(back16), C16, st), 20, 3)
+        plane, half = NSIDE * NSIDE * s, NSIDE * (NSIDE // 2 + 1) * 2 * s
+        per = C16 * (plane + 3 * half)                                  # column pass: plane <-> half-spectrum; row pass: half-spectrum in and out
+        fft_line = {"workload": f"cmbl_rfft2 / cmbl_irfft2, {C16} planes of {NSIDE}x{NSIDE}, {args.dtype}", "rfft2_us": ms_r * 1e3, "irfft2_us": ms_i * 1e3,
+                    "algorithmic_bytes_two_passes": per, "rfft2_GBs": per / ms_r / 1e6, "irfft2_GBs": per / ms_i / 1e6,
+                    "rfft2_frac_of_measured_peak": per / ms_r / 1e6 / peak, "irfft2_frac_of_measured_peak": per / ms_i / 1e6 / peak,
+                    "round_trip_max_abs_err": float((back16 - fm16).abs().max())}
+        del F16, back16
+
     # free the headline workload before the other configs
     del cache, L, ds, noise, hin, hout
     torch.cuda.empty_cache()
@@ -593,6 +609,7 @@ def main():
                                "algorithmic_bytes_per_apply": AB["apply"]},
             "cpu_baseline": cpu,
             "other_precision": other,
+            "fft": fft_line,
             "cg": cg_line,
             "map_joint": mj_line,
             "hmc": hmc_line,

@@ -58,3 +58,5 @@ def test_b200_arm_line():
     mj, hm = d["map_joint"], d["hmc"]
     assert mj["value"] > 0 and mj["higher_is_better"] is False and 0.05 < min(mj["alpha"]) and mj["corr_phi_map_vs_truth_rank0"] > 0.2
     assert hm["value"] > 0 and hm["abs_dH_max_rank0"] < 50
+    ff = d["fft"]
+    assert ff["rfft2_us"] > 0 and ff["irfft2_us"] > 0 and ff["round_trip_max_abs_err"] < 1e-10 and 0.05 < ff["rfft2_frac_of_measured_peak"] < 1.2
