@@ -64,3 +64,53 @@ def test_kernel_family_knobs_agree(backend, request):
             assert abs(base[k][1] - other[k][1]) <= tol * abs(base[k][1]), (env, k, base[k][1], other[k][1])
             if keys is not None and k.split(":")[1] not in keys:
                 assert base[k][0] == other[k][0], (env, k)
+
+
+CODE_2048 = r'''
+import json, os, sys
+import numpy as np, torch
+ROOT = sys.argv[1]
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g
+pkg = g.load_package()
+dev, N = "cuda:0", 2048
+out = {}
+for dt, tT in (("f64", torch.float64), ("f32", torch.float32)):
+    proj = pkg.ProjLambert(N, N, 2.0, tT, dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    k = torch.fft.fftfreq(N, device=dev, dtype=torch.float64)
+    kk = torch.sqrt(k[:, None] ** 2 + k[None, :] ** 2) + 1e-3
+    phi = torch.fft.ifft2(torch.fft.fft2(torch.randn((1, 1, N, N), generator=gen, device=dev, dtype=torch.float64)) / kk ** 3).real
+    phi = (phi / phi.std() * 1e-5).to(tT)                                  # arcminute-scale deflections, red spectrum (curvature from the large scales: weak lensing)
+    f = pkg.Field("IQUMap", torch.randn((1, 3, N, N), generator=gen, device=dev, dtype=tT), proj)
+    L = pkg.LenseFlow(pkg.Field("Map", phi, proj), 3)
+    F = pkg.convert(f, "IQUFourier")
+    res = {"L": (L * f).arr, "Linv": L.ldiv(f).arr, "LH": (L.H * F).arr}
+    probe = torch.Generator(device=dev).manual_seed(11)
+    for kname, v in res.items():
+        a = torch.view_as_real(v) if v.is_complex() else v
+        w = torch.randn(a.shape, generator=probe, device=dev, dtype=torch.float64)
+        out[dt + ":" + kname] = [float((a.double() * w).sum()), float(a.double().norm())]      # a random projection and the norm
+    out[dt + ":path"] = pkg.load().cdll.cmbl_lenseflow_kernel_path(L.cache(f).handle)
+print(json.dumps(out))
+'''
+
+
+@pytest.mark.gpu
+def test_fast_stage_kernels_at_2048_match_generic_full_size(request):
+    """Nside=2048 IQU (BASELINE config 4's shape): the fast stage kernels (64 KB tiles, 256 threads, [8,16,16]) against the generic kernels on the
+    reference layout, whole maps, through a random projection and the norm of every result."""
+    request.getfixturevalue("cuda_pkg")
+    def run(env):
+        e = dict(os.environ); e.update(env)
+        r = subprocess.run([sys.executable, "-c", CODE_2048, ROOT], capture_output=True, text=True, timeout=900, env=e)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    fast, gen = run({}), run({"CMBL_FLOW_FAST": "0"})
+    assert fast["f64:path"] == 3 and gen["f64:path"] == 0
+    for k in fast:
+        if k.endswith(":path"):
+            continue
+        tol = 1e-11 if k.startswith("f64") else 5e-5
+        (pf, nf), (pg, ng) = fast[k], gen[k]
+        assert abs(nf - ng) <= tol * ng and abs(pf - pg) <= tol * ng * 10, (k, fast[k], gen[k])     # |projection| ~ norm: compare on that scale
